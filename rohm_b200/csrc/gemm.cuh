@@ -1,0 +1,80 @@
+// Segmented-A GEMM on tcgen05 tensor cores with error-compensated TF32 ("3xTF32") for fp32-grade results.
+//
+//   C[m, n] = epilogue( sum_s sum_k A_s[m * row_mul_s + row_shift_s, k] * W[n, koff_s + k] )
+//
+// * A is a list of up to kMaxSegs "segments": each is a row-major fp32 matrix (given as a hi/lo TF32 split
+//   pair) read through its own TMA descriptor with a row shift.  One segment = a plain linear layer
+//   (PoseNet, reference model/posenet.py:59-72).  Several segments = the taps of a Conv1d / the halves of a
+//   channel concat (TrajNet, reference model/heads.py:90-106, model/trajnet.py:222-271): a k-tap convolution
+//   over channels-last activations is k shifted copies of the same matrix, so no im2col buffer ever exists.
+//   Out-of-range rows/columns are zero-filled by TMA, which is exactly Conv1d's zero padding.
+// * W is [N, K_total] K-major (torch Linear layout), also a hi/lo pair.
+// * PASSES == 3: D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (drops only the lo*lo term, ~2^-22 relative).
+//   PASSES == 1: D += A_hi*W_hi (plain TF32, ~2^-11 relative) -- the documented fast mode.
+//
+// Kernel shape: one 128 x BLOCK_N output tile per CTA, 192 threads:
+//   warp 0   : TMA producer (one elected lane)        smem ring: full[]/empty[] mbarriers
+//   warp 1   : TMEM allocator + tcgen05.mma issuer    accumulator: BLOCK_N fp32 columns x 128 lanes in TMEM
+//   warps 2-5: epilogue (tcgen05.ld -> bias/act/residual -> global, optional hi/lo split for the next GEMM)
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace rohm {
+
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 32;  // fp32 elements: 128 bytes = one SWIZZLE_128B span
+constexpr int kMaxSegs = 10;
+
+enum GemmAct : int { kActNone = 0, kActGelu = 1, kActSilu = 2, kActMish = 3 };
+
+struct alignas(64) GemmParams {
+  CUtensorMap a_hi[kMaxSegs];
+  CUtensorMap a_lo[kMaxSegs];
+  CUtensorMap b_hi;
+  CUtensorMap b_lo;
+  int seg_kblocks[kMaxSegs];    // number of 32-wide K blocks of this segment
+  int seg_row_shift[kMaxSegs];  // A row coordinate = m0 * seg_row_mul + seg_row_shift
+  int seg_row_mul[kMaxSegs];
+  int num_segs;
+  // ---- epilogue ----
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // fp32 [*, ldr] added after the activation, or nullptr
+  int ldr;
+  float* out;  // fp32 [*, ldo] or nullptr
+  int ldo;
+  float* out_hi;  // TF32 split of the result for a following GEMM, or nullptr
+  float* out_lo;
+  int lds;
+  int act;
+  int M;  // rows to store (rows >= M are never written)
+  int N;  // columns to store
+  int out_row_mul;  // output row = m * out_row_mul + out_row_add (transposed-conv phase interleave)
+  int out_row_add;
+  // Padded-clip layouts (TrajNet): rows are grouped in clips of clip_rows rows of which the first clip_valid
+  // are real frames; the others are written as zeros so that they act as conv padding for the next layer.
+  int clip_rows;  // 0 = disabled
+  int clip_valid;
+  // GroupNorm statistics (TrajNet): per (clip, group) sum and sum of squares of the stored fp32 values.
+  double* gn_stats;  // [num_clips, gn_groups, 2] or nullptr
+  int gn_groups;
+  int gn_group_size;  // channels per group
+};
+
+// Host side ------------------------------------------------------------------------------------
+// Fills a 2-D fp32 tensor map: inner dim `cols` (contiguous), outer dim `rows`, row pitch `ld` elements,
+// box = {32, box_rows}, SWIZZLE_128B, zero OOB fill, optional row traversal stride.
+// Returns 0 on success, a CUresult otherwise.
+int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                 int row_elem_stride = 1);
+
+// Launches the tile kernel.  block_n in {32, 64, 96, 128}; passes in {1, 3}.
+// grid = ceil(M_tiles) x ceil(N_tiles) where M_tiles covers `m_rows` GEMM rows.
+cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n, int passes, cudaStream_t stream,
+                        bool pdl = false);
+
+// fp32 -> (hi, lo) TF32 split, elementwise; n elements.
+cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
+
+}  // namespace rohm

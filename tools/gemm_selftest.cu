@@ -1,0 +1,281 @@
+// Standalone numerics + timing check of the tcgen05 3xTF32 GEMM (rohm_b200/csrc/gemm.cu) against a CPU fp64
+// reference.  Build:  make -C tools   Run on a B200:  tools/gemm_selftest
+// Cases: plain linear layers (PoseNet shapes), ragged K/N tails, multi-segment shifted reads (Conv1d k=5 over a
+// padded-clip layout), stride-2 reads (Downsample1d), GroupNorm statistics, hi/lo split outputs.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "../rohm_b200/csrc/gemm.cuh"
+
+using namespace rohm;
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      printf("CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, #x);     \
+      exit(2);                                                                                  \
+    }                                                                                           \
+  } while (0)
+
+static std::mt19937 rng(1234);
+static void fill(std::vector<float>& v, float scale = 1.0f) {
+  std::normal_distribution<float> d(0.0f, scale);
+  for (auto& x : v) x = d(rng);
+}
+template <class T>
+static T* dev(const std::vector<T>& h) {
+  T* d;
+  CK(cudaMalloc(&d, h.size() * sizeof(T)));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static float* dev_zero(size_t n) {
+  float* d;
+  CK(cudaMalloc(&d, n * sizeof(float)));
+  CK(cudaMemset(d, 0, n * sizeof(float)));
+  return d;
+}
+static std::vector<float> host(const float* d, size_t n) {
+  std::vector<float> h(n);
+  CK(cudaMemcpy(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return h;
+}
+struct Split {
+  float *hi, *lo;
+};
+static Split split(const float* d, size_t n) {
+  Split s;
+  s.hi = dev_zero(n);
+  s.lo = dev_zero(n);
+  CK(launch_split_tf32(d, s.hi, s.lo, (int64_t)n, 0));
+  return s;
+}
+
+static int failures = 0;
+static void report(const char* name, double maxerr, double maxref, double tol) {
+  const bool ok = maxerr <= tol && std::isfinite(maxerr);
+  printf("%-44s max_abs_err %.3e (max |ref| %.3e) tol %.1e  %s\n", name, maxerr, maxref, tol, ok ? "OK" : "FAIL");
+  if (!ok) ++failures;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Case 1: plain linear  C = act(A W^T + b) + R
+// ------------------------------------------------------------------------------------------------
+static void case_linear(int M, int N, int K, int block_n, int act, bool with_res, bool timing) {
+  const int ldk = (K + 3) / 4 * 4;            // 16-byte row pitch
+  const int Kp = (K + 31) / 32 * 32;          // weights are stored K-padded to the 32-wide k-block
+  const int Np = (N + block_n - 1) / block_n * block_n;
+  std::vector<float> A((size_t)M * ldk, 0.f), W((size_t)Np * Kp, 0.f), b(N), R((size_t)M * N);
+  {
+    std::normal_distribution<float> d(0.f, 1.f);
+    for (int m = 0; m < M; ++m)
+      for (int k = 0; k < K; ++k) A[(size_t)m * ldk + k] = d(rng);
+    const float ws = 1.0f / std::sqrt((float)K);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) W[(size_t)n * Kp + k] = d(rng) * ws;
+  }
+  fill(b);
+  fill(R);
+  float *dA = dev(A), *dW = dev(W), *db = dev(b), *dR = dev(R);
+  Split sA = split(dA, A.size()), sW = split(dW, W.size());
+  float* dC = dev_zero((size_t)M * N);
+  float* dCh = dev_zero((size_t)M * N);
+  float* dCl = dev_zero((size_t)M * N);
+
+  for (int passes : {3, 1}) {
+    GemmParams p{};
+    if (make_tmap_2d(&p.a_hi[0], sA.hi, M, K, ldk, kGemmBlockM) || make_tmap_2d(&p.a_lo[0], sA.lo, M, K, ldk, kGemmBlockM) ||
+        make_tmap_2d(&p.b_hi, sW.hi, Np, Kp, Kp, block_n) || make_tmap_2d(&p.b_lo, sW.lo, Np, Kp, Kp, block_n)) {
+      printf("tensor map encode failed\n");
+      exit(2);
+    }
+    p.num_segs = 1;
+    p.seg_kblocks[0] = Kp / 32;
+    p.seg_row_shift[0] = 0;
+    p.seg_row_mul[0] = 1;
+    p.bias = db;
+    p.residual = with_res ? dR : nullptr;
+    p.ldr = N;
+    p.out = dC, p.ldo = N;
+    p.out_hi = dCh, p.out_lo = dCl, p.lds = N;
+    p.act = act;
+    p.M = M, p.N = N;
+    p.out_row_mul = 1, p.out_row_add = 0;
+    CK(cudaMemset(dC, 0, (size_t)M * N * 4));
+    CK(launch_gemm(p, M, N, block_n, passes, 0));
+    CK(cudaDeviceSynchronize());
+    auto C = host(dC, (size_t)M * N);
+    auto Ch = host(dCh, (size_t)M * N);
+    auto Cl = host(dCl, (size_t)M * N);
+    double maxerr = 0, maxref = 0, maxsplit = 0;
+    // check a subset of rows to keep the CPU side quick
+    const int step = M > 600 ? 7 : 1;
+    for (int m = 0; m < M; m += step)
+      for (int n = 0; n < N; ++n) {
+        double acc = 0;
+        for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * ldk + k] * (double)W[(size_t)n * Kp + k];
+        acc += b[n];
+        if (act == kActGelu) acc = 0.5 * acc * (1.0 + std::erf(acc / std::sqrt(2.0)));
+        if (act == kActSilu) acc = acc / (1.0 + std::exp(-acc));
+        if (act == kActMish) acc = acc * std::tanh(std::log1p(std::exp(acc)));
+        if (with_res) acc += R[(size_t)m * N + n];
+        const double got = C[(size_t)m * N + n];
+        maxerr = std::fmax(maxerr, std::fabs(got - acc));
+        maxref = std::fmax(maxref, std::fabs(acc));
+        maxsplit = std::fmax(maxsplit, std::fabs((double)Ch[(size_t)m * N + n] + (double)Cl[(size_t)m * N + n] - got));
+      }
+    char name[128];
+    snprintf(name, sizeof name, "linear M%d N%d K%d bn%d act%d passes%d", M, N, K, block_n, act, passes);
+    report(name, maxerr, maxref, passes == 3 ? 2e-5 : 2e-2);
+    snprintf(name, sizeof name, "  hi+lo == out (split epilogue)");
+    report(name, maxsplit, maxref, 1e-5);
+
+    if (timing) {
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      for (int i = 0; i < 5; ++i) CK(launch_gemm(p, M, N, block_n, passes, 0));
+      CK(cudaEventRecord(e0));
+      const int iters = 50;
+      for (int i = 0; i < iters; ++i) CK(launch_gemm(p, M, N, block_n, passes, 0));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double us = ms * 1000.0 / iters;
+      const double flops = 2.0 * M * N * K;
+      printf("    timing: %.2f us/launch  -> %.1f TFLOP/s algorithmic (x%d tensor passes)\n", us, flops / us * 1e-6, passes);
+    }
+  }
+  cudaFree(dA), cudaFree(dW), cudaFree(db), cudaFree(dR), cudaFree(dC), cudaFree(dCh), cudaFree(dCl);
+  cudaFree(sA.hi), cudaFree(sA.lo), cudaFree(sW.hi), cudaFree(sW.lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Case 2: Conv1d over a padded-clip channels-last layout, as TrajNet uses it.
+//   x: [B, Tp_in, Cin] with the first T_in rows of each clip real, others zero.
+//   y[b, t, co] = bias[co] + sum_{j<ks} sum_ci W[co, ci, j] * x[b, t*stride + j - pad, ci]
+//   Weight matrix for the GEMM: [Cout, ks * Cin_p] with tap-major K (Cin padded to 32).
+// ------------------------------------------------------------------------------------------------
+static void case_conv(int B, int T_in, int Tp_in, int Cin, int Cout, int ks, int stride, int pad, int block_n, int groups) {
+  const int T_out = (T_in + 2 * pad - ks) / stride + 1;
+  const int Tp_out = Tp_in / stride;
+  const int Cin_p = (Cin + 31) / 32 * 32;
+  const int ldx = (Cin + 3) / 4 * 4;
+  const int Np = (Cout + block_n - 1) / block_n * block_n;
+  const int Kt = ks * Cin_p;
+  std::vector<float> x((size_t)B * Tp_in * ldx, 0.f), W((size_t)Np * Kt, 0.f), Wt((size_t)Cout * Cin * ks), bias(Cout);
+  std::normal_distribution<float> d(0.f, 1.f);
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < T_in; ++t)
+      for (int c = 0; c < Cin; ++c) x[((size_t)b * Tp_in + t) * ldx + c] = d(rng);
+  const float ws = 1.0f / std::sqrt((float)(Cin * ks));
+  for (auto& w : Wt) w = d(rng) * ws;
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int j = 0; j < ks; ++j) W[(size_t)co * Kt + j * Cin_p + ci] = Wt[((size_t)co * Cin + ci) * ks + j];
+  fill(bias);
+  float *dx = dev(x), *dW = dev(W), *db = dev(bias);
+  Split sx = split(dx, x.size()), sW = split(dW, W.size());
+  const int Mrows = B * Tp_out;
+  float* dy = dev_zero((size_t)Mrows * Cout);
+  double* dstats;
+  CK(cudaMalloc(&dstats, sizeof(double) * B * groups * 2));
+  CK(cudaMemset(dstats, 0, sizeof(double) * B * groups * 2));
+
+  GemmParams p{};
+  for (int j = 0; j < ks; ++j) {
+    if (make_tmap_2d(&p.a_hi[j], sx.hi, (int64_t)B * Tp_in, Cin, ldx, kGemmBlockM, stride) ||
+        make_tmap_2d(&p.a_lo[j], sx.lo, (int64_t)B * Tp_in, Cin, ldx, kGemmBlockM, stride)) {
+      printf("tensor map encode failed (conv A)\n");
+      exit(2);
+    }
+    p.seg_kblocks[j] = Cin_p / 32;
+    p.seg_row_shift[j] = j - pad;
+    p.seg_row_mul[j] = stride;
+  }
+  if (make_tmap_2d(&p.b_hi, sW.hi, Np, Kt, Kt, block_n) || make_tmap_2d(&p.b_lo, sW.lo, Np, Kt, Kt, block_n)) {
+    printf("tensor map encode failed (conv B)\n");
+    exit(2);
+  }
+  p.num_segs = ks;
+  p.bias = db;
+  p.out = dy, p.ldo = Cout;
+  p.act = kActNone;
+  p.M = Mrows, p.N = Cout;
+  p.out_row_mul = 1, p.out_row_add = 0;
+  p.clip_rows = Tp_out, p.clip_valid = T_out;
+  p.gn_stats = dstats, p.gn_groups = groups, p.gn_group_size = Cout / groups;
+  CK(launch_gemm(p, Mrows, Cout, block_n, 3, 0));
+  CK(cudaDeviceSynchronize());
+  auto y = host(dy, (size_t)Mrows * Cout);
+  std::vector<double> stats(B * groups * 2);
+  CK(cudaMemcpy(stats.data(), dstats, stats.size() * 8, cudaMemcpyDeviceToHost));
+
+  double maxerr = 0, maxref = 0, maxpad = 0, maxstat = 0;
+  std::vector<double> rs(B * groups * 2, 0.0);
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < Tp_out; ++t)
+      for (int co = 0; co < Cout; ++co) {
+        const double got = y[((size_t)b * Tp_out + t) * Cout + co];
+        if (t >= T_out) {
+          maxpad = std::fmax(maxpad, std::fabs(got));
+          continue;
+        }
+        double acc = bias[co];
+        for (int j = 0; j < ks; ++j) {
+          const int ti = t * stride + j - pad;
+          if (ti < 0 || ti >= T_in) continue;
+          for (int ci = 0; ci < Cin; ++ci)
+            acc += (double)Wt[((size_t)co * Cin + ci) * ks + j] * (double)x[((size_t)b * Tp_in + ti) * ldx + ci];
+        }
+        maxerr = std::fmax(maxerr, std::fabs(got - acc));
+        maxref = std::fmax(maxref, std::fabs(acc));
+        const int g = co / (Cout / groups);
+        rs[(b * groups + g) * 2] += acc;
+        rs[(b * groups + g) * 2 + 1] += acc * acc;
+      }
+  for (size_t i = 0; i < rs.size(); ++i) maxstat = std::fmax(maxstat, std::fabs(rs[i] - stats[i]) / (1.0 + std::fabs(rs[i])));
+  char name[160];
+  snprintf(name, sizeof name, "conv B%d T%d/%d Cin%d Cout%d k%d s%d bn%d", B, T_in, Tp_in, Cin, Cout, ks, stride, block_n);
+  report(name, maxerr, maxref, 2e-5);
+  report("  pad rows written as zero", maxpad, 0, 0.0);
+  report("  GroupNorm sum/sumsq (relative)", maxstat, 1, 1e-5);
+  cudaFree(dx), cudaFree(dW), cudaFree(db), cudaFree(dy), cudaFree(dstats);
+  cudaFree(sx.hi), cudaFree(sx.lo), cudaFree(sW.hi), cudaFree(sW.lo);
+}
+
+int main() {
+  int devcount = 0;
+  CK(cudaGetDeviceCount(&devcount));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s  sm_%d%d  SMs %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+
+  // PoseNet shapes at B=32, S=145 (M = 4640)
+  case_linear(4640, 512, 512, 128, kActNone, true, true);    // out-proj + residual
+  case_linear(4640, 1536, 512, 128, kActNone, false, true);  // QKV
+  case_linear(4640, 1024, 512, 128, kActGelu, false, true);  // FFN1 + GELU
+  case_linear(4640, 512, 1024, 128, kActNone, true, true);   // FFN2 + residual
+  case_linear(4640, 512, 294, 128, kActNone, true, false);   // input embedding (K tail via TMA OOB)
+  case_linear(4640, 272, 512, 96, kActNone, false, true);    // output head (N tail)
+  // small / ragged
+  case_linear(300, 272, 294, 96, kActNone, false, false);
+  case_linear(77, 64, 40, 64, kActSilu, false, false);
+  case_linear(200, 128, 128, 128, kActMish, false, false);
+  case_linear(33, 13, 32, 32, kActNone, false, false);
+  // TrajNet-style convolutions over padded clips
+  case_conv(3, 18, 22, 64, 64, 5, 1, 2, 64, 8);
+  case_conv(2, 144, 176, 13, 64, 5, 1, 2, 64, 8);
+  case_conv(2, 36, 44, 256, 256, 5, 1, 2, 128, 8);
+  case_conv(3, 72, 88, 128, 128, 3, 2, 1, 128, 8);  // Downsample1d
+  case_conv(2, 9, 11, 1024, 512, 5, 1, 2, 128, 8);
+  case_conv(2, 144, 176, 32, 32, 5, 1, 2, 32, 8);
+
+  printf(failures ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", failures);
+  return failures ? 1 : 0;
+}
