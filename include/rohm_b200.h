@@ -1,0 +1,145 @@
+/* rohm_b200 -- C ABI of the B200-native RoHM hot path.
+ *
+ * The reference (sanweiliti/RoHM) is pure Python/PyTorch and has no FFI; its boundary is a set of Python symbols
+ * (layer A).  This header is layer B: the plain-C entry points the Python drop-in
+ * (rohm_b200/dropin/{model,diffusion,utils}) binds with ctypes.  Each entry point names the reference code it
+ * replaces (file:line @ 57ba22c).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (or int64 where stated) unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it;
+ *   - no entry point allocates device memory except the *_create functions;
+ *   - return value: 0 on success, negative rohm_status otherwise; rohm_last_error(ctx) gives the message;
+ *   - one ctx per device/stream user; handles are not thread-safe.
+ */
+#ifndef ROHM_B200_H_
+#define ROHM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ROHM_API __attribute__((visibility("default")))
+#else
+#define ROHM_API
+#endif
+
+typedef enum {
+  ROHM_OK = 0,
+  ROHM_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  ROHM_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  ROHM_ERR_NO_DEVICE = -3, /* no sm_100 device */
+  ROHM_ERR_STATE = -4      /* call order violated (e.g. forward before set_cond) */
+} rohm_status;
+
+/* Arithmetic mode of the tensor-core GEMMs. */
+typedef enum {
+  ROHM_PRECISION_TF32X3 = 3, /* error-compensated TF32: fp32-grade results (parity mode, default) */
+  ROHM_PRECISION_TF32 = 1    /* single-pass TF32: ~1e-3 relative (fast mode) */
+} rohm_precision;
+
+typedef struct rohm_ctx rohm_ctx;
+typedef struct rohm_posenet rohm_posenet;
+typedef struct rohm_trajnet rohm_trajnet;
+typedef struct rohm_body rohm_body;
+
+ROHM_API int rohm_version(void);
+ROHM_API int rohm_ctx_create(int device, rohm_ctx** out);
+ROHM_API void rohm_ctx_destroy(rohm_ctx* ctx);
+ROHM_API const char* rohm_last_error(const rohm_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sampler arithmetic (diffusion/gaussian_diffusion_posenet.py and _trajnet.py)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One ancestral update over n_clips clips of clip_elems contiguous elements each (all operands share the layout):
+ *   mean = c1*x0 + c2*x_t                           q_posterior_mean_variance  :212-234, p_mean_variance :236-280
+ *   mean += gs_k*grad_k        for k < n_grads      p_sample_with_grad         :461-477 (gs = weight*variance[t])
+ *   out  = mean + sigma*noise                       p_sample :426-434          (sigma = (t!=0)*exp(0.5*logvar[t]))
+ * coef points to device rows of ROHM_DDPM_COEFS floats {c1, c2, sigma, gs0, gs1, unused, unused, unused}; clip b reads
+ * row coef + b*coef_clip_stride (stride 0 = one row for the whole batch, e.g. a row of a per-step table uploaded once).
+ * Products and sums are rounded individually (no FMA contraction) so the result matches the reference's chain of
+ * separate elementwise kernels bit for bit.  grads may be NULL when n_grads == 0.  `out` may alias x_t. */
+#define ROHM_DDPM_COEFS 8
+ROHM_API int rohm_ddpm_step(rohm_ctx* ctx, const float* x0, const float* x_t, const float* noise, const float* grad0,
+                            const float* grad1, int n_grads, float* out, int64_t n_clips, int64_t clip_elems,
+                            const float* coef, int64_t coef_clip_stride, void* stream);
+
+/* q_sample :192-210:  out = sqrt_ac*x_start + sqrt_1m_ac*noise. */
+ROHM_API int rohm_q_sample(rohm_ctx* ctx, const float* x_start, const float* noise, float* out, int64_t n, float sqrt_ac,
+                  float sqrt_one_minus_ac, void* stream);
+
+/* DDIM update as INTENDED by ddim_sample :665-715 (unreachable in the reference):
+ *   eps  = (sqrt_recip_ac*x_t - x0) / sqrt_recipm1_ac
+ *   out  = x0*sqrt(ac_prev) + sqrt(1 - ac_prev - sigma^2)*eps + nonzero*sigma*noise
+ * The four scalars are precomputed on the host from the float64 tables. */
+ROHM_API int rohm_ddim_step(rohm_ctx* ctx, const float* x0, const float* x_t, const float* noise, float* out, int64_t n,
+                   float sqrt_recip_ac, float sqrt_recipm1_ac, float sqrt_ac_prev, float dir_coef, float sigma,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PoseNet denoiser (model/posenet.py:75-96, model/heads.py:112-176, nn.TransformerEncoder post-norm/gelu)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* in_proj_w;  /* self_attn.in_proj_weight [3D, D] */
+  const float* in_proj_b;  /* [3D] */
+  const float* out_proj_w; /* self_attn.out_proj.weight [D, D] */
+  const float* out_proj_b;
+  const float* lin1_w; /* linear1.weight [F, D] */
+  const float* lin1_b;
+  const float* lin2_w; /* linear2.weight [D, F] */
+  const float* lin2_b;
+  const float* norm1_w;
+  const float* norm1_b;
+  const float* norm2_w;
+  const float* norm2_b;
+} rohm_posenet_layer;
+
+typedef struct {
+  int d_model;     /* latent_dim (512) */
+  int ff_size;     /* 1024 */
+  int num_layers;  /* 8 */
+  int num_heads;   /* 4 */
+  int in_feats;    /* body_feat_dim (294) */
+  int out_feats;   /* pose_feat_dim (272) */
+  int traj_feats;  /* channels copied from cond to the output (22) */
+  int pe_len;      /* rows of the positional table (5000) */
+  const float* in_w;   /* input_process.poseEmbedding.weight [D, in_feats] */
+  const float* in_b;
+  const float* cond_w; /* input_process_cond.poseEmbedding.weight [D, in_feats] */
+  const float* cond_b;
+  const float* pe;     /* sequence_pos_encoder.pe as [pe_len, D] */
+  const float* t0_w;   /* embed_timestep.time_embed.0 [D, D] */
+  const float* t0_b;
+  const float* t2_w;   /* embed_timestep.time_embed.2 [D, D] */
+  const float* t2_b;
+  const float* out_w;  /* output_process.poseFinal.weight [out_feats, D] */
+  const float* out_b;
+  const rohm_posenet_layer* layers; /* host array of num_layers entries */
+} rohm_posenet_weights;
+
+/* Copies and repacks the weights (TF32 hi/lo split, K-padded) into library-owned device memory and allocates the
+ * activation workspace for up to max_batch clips of max_frames frames. */
+ROHM_API int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w, int max_batch, int max_frames, int precision,
+                        rohm_posenet** out);
+ROHM_API void rohm_posenet_destroy(rohm_posenet* pn);
+
+/* Step-invariant part of PoseNet.forward (posenet.py:86, 90-91): input_process_cond(cond) + positional rows.
+ * cond: [B, in_feats, 1, T] contiguous.  Must be called whenever batch['cond'], B or T change. */
+ROHM_API int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B, int T, void* stream);
+
+/* PoseNet.forward (posenet.py:75-96).  x_t: [B, in_feats, 1, T]; timesteps: int64 [B] (original, un-respaced);
+ * out: [B, in_feats, 1, T] with channels [0, traj_feats) copied from the cond given to set_cond. */
+ROHM_API int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
+                         void* stream);
+
+/* Kernel launches issued by the last forward (for bench.py's gpu_launches accounting). */
+ROHM_API int rohm_posenet_launches_per_forward(const rohm_posenet* pn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROHM_B200_H_ */

@@ -1,0 +1,76 @@
+// Shared host-side plumbing for the C-ABI library: context, error reporting, device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/rohm_b200.h"
+
+struct rohm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+};
+
+namespace rohm {
+
+inline int fail(rohm_ctx* ctx, int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx != nullptr) ctx->err = buf;
+  return status;
+}
+
+#define ROHM_CUDA(ctx, call)                                                                                  \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      return ::rohm::fail((ctx), ROHM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                          __LINE__);                                                                          \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// Owns a set of cudaMalloc'ed buffers; frees them on destruction.
+class DevicePool {
+ public:
+  ~DevicePool() {
+    for (void* p : ptrs_) cudaFree(p);
+  }
+  // Zero-initialised fp32 buffer of n elements (nullptr on failure, error kept in last_error()).
+  float* floats(int64_t n) { return static_cast<float*>(bytes(n * static_cast<int64_t>(sizeof(float)))); }
+  void* bytes(int64_t n) {
+    void* p = nullptr;
+    if (n <= 0) n = 16;
+    last_ = cudaMalloc(&p, static_cast<size_t>(n));
+    if (last_ != cudaSuccess) return nullptr;
+    last_ = cudaMemset(p, 0, static_cast<size_t>(n));
+    if (last_ != cudaSuccess) return nullptr;
+    ptrs_.push_back(p);
+    total_ += n;
+    return p;
+  }
+  cudaError_t last_error() const { return last_; }
+  int64_t total_bytes() const { return total_; }
+
+ private:
+  std::vector<void*> ptrs_;
+  cudaError_t last_ = cudaSuccess;
+  int64_t total_ = 0;
+};
+
+// A weight matrix [N, K] repacked for the GEMM: zero-padded to [Np, Kp] and split into TF32 hi / lo.
+struct PackedWeight {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int N = 0, K = 0, Np = 0, Kp = 0, block_n = 0;
+};
+
+}  // namespace rohm

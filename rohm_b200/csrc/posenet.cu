@@ -1,0 +1,667 @@
+// PoseNet denoiser engine: the per-step transformer-encoder forward of RoHM's PoseNet
+// (reference model/posenet.py:75-96, model/heads.py:112-176; torch nn.TransformerEncoderLayer post-norm, exact GELU).
+//
+// Token-major layout: every activation is a row-major [B*S, width] matrix, S = T + 1 tokens per clip (token 0 is the
+// timestep embedding), clips contiguous.  All linear layers run on the tcgen05 GEMM (gemm.cu); operands that feed a
+// GEMM are kept as TF32 hi/lo pairs written by the producing kernel, so no separate conversion pass exists.
+//
+//   x_t [B,C,1,T] --pack--> A_in --GEMM(+bias+cond_embed+pe)--> X  (token 0 <- time MLP)
+//   8 x { X --GEMM--> QKV --attention--> CTX --GEMM(+bias+X)--> Y --LN--> X
+//         X --GEMM(+bias,GELU)--> H --GEMM(+bias+X)--> Y --LN--> X }
+//   X --GEMM--> OUT_tok --unpack(+copy cond[:, :traj])--> out [B,C,1,T]
+#include <cmath>
+#include <new>
+
+#include "common.h"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace rohm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------
+
+// [B, C, T] (frames contiguous) -> token rows (b*S + 1 + t) of a [B*S, ld] hi/lo pair.  32x32 smem transpose.
+__global__ void pack_tokens_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int C,
+                                   int T, int S, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, t = t0 + tx;
+    tile[j][tx] = (c < C && t < T) ? x[(static_cast<int64_t>(b) * C + c) * T + t] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int t = t0 + j, c = c0 + tx;
+    if (t < T && c < C) {
+      const float v = tile[tx][j];
+      const float h = ptx::to_tf32(v);
+      const int64_t o = (static_cast<int64_t>(b) * S + 1 + t) * ld + c;
+      hi[o] = h;
+      lo[o] = v - h;
+    }
+  }
+}
+
+// Token rows -> [B, C, T]: channels [traj, traj+Cout) from tok[b*S+1+t][c - traj], channels [0, traj) from cond.
+__global__ void unpack_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ cond_traj,
+                                     float* __restrict__ out, int C, int Cout, int traj, int T, int S, int ldt) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // c0 indexes the Cout predicted channels
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const int t = t0 + j, c = c0 + tx;
+    tile[j][tx] = (t < T && c < Cout) ? tok[(static_cast<int64_t>(b) * S + 1 + t) * ldt + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, t = t0 + tx;
+    if (c < Cout && t < T) out[(static_cast<int64_t>(b) * C + traj + c) * T + t] = tile[tx][j];
+  }
+  if (blockIdx.y == 0) {  // given trajectory channels are a verbatim copy of the condition (posenet.py:94-95)
+    for (int c = ty; c < traj; c += 8) {
+      const int t = t0 + tx;
+      if (t < T) out[(static_cast<int64_t>(b) * C + c) * T + t] = cond_traj[(static_cast<int64_t>(b) * traj + c) * T + t];
+    }
+  }
+}
+
+// rows[b*S + s][:] = pe[s][:]   (positional rows added to every token incl. the timestep token, posenet.py:90-91)
+__global__ void pe_rows_kernel(const float* __restrict__ pe, float* __restrict__ rows, int S, int D, int64_t total4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int d4 = D / 4;
+  const int64_t row = i / d4;
+  const int c = static_cast<int>(i - row * d4);
+  const int s = static_cast<int>(row % S);
+  reinterpret_cast<float4*>(rows)[i] = reinterpret_cast<const float4*>(pe)[static_cast<int64_t>(s) * d4 + c];
+}
+
+// TimestepEmbedder (heads.py:132-146): e = W2 silu(W0 pe[t_b] + b0) + b2; token row (b, 0) = e + pe[0].
+// One CTA per clip, 8 warps, each output is a warp-wide dot product.
+__global__ void __launch_bounds__(256) time_token_kernel(const int64_t* __restrict__ timesteps,
+                                                         const float* __restrict__ pe, int pe_len,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float* __restrict__ X, float* __restrict__ Xh,
+                                                         float* __restrict__ Xl, int S, int D) {
+  extern __shared__ float sm[];  // v[D], h[D]
+  float* v = sm;
+  float* h = sm + D;
+  const int b = blockIdx.x;
+  int64_t t = timesteps[b];
+  if (t < 0) t = 0;
+  if (t >= pe_len) t = pe_len - 1;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) v[i] = pe[t * D + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < D; n += nw) {
+    const float* w = w0 + static_cast<int64_t>(n) * D;
+    float acc = 0.0f;
+    for (int k = lane; k < D; k += 32) acc = fmaf(w[k], v[k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float z = acc + b0[n];
+      h[n] = z / (1.0f + expf(-z));
+    }
+  }
+  __syncthreads();
+  for (int n = warp; n < D; n += nw) {
+    const float* w = w2 + static_cast<int64_t>(n) * D;
+    float acc = 0.0f;
+    for (int k = lane; k < D; k += 32) acc = fmaf(w[k], h[k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float e = (acc + b2[n]) + pe[n];  // + pe[0][n]
+      const int64_t o = static_cast<int64_t>(b) * S * D + n;
+      const float hh = ptx::to_tf32(e);
+      X[o] = e;
+      Xh[o] = hh;
+      Xl[o] = e - hh;
+    }
+  }
+}
+
+// LayerNorm over the last dim (eps 1e-5), one warp per row; writes fp32 and the TF32 hi/lo pair.
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ out,
+                                                        float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                        int rows) {
+  static_assert(D % 128 == 0, "row must be a multiple of 32 lanes x float4");
+  constexpr int V = D / 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + static_cast<int64_t>(row) * D);
+  float4 x[V];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    x[i] = src[lane + 32 * i];
+    sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  const float rstd = rsqrtf(sq * (1.0f / D) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4* o = reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * D);
+  float4* oh = reinterpret_cast<float4*>(out_hi + static_cast<int64_t>(row) * D);
+  float4* ol = reinterpret_cast<float4*>(out_lo + static_cast<int64_t>(row) * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+    float4 y, h, l;
+    y.x = (x[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (x[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (x[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (x[i].w - mean) * rstd * g.w + bb.w;
+    h.x = ptx::to_tf32(y.x), h.y = ptx::to_tf32(y.y), h.z = ptx::to_tf32(y.z), h.w = ptx::to_tf32(y.w);
+    l.x = y.x - h.x, l.y = y.y - h.y, l.z = y.z - h.z, l.w = y.w - h.w;
+    o[lane + 32 * i] = y;
+    oh[lane + 32 * i] = h;
+    ol[lane + 32 * i] = l;
+  }
+}
+
+// Multi-head self-attention, fp32 on CUDA cores (v1): one CTA per (clip, head); K and V of the head live in shared
+// memory, each warp owns query rows round-robin.  softmax(Q K^T / sqrt(dh)) V with no mask (posenet.py:63-69).
+// qkv: [B*S, 3*D] fp32 (Q | K | V, head h at columns h*DH).  ctx hi/lo: [B*S, D].
+template <int DH>
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx_hi,
+                                                        float* __restrict__ ctx_lo, int S, int D, int H, float scale) {
+  constexpr int KP = DH + 4;  // padded K row: conflict-free float4 reads with one key per lane
+  constexpr int NW = 8;
+  extern __shared__ float sm[];
+  float* Ks = sm;                      // [S][KP]
+  float* Vs = Ks + S * KP;             // [S][DH]
+  float* Qs = Vs + S * DH;             // [NW][DH]
+  const int Sp = (S + 31) & ~31;
+  float* Ps = Qs + NW * DH;            // [NW][Sp]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = static_cast<int64_t>(b) * S;
+  const int ld = 3 * D;
+
+  for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
+    const int s = i / (DH / 4), c = i % (DH / 4);
+    const float* row = qkv + (base + s) * ld + h * DH + c * 4;
+    const float4 k = *reinterpret_cast<const float4*>(row + D);
+    const float4 v = *reinterpret_cast<const float4*>(row + 2 * D);
+    *reinterpret_cast<float4*>(Ks + s * KP + c * 4) = k;
+    *reinterpret_cast<float4*>(Vs + s * DH + c * 4) = v;
+  }
+  __syncthreads();
+
+  constexpr int MAXJ = 8;  // supports S <= 256
+  const int nj = Sp / 32;
+  float* q = Qs + warp * DH;
+  float* p = Ps + warp * Sp;
+  for (int i = warp; i < S; i += NW) {
+    const float* qrow = qkv + (base + i) * ld + h * DH;
+    for (int c = lane; c < DH / 4; c += 32) *reinterpret_cast<float4*>(q + c * 4) = *reinterpret_cast<const float4*>(qrow + c * 4);
+    __syncwarp();
+    float sc[MAXJ];
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) sc[jj] = 0.0f;
+    for (int d = 0; d < DH; d += 4) {
+      const float4 qv = *reinterpret_cast<const float4*>(q + d);
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        if (jj < nj) {
+          int j = lane + 32 * jj;
+          j = j < S ? j : S - 1;
+          const float4 kv = *reinterpret_cast<const float4*>(Ks + j * KP + d);
+          sc[jj] = fmaf(qv.x, kv.x, sc[jj]);
+          sc[jj] = fmaf(qv.y, kv.y, sc[jj]);
+          sc[jj] = fmaf(qv.z, kv.z, sc[jj]);
+          sc[jj] = fmaf(qv.w, kv.w, sc[jj]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      if (jj < nj) {
+        sc[jj] = (lane + 32 * jj < S) ? sc[jj] * scale : -INFINITY;
+        mx = fmaxf(mx, sc[jj]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      if (jj < nj) {
+        sc[jj] = (lane + 32 * jj < S) ? expf(sc[jj] - mx) : 0.0f;
+        sum += sc[jj];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj)
+      if (jj < nj) p[lane + 32 * jj] = sc[jj] * inv;
+    __syncwarp();
+    // P V: lane owns DH/32 consecutive channels
+    constexpr int CPL = DH / 32;
+    float acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.0f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = p[j];
+      const float* vr = Vs + j * DH + lane * CPL;
+      if (CPL == 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(vr);
+        acc[0] = fmaf(pj, vv.x, acc[0]);
+        acc[1] = fmaf(pj, vv.y, acc[1]);
+        acc[2 % CPL] = fmaf(pj, vv.z, acc[2 % CPL]);
+        acc[3 % CPL] = fmaf(pj, vv.w, acc[3 % CPL]);
+      } else {
+        const float2 vv = *reinterpret_cast<const float2*>(vr);
+        acc[0] = fmaf(pj, vv.x, acc[0]);
+        acc[1] = fmaf(pj, vv.y, acc[1]);
+      }
+    }
+    const int64_t o = (base + i) * D + h * DH + lane * CPL;
+    float hh[CPL], ll[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      hh[c] = ptx::to_tf32(acc[c]);
+      ll[c] = acc[c] - hh[c];
+    }
+    if (CPL == 4) {
+      *reinterpret_cast<float4*>(ctx_hi + o) = make_float4(hh[0], hh[1], hh[2 % CPL], hh[3 % CPL]);
+      *reinterpret_cast<float4*>(ctx_lo + o) = make_float4(ll[0], ll[1], ll[2 % CPL], ll[3 % CPL]);
+    } else {
+      *reinterpret_cast<float2*>(ctx_hi + o) = make_float2(hh[0], hh[1]);
+      *reinterpret_cast<float2*>(ctx_lo + o) = make_float2(ll[0], ll[1]);
+    }
+    __syncwarp();
+  }
+}
+
+size_t attention_smem_bytes(int S, int DH) {
+  const int Sp = (S + 31) & ~31;
+  return sizeof(float) * (static_cast<size_t>(S) * (DH + 4) + static_cast<size_t>(S) * DH + 8 * DH + 8 * Sp);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------------
+struct PoseNetLayerDev {
+  PackedWeight qkv, proj, ff1, ff2;
+  float *qkv_b, *proj_b, *ff1_b, *ff2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+};
+
+}  // namespace rohm
+
+using namespace rohm;
+
+struct rohm_posenet {
+  rohm_ctx* ctx = nullptr;
+  DevicePool pool;
+  int D = 0, F = 0, L = 0, H = 0, C = 0, Cout = 0, traj = 0, pe_len = 0, passes = 3;
+  int max_batch = 0, max_frames = 0;
+  int64_t max_rows = 0;
+  int Kin_p = 0;
+  // weights
+  PackedWeight w_in, w_cond, w_out;
+  float *in_b = nullptr, *cond_b = nullptr, *out_b = nullptr, *pe = nullptr;
+  float *t0_w = nullptr, *t0_b = nullptr, *t2_w = nullptr, *t2_b = nullptr;
+  std::vector<PoseNetLayerDev> layers;
+  // activations
+  float *Ain_h = nullptr, *Ain_l = nullptr;
+  float *X = nullptr, *Xh = nullptr, *Xl = nullptr, *Y = nullptr, *QKV = nullptr, *CTXh = nullptr, *CTXl = nullptr;
+  float *Hh = nullptr, *Hl = nullptr, *condpe = nullptr, *OUT = nullptr;
+  float* cond_traj = nullptr;  // [B, traj, T] copy of cond[:, :traj] taken by set_cond (output channels [0,traj))
+  int cond_B = -1, cond_T = -1;
+  int launches = 0;
+  // GEMM parameter blocks (tensor maps are built once; only the grid depends on B*S)
+  GemmParams g_in{}, g_cond{}, g_out{};
+  std::vector<GemmParams> g_qkv, g_proj, g_ff1, g_ff2;
+};
+
+static int pick_block_n(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0) return 96;
+  if (N % 64 == 0) return 64;
+  if (N <= 32) return 32;
+  // ragged N: choose the tile with the least padding, preferring wide tiles
+  int best = 128, waste = static_cast<int>(round_up(N, 128)) - N;
+  for (int bn : {96, 64}) {
+    const int w = static_cast<int>(round_up(N, bn)) - N;
+    if (w < waste) best = bn, waste = w;
+  }
+  return best;
+}
+
+// device [N,K] fp32 -> padded hi/lo pair
+static __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int N,
+                                   int K, int Kp) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  const float v = w[i];
+  const float h = ptx::to_tf32(v);
+  hi[static_cast<int64_t>(n) * Kp + k] = h;
+  lo[static_cast<int64_t>(n) * Kp + k] = v - h;
+}
+
+static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out) {
+  out->N = N, out->K = K;
+  out->block_n = pick_block_n(N);
+  out->Np = static_cast<int>(round_up(N, out->block_n));
+  out->Kp = static_cast<int>(round_up(K, kGemmBlockK));
+  out->hi = pn->pool.floats(static_cast<int64_t>(out->Np) * out->Kp);
+  out->lo = pn->pool.floats(static_cast<int64_t>(out->Np) * out->Kp);
+  if (out->hi == nullptr || out->lo == nullptr)
+    return fail(pn->ctx, ROHM_ERR_CUDA, "weight alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
+  const int64_t n = static_cast<int64_t>(N) * K;
+  pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w, out->hi, out->lo, N, K, out->Kp);
+  ROHM_CUDA(pn->ctx, cudaGetLastError());
+  return ROHM_OK;
+}
+
+static int copy_vec(rohm_posenet* pn, const float* src, int64_t n, float** dst) {
+  *dst = pn->pool.floats(n);
+  if (*dst == nullptr) return fail(pn->ctx, ROHM_ERR_CUDA, "alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
+  ROHM_CUDA(pn->ctx, cudaMemcpy(*dst, src, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToDevice));
+  return ROHM_OK;
+}
+
+// Plain linear layer: A (hi/lo, [rows, K] with pitch lda) x W^T.
+static int setup_linear(rohm_posenet* pn, GemmParams* g, const float* a_hi, const float* a_lo, int64_t rows, int K, int lda,
+                 const PackedWeight& w, const float* bias) {
+  *g = GemmParams{};
+  int rc = make_tmap_2d(&g->a_hi[0], a_hi, rows, K, lda, kGemmBlockM);
+  rc |= make_tmap_2d(&g->a_lo[0], a_lo, rows, K, lda, kGemmBlockM);
+  rc |= make_tmap_2d(&g->b_hi, w.hi, w.Np, w.Kp, w.Kp, w.block_n);
+  rc |= make_tmap_2d(&g->b_lo, w.lo, w.Np, w.Kp, w.Kp, w.block_n);
+  if (rc != 0) return fail(pn->ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
+  g->num_segs = 1;
+  g->seg_kblocks[0] = w.Kp / kGemmBlockK;
+  g->seg_row_shift[0] = 0;
+  g->seg_row_mul[0] = 1;
+  g->bias = bias;
+  g->N = w.N;
+  g->out_row_mul = 1;
+  g->out_row_add = 0;
+  return ROHM_OK;
+}
+
+static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int rows, cudaStream_t st) {
+  g.M = rows;
+  ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st));
+  pn->launches++;
+  return ROHM_OK;
+}
+
+template <int D>
+static void launch_ln(const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
+               cudaStream_t st) {
+  layernorm_kernel<D><<<(rows + 7) / 8, 256, 0, st>>>(in, g, b, out, oh, ol, rows);
+}
+
+static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
+           cudaStream_t st) {
+  switch (pn->D) {
+    case 128: launch_ln<128>(in, g, b, out, oh, ol, rows, st); break;
+    case 256: launch_ln<256>(in, g, b, out, oh, ol, rows, st); break;
+    case 512: launch_ln<512>(in, g, b, out, oh, ol, rows, st); break;
+    case 1024: launch_ln<1024>(in, g, b, out, oh, ol, rows, st); break;
+    default: return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported d_model %d for LayerNorm", pn->D);
+  }
+  ROHM_CUDA(pn->ctx, cudaGetLastError());
+  pn->launches++;
+  return ROHM_OK;
+}
+
+static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
+  const int dh = pn->D / pn->H;
+  const size_t smem = attention_smem_bytes(S, dh);
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  if (dh == 128) {
+    attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+  } else if (dh == 64) {
+    attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+  } else {
+    return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
+  }
+  ROHM_CUDA(pn->ctx, cudaGetLastError());
+  pn->launches++;
+  return ROHM_OK;
+}
+
+extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w, int max_batch, int max_frames,
+                                   int precision, rohm_posenet** out) {
+  if (ctx == nullptr) return ROHM_ERR_INVALID;
+  if (w == nullptr || out == nullptr || max_batch <= 0 || max_frames <= 0)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: bad arguments");
+  if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: precision must be 3 (TF32x3) or 1 (TF32)");
+  if (w->d_model % 128 != 0 || w->d_model % w->num_heads != 0 || w->ff_size % 32 != 0)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: d_model must be a multiple of 128, ff_size of 32");
+  const int dh = w->d_model / w->num_heads;
+  if (dh != 64 && dh != 128) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: head dim must be 64 or 128");
+  if (max_frames + 1 > 256) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: at most 255 frames per clip");
+  if (max_frames + 1 > w->pe_len) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: clip longer than pe table");
+  ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  rohm_posenet* pn = new (std::nothrow) rohm_posenet();
+  if (pn == nullptr) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
+  pn->ctx = ctx;
+  pn->D = w->d_model, pn->F = w->ff_size, pn->L = w->num_layers, pn->H = w->num_heads;
+  pn->C = w->in_feats, pn->Cout = w->out_feats, pn->traj = w->traj_feats, pn->pe_len = w->pe_len;
+  pn->passes = precision;
+  pn->max_batch = max_batch, pn->max_frames = max_frames;
+  pn->max_rows = static_cast<int64_t>(max_batch) * (max_frames + 1);
+  pn->Kin_p = static_cast<int>(round_up(pn->C, kGemmBlockK));
+  const int D = pn->D, F = pn->F;
+  const int64_t R = pn->max_rows;
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != ROHM_OK) {   \
+      delete pn;             \
+      return rc__;           \
+    }                        \
+  } while (0)
+
+  TRY(pack_weight(pn, w->in_w, D, pn->C, &pn->w_in));
+  TRY(pack_weight(pn, w->cond_w, D, pn->C, &pn->w_cond));
+  TRY(pack_weight(pn, w->out_w, pn->Cout, D, &pn->w_out));
+  TRY(copy_vec(pn, w->in_b, D, &pn->in_b));
+  TRY(copy_vec(pn, w->cond_b, D, &pn->cond_b));
+  TRY(copy_vec(pn, w->out_b, pn->Cout, &pn->out_b));
+  TRY(copy_vec(pn, w->pe, static_cast<int64_t>(pn->pe_len) * D, &pn->pe));
+  TRY(copy_vec(pn, w->t0_w, static_cast<int64_t>(D) * D, &pn->t0_w));
+  TRY(copy_vec(pn, w->t0_b, D, &pn->t0_b));
+  TRY(copy_vec(pn, w->t2_w, static_cast<int64_t>(D) * D, &pn->t2_w));
+  TRY(copy_vec(pn, w->t2_b, D, &pn->t2_b));
+  pn->layers.resize(pn->L);
+  for (int l = 0; l < pn->L; ++l) {
+    const rohm_posenet_layer& s = w->layers[l];
+    PoseNetLayerDev& d = pn->layers[l];
+    TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv));
+    TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj));
+    TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1));
+    TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2));
+    TRY(copy_vec(pn, s.in_proj_b, 3 * D, &d.qkv_b));
+    TRY(copy_vec(pn, s.out_proj_b, D, &d.proj_b));
+    TRY(copy_vec(pn, s.lin1_b, F, &d.ff1_b));
+    TRY(copy_vec(pn, s.lin2_b, D, &d.ff2_b));
+    TRY(copy_vec(pn, s.norm1_w, D, &d.n1_w));
+    TRY(copy_vec(pn, s.norm1_b, D, &d.n1_b));
+    TRY(copy_vec(pn, s.norm2_w, D, &d.n2_w));
+    TRY(copy_vec(pn, s.norm2_b, D, &d.n2_b));
+  }
+
+  struct {
+    float** p;
+    int64_t n;
+  } bufs[] = {{&pn->Ain_h, R * pn->Kin_p}, {&pn->Ain_l, R * pn->Kin_p}, {&pn->X, R * D},     {&pn->Xh, R * D},
+              {&pn->Xl, R * D},           {&pn->Y, R * D},             {&pn->QKV, R * 3 * D}, {&pn->CTXh, R * D},
+              {&pn->CTXl, R * D},         {&pn->Hh, R * F},            {&pn->Hl, R * F},      {&pn->condpe, R * D},
+              {&pn->OUT, R * pn->Cout},
+              {&pn->cond_traj, static_cast<int64_t>(max_batch) * (pn->traj > 0 ? pn->traj : 1) * max_frames}};
+  for (auto& b : bufs) {
+    *b.p = pn->pool.floats(b.n);
+    if (*b.p == nullptr) {
+      const int rc = fail(ctx, ROHM_ERR_CUDA, "workspace alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
+      delete pn;
+      return rc;
+    }
+  }
+
+  // GEMM descriptors.  Input embedding: residual = cond embedding + positional rows (set per set_cond).
+  TRY(setup_linear(pn, &pn->g_in, pn->Ain_h, pn->Ain_l, R, pn->C, pn->Kin_p, pn->w_in, pn->in_b));
+  pn->g_in.residual = pn->condpe, pn->g_in.ldr = D;
+  pn->g_in.out = pn->X, pn->g_in.ldo = D;
+  pn->g_in.out_hi = pn->Xh, pn->g_in.out_lo = pn->Xl, pn->g_in.lds = D;
+  // Condition embedding: residual = positional rows (held in condpe itself: written in place).
+  TRY(setup_linear(pn, &pn->g_cond, pn->Ain_h, pn->Ain_l, R, pn->C, pn->Kin_p, pn->w_cond, pn->cond_b));
+  pn->g_cond.residual = pn->condpe, pn->g_cond.ldr = D;
+  pn->g_cond.out = pn->condpe, pn->g_cond.ldo = D;
+  // Output head.
+  TRY(setup_linear(pn, &pn->g_out, pn->Xh, pn->Xl, R, D, D, pn->w_out, pn->out_b));
+  pn->g_out.out = pn->OUT, pn->g_out.ldo = pn->Cout;
+  pn->g_qkv.resize(pn->L), pn->g_proj.resize(pn->L), pn->g_ff1.resize(pn->L), pn->g_ff2.resize(pn->L);
+  for (int l = 0; l < pn->L; ++l) {
+    PoseNetLayerDev& d = pn->layers[l];
+    TRY(setup_linear(pn, &pn->g_qkv[l], pn->Xh, pn->Xl, R, D, D, d.qkv, d.qkv_b));
+    pn->g_qkv[l].out = pn->QKV, pn->g_qkv[l].ldo = 3 * D;
+    TRY(setup_linear(pn, &pn->g_proj[l], pn->CTXh, pn->CTXl, R, D, D, d.proj, d.proj_b));
+    pn->g_proj[l].residual = pn->X, pn->g_proj[l].ldr = D;
+    pn->g_proj[l].out = pn->Y, pn->g_proj[l].ldo = D;
+    TRY(setup_linear(pn, &pn->g_ff1[l], pn->Xh, pn->Xl, R, D, D, d.ff1, d.ff1_b));
+    pn->g_ff1[l].act = kActGelu;
+    pn->g_ff1[l].out_hi = pn->Hh, pn->g_ff1[l].out_lo = pn->Hl, pn->g_ff1[l].lds = F;
+    TRY(setup_linear(pn, &pn->g_ff2[l], pn->Hh, pn->Hl, R, F, F, d.ff2, d.ff2_b));
+    pn->g_ff2[l].residual = pn->X, pn->g_ff2[l].ldr = D;
+    pn->g_ff2[l].out = pn->Y, pn->g_ff2[l].ldo = D;
+  }
+#undef TRY
+
+  // attention kernels need > 48 KB of dynamic shared memory
+  const size_t smem_max = attention_smem_bytes(max_frames + 1, dh);
+  if (smem_max > 227 * 1024) {
+    delete pn;
+    return fail(ctx, ROHM_ERR_INVALID, "clip too long for the attention kernel (%zu B smem)", smem_max);
+  }
+  cudaError_t e = dh == 128 ? cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem_max))
+                            : cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem_max));
+  if (e != cudaSuccess) {
+    delete pn;
+    return fail(ctx, ROHM_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    delete pn;
+    return fail(ctx, ROHM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(e));
+  }
+  *out = pn;
+  return ROHM_OK;
+}
+
+extern "C" void rohm_posenet_destroy(rohm_posenet* pn) { delete pn; }
+
+extern "C" int rohm_posenet_launches_per_forward(const rohm_posenet* pn) { return pn ? pn->launches : 0; }
+
+extern "C" int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B, int T, void* stream) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = pn->ctx;
+  if (cond == nullptr || B <= 0 || T <= 0 || B > pn->max_batch || T > pn->max_frames)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_set_cond: B=%d T=%d outside the created capacity (%d, %d)", B, T,
+                pn->max_batch, pn->max_frames);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = T + 1, D = pn->D;
+  const int rows = B * S;
+  // A_in <- tokens of cond (row (b,0) stays zero: the buffer was zero-initialised and is never written there)
+  dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
+  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(cond, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  const int64_t total4 = static_cast<int64_t>(rows) * D / 4;
+  pe_rows_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(pn->pe, pn->condpe, S, D, total4);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  // condpe <- cond_embed(cond) + cond_b + pe rows   (in place; rows (b,0) become cond_b + pe[0]: overwritten later
+  // by the timestep token, so their value is irrelevant)
+  const int saved = pn->launches;
+  int rc = run_gemm(pn, pn->g_cond, pn->w_cond, rows, st);
+  pn->launches = saved;
+  if (rc != ROHM_OK) return rc;
+  if (pn->traj > 0) {
+    const size_t width = static_cast<size_t>(pn->traj) * T * sizeof(float);
+    ROHM_CUDA(ctx, cudaMemcpy2DAsync(pn->cond_traj, width, cond, static_cast<size_t>(pn->C) * T * sizeof(float), width,
+                                     B, cudaMemcpyDeviceToDevice, st));
+  }
+  pn->cond_B = B, pn->cond_T = T;
+  return ROHM_OK;
+}
+
+extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
+                                    int T, void* stream) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = pn->ctx;
+  if (x_t == nullptr || timesteps == nullptr || out == nullptr)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_forward: null pointer");
+  if (B != pn->cond_B || T != pn->cond_T)
+    return fail(ctx, ROHM_ERR_STATE, "rohm_posenet_forward: B=%d T=%d but set_cond was called with B=%d T=%d", B, T,
+                pn->cond_B, pn->cond_T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = T + 1, D = pn->D;
+  const int rows = B * S;
+  pn->launches = 0;
+  int rc;
+
+  dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
+  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  pn->launches++;
+  if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
+  time_token_kernel<<<B, 256, 2 * D * sizeof(float), st>>>(timesteps, pn->pe, pn->pe_len, pn->t0_w, pn->t0_b, pn->t2_w,
+                                                          pn->t2_b, pn->X, pn->Xh, pn->Xl, S, D);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  pn->launches++;
+
+  for (int l = 0; l < pn->L; ++l) {
+    PoseNetLayerDev& d = pn->layers[l];
+    if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
+    if ((rc = run_gemm(pn, pn->g_proj[l], d.proj, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_ln(pn, pn->Y, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_gemm(pn, pn->g_ff1[l], d.ff1, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_gemm(pn, pn->g_ff2[l], d.ff2, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_ln(pn, pn->Y, d.n2_w, d.n2_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+  }
+  if ((rc = run_gemm(pn, pn->g_out, pn->w_out, rows, st)) != ROHM_OK) return rc;
+  dim3 grid_o((T + 31) / 32, (pn->Cout + 31) / 32, B);
+  unpack_tokens_kernel<<<grid_o, dim3(32, 8), 0, st>>>(pn->OUT, pn->cond_traj, out, pn->C, pn->Cout, pn->traj, T, S,
+                                                      pn->Cout);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  pn->launches++;
+  return ROHM_OK;
+}

@@ -1,0 +1,106 @@
+"""PyTorch-facing operators: thin checked wrappers that hand raw device pointers and the current CUDA stream to the
+C-ABI library.  PyTorch is plumbing here (device memory, streams); all arithmetic happens in librohm_b200.so.
+
+The elementwise sampler ops are also registered as ``torch.ops.rohm.*`` custom ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RohmB200Error
+
+
+def _require_cuda(name, t, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RohmB200Error(f"{name}: expected a CUDA tensor (rohm_b200 has no CPU path), got "
+                            f"{getattr(t, 'device', type(t))}")
+    if t.dtype != dtype:
+        raise RohmB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RohmB200Error(f"{name}: tensor must be contiguous")
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def ddpm_step(x0, x_t, noise, coef, grads=(), out=None):
+    """out = c1*x0 + c2*x_t (+ gs_k*grad_k) + sigma*noise; coef: fp32 CUDA [8] (shared) or [B, 8] (per clip)."""
+    for n, t in (("x0", x0), ("x_t", x_t), ("noise", noise), ("coef", coef)):
+        _require_cuda(n, t)
+    if not (x0.shape == x_t.shape == noise.shape):
+        raise RohmB200Error("ddpm_step: x0, x_t and noise must have the same shape")
+    for g in grads:
+        _require_cuda("grad", g)
+        if g.shape != x0.shape:
+            raise RohmB200Error("ddpm_step: grad shape mismatch")
+    B = x0.shape[0]
+    clip_elems = x0.numel() // max(B, 1)
+    if coef.dim() == 1:
+        stride = 0
+        if coef.numel() < _lib.DDPM_COEFS:
+            raise RohmB200Error("ddpm_step: coef row must hold 8 floats")
+    else:
+        if coef.shape != (B, _lib.DDPM_COEFS):
+            raise RohmB200Error(f"ddpm_step: per-clip coef must be [{B}, 8]")
+        stride = _lib.DDPM_COEFS
+    if out is None:
+        out = torch.empty_like(x0)
+    lib, c = _lib.load(), _lib.ctx(x0.device.index)
+    g0 = grads[0] if len(grads) > 0 else None
+    g1 = grads[1] if len(grads) > 1 else None
+    rc = lib.rohm_ddpm_step(c, _ptr(x0), _ptr(x_t), _ptr(noise), _ptr(g0), _ptr(g1), len(grads), _ptr(out), B,
+                            clip_elems, _ptr(coef), stride, _stream(x0.device))
+    _lib.check(rc, c)
+    return out
+
+
+def q_sample(x_start, noise, sqrt_ac, sqrt_one_minus_ac):
+    _require_cuda("x_start", x_start)
+    _require_cuda("noise", noise)
+    out = torch.empty_like(x_start)
+    lib, c = _lib.load(), _lib.ctx(x_start.device.index)
+    rc = lib.rohm_q_sample(c, _ptr(x_start), _ptr(noise), _ptr(out), x_start.numel(), float(sqrt_ac),
+                           float(sqrt_one_minus_ac), _stream(x_start.device))
+    _lib.check(rc, c)
+    return out
+
+
+def ddim_step(x0, x_t, noise, coefs):
+    for n, t in (("x0", x0), ("x_t", x_t), ("noise", noise)):
+        _require_cuda(n, t)
+    out = torch.empty_like(x0)
+    lib, c = _lib.load(), _lib.ctx(x0.device.index)
+    sr, srm1, sap, dirc, sigma = coefs
+    rc = lib.rohm_ddim_step(c, _ptr(x0), _ptr(x_t), _ptr(noise), _ptr(out), x0.numel(), sr, srm1, sap, dirc, sigma,
+                            _stream(x0.device))
+    _lib.check(rc, c)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torch.library registration (torch.ops.rohm.*)
+# ---------------------------------------------------------------------------------------------------------------
+try:
+    @torch.library.custom_op("rohm::ddpm_step", mutates_args=(), device_types="cuda")
+    def _ddpm_step_op(x0: torch.Tensor, x_t: torch.Tensor, noise: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+        return ddpm_step(x0, x_t, noise, coef)
+
+    @_ddpm_step_op.register_fake
+    def _(x0, x_t, noise, coef):
+        return torch.empty_like(x0)
+
+    @torch.library.custom_op("rohm::q_sample", mutates_args=(), device_types="cuda")
+    def _q_sample_op(x_start: torch.Tensor, noise: torch.Tensor, a: float, b: float) -> torch.Tensor:
+        return q_sample(x_start, noise, a, b)
+
+    @_q_sample_op.register_fake
+    def _(x_start, noise, a, b):
+        return torch.empty_like(x_start)
+except Exception:  # pragma: no cover - registration is a convenience, the python entry points above are the API
+    pass

@@ -1,0 +1,236 @@
+"""PoseNet: drop-in for reference model/posenet.py:11-96 (constructor, attributes, state-dict keys, call signature),
+with the forward pass executed by the CUDA engine behind ``rohm_posenet_*`` (include/rohm_b200.h).
+
+The module owns its parameters in torch containers named exactly like the reference so ``load_state_dict(strict=True)``
+works on released checkpoints; on the first forward (and whenever parameters change) they are repacked into the
+engine's TF32 hi/lo layout.  There is no eager / CPU forward: calling the model without a B200 raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RohmB200Error
+from .heads import InputProcess, OutputProcess, PositionalEncoding, TimestepEmbedder
+
+
+def _precision_from_env():
+    v = os.environ.get("ROHM_B200_PRECISION", "tf32x3").lower()
+    if v in ("tf32x3", "3xtf32", "fp32", "parity"):
+        return _lib.PRECISION_TF32X3
+    if v in ("tf32", "fast"):
+        return _lib.PRECISION_TF32
+    raise RohmB200Error(f"ROHM_B200_PRECISION={v!r}: expected 'tf32x3' (default, parity) or 'tf32' (fast)")
+
+
+class PoseNetEngine:
+    """Owns one rohm_posenet handle (device weights + workspace) sized for (max_batch, max_frames)."""
+
+    def __init__(self, module, device, max_batch, max_frames, precision):
+        self.lib = _lib.load()
+        self.ctx = _lib.ctx(device.index)
+        self.device = device
+        self.max_batch, self.max_frames, self.precision = max_batch, max_frames, precision
+        sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in module.state_dict().items()
+              if not k.startswith("smplx_model.")}
+        self._keep = sd  # keeps the source tensors alive during create (the library copies them)
+        L = module.num_layers
+        layers = (_lib.PoseNetLayerW * L)()
+        for l in range(L):
+            p = f"seqTransEncoder.layers.{l}."
+            for field, key in (("in_proj_w", "self_attn.in_proj_weight"), ("in_proj_b", "self_attn.in_proj_bias"),
+                               ("out_proj_w", "self_attn.out_proj.weight"), ("out_proj_b", "self_attn.out_proj.bias"),
+                               ("lin1_w", "linear1.weight"), ("lin1_b", "linear1.bias"),
+                               ("lin2_w", "linear2.weight"), ("lin2_b", "linear2.bias"),
+                               ("norm1_w", "norm1.weight"), ("norm1_b", "norm1.bias"),
+                               ("norm2_w", "norm2.weight"), ("norm2_b", "norm2.bias")):
+                setattr(layers[l], field, sd[p + key].data_ptr())
+        pe = sd["sequence_pos_encoder.pe"].reshape(-1, module.latent_dim).contiguous()
+        self._keep["__pe2d"] = pe
+        w = _lib.PoseNetW()
+        w.d_model, w.ff_size, w.num_layers, w.num_heads = module.latent_dim, module.ff_size, L, module.num_heads
+        w.in_feats, w.out_feats, w.traj_feats = module.input_feats, module.output_process.output_feats, module.traj_feat_dim
+        w.pe_len = pe.shape[0]
+        for field, key in (("in_w", "input_process.poseEmbedding.weight"), ("in_b", "input_process.poseEmbedding.bias"),
+                           ("cond_w", "input_process_cond.poseEmbedding.weight"),
+                           ("cond_b", "input_process_cond.poseEmbedding.bias"),
+                           ("t0_w", "embed_timestep.time_embed.0.weight"), ("t0_b", "embed_timestep.time_embed.0.bias"),
+                           ("t2_w", "embed_timestep.time_embed.2.weight"), ("t2_b", "embed_timestep.time_embed.2.bias"),
+                           ("out_w", "output_process.poseFinal.weight"), ("out_b", "output_process.poseFinal.bias")):
+            setattr(w, field, sd[key].data_ptr())
+        w.pe = pe.data_ptr()
+        w.layers = layers
+        if w.in_feats != w.traj_feats + w.out_feats:
+            raise RohmB200Error(f"PoseNet: body_feat_dim ({w.in_feats}) must equal traj_feat_dim ({w.traj_feats}) + "
+                                f"pose_feat_dim ({w.out_feats})")
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.rohm_posenet_create(self.ctx, C.byref(w), max_batch, max_frames, precision, C.byref(handle))
+        _lib.check(rc, self.ctx)
+        self.handle = handle
+        self._keep = None  # the library owns its copies now
+        self.cond_key = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.rohm_posenet_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_cond(self, cond):
+        B, _, _, T = cond.shape
+        rc = self.lib.rohm_posenet_set_cond(self.handle, C.c_void_p(cond.data_ptr()), B, T, self._stream())
+        _lib.check(rc, self.ctx)
+
+    def forward(self, x_t, timesteps, out=None):
+        B, _, _, T = x_t.shape
+        if out is None:
+            out = torch.empty_like(x_t)
+        rc = self.lib.rohm_posenet_forward(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(timesteps.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), B, T, self._stream())
+        _lib.check(rc, self.ctx)
+        return out
+
+    @property
+    def launches_per_forward(self):
+        return int(self.lib.rohm_posenet_launches_per_forward(self.handle))
+
+
+def _create_body_model(body_model_path, device):
+    """The SMPL-X body model submodule (reference posenet.py:57-58).  Uses the real ``smplx`` package when it is
+    installed (so checkpoint keys under ``smplx_model.*`` match); otherwise the package's own BodyModel."""
+    try:
+        import smplx  # noqa: F401  third-party, optional
+        m = smplx.create(model_path=body_model_path, model_type="smplx", gender='neutral', flat_hand_mean=True,
+                         use_pca=False)
+        return m.to(device) if device is not None else m
+    except ImportError:
+        from .body_model import BodyModel
+        return BodyModel.create(body_model_path, device=device)
+
+
+class PoseNet(nn.Module):
+    def __init__(self, dataset, body_feat_dim, nfeats=1,
+                 latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1, activation="gelu",
+                 body_model_path='',
+                 device=None,
+                 traj_feat_dim=4,
+                 weight_loss_rec_repr_full_body=0.0,
+                 weight_loss_repr_foot_contact_mse=0.0,
+                 weight_loss_joint_pos_global=0.0,
+                 weight_loss_joint_vel_global=0.0, weight_loss_joint_smooth=0.0,
+                 weight_loss_foot_skating=0.0,
+                 start_skating_loss_epoch=0,
+                 ):
+        super().__init__()
+        if activation != "gelu":
+            raise RohmB200Error("PoseNet: only activation='gelu' (the configuration RoHM ships) is implemented")
+        self.dataset = dataset
+        self.body_feat_dim = body_feat_dim
+        self.nfeats = nfeats
+        self.traj_feat_dim = traj_feat_dim
+        self.foot_joint_index_list = [7, 10, 8, 11]  # left ankle, left toe, right ankle, right toe
+        self.foot_skating_vel_thres = 0.1
+        self.fps = 30
+        self.latent_dim = latent_dim
+        self.ff_size = ff_size
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.activation = activation
+        self.input_feats = self.body_feat_dim * self.nfeats
+        self.normalize_output = False
+        self.device = device
+        self.weight_loss_rec_repr_full_body = weight_loss_rec_repr_full_body
+        self.weight_loss_repr_foot_contact_mse = weight_loss_repr_foot_contact_mse
+        self.weight_loss_joint_pos_global = weight_loss_joint_pos_global
+        self.weight_loss_joint_vel_global = weight_loss_joint_vel_global
+        self.weight_loss_joint_smooth = weight_loss_joint_smooth
+        self.weight_loss_foot_skating = weight_loss_foot_skating
+        self.start_skating_loss_epoch = start_skating_loss_epoch
+
+        self.smplx_model = _create_body_model(body_model_path, device)
+        self.input_process = InputProcess(self.input_feats, self.latent_dim)
+        self.input_process_cond = InputProcess(self.input_feats, self.latent_dim)
+        self.sequence_pos_encoder = PositionalEncoding(self.latent_dim, self.dropout)
+        enc_layer = nn.TransformerEncoderLayer(d_model=self.latent_dim, nhead=self.num_heads,
+                                               dim_feedforward=self.ff_size, dropout=self.dropout,
+                                               activation=self.activation)
+        self.seqTransEncoder = nn.TransformerEncoder(enc_layer, num_layers=self.num_layers,
+                                                     enable_nested_tensor=False)
+        self.embed_timestep = TimestepEmbedder(self.latent_dim, self.sequence_pos_encoder)
+        self.output_process = OutputProcess(self.dataset.pose_feat_dim, self.latent_dim, self.nfeats)
+
+        self.precision = None  # None -> ROHM_B200_PRECISION env (default tf32x3)
+        self._engine = None
+        self._engine_fingerprint = None
+
+    # ---------------------------------------------------------------- engine management
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_engine(self):
+        """Forces the weights to be repacked on the next forward (call after mutating parameters in place)."""
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine(self, B, T, device):
+        if self.training:
+            raise RohmB200Error("PoseNet: the CUDA engine implements the inference path (model.eval()); training is "
+                                "out of scope")
+        prec = self.precision if self.precision is not None else _precision_from_env()
+        e = self._engine
+        if (e is None or e.device != device or B > e.max_batch or T > e.max_frames or e.precision != prec):
+            mb = max(B, e.max_batch if e is not None and e.device == device else 0)
+            mf = max(T, e.max_frames if e is not None and e.device == device else 0)
+            self._engine = None
+            e = PoseNetEngine(self, device, mb, mf, prec)
+            self._engine = e
+            self._engine_fingerprint = self._fingerprint()
+        return e
+
+    def prepare_cond(self, cond):
+        """Runs the step-invariant part of the forward for this condition tensor if it is new or was modified."""
+        if cond.device.type != "cuda":
+            raise RohmB200Error("PoseNet: batch tensors must live on a CUDA device (no CPU path)")
+        B, Cc, _, T = cond.shape
+        e = self.engine(B, T, cond.device)
+        key = (cond.data_ptr(), cond._version, tuple(cond.shape), tuple(cond.stride()))
+        if e.cond_key != key:
+            fp = self._fingerprint()  # parameters are re-checked once per new condition, not per step
+            if fp != self._engine_fingerprint:
+                self._engine = None
+                e = self.engine(B, T, cond.device)
+            c = cond if (cond.is_contiguous() and cond.dtype == torch.float32) else cond.contiguous().float()
+            e.set_cond(c)
+            e.cond_key = key
+        return e
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, batch, timesteps):
+        """batch['x_t'], batch['cond']: [bs, body_feat_dim, 1, T]; timesteps: [bs] int -> [bs, body_feat_dim, 1, T]
+        (channels [0, traj_feat_dim) are batch['cond'][:, :traj_feat_dim], the rest is the denoised pose)."""
+        x_t, cond = batch['x_t'], batch['cond']
+        if x_t.dim() != 4 or x_t.shape[2] != 1 or x_t.shape != cond.shape or x_t.shape[1] != self.input_feats:
+            raise RohmB200Error(f"PoseNet: expected x_t/cond of shape [B, {self.input_feats}, 1, T], got "
+                                f"{tuple(x_t.shape)} / {tuple(cond.shape)}")
+        e = self.prepare_cond(cond)
+        x = x_t if (x_t.is_contiguous() and x_t.dtype == torch.float32) else x_t.contiguous().float()
+        ts = timesteps.to(device=x.device, dtype=torch.int64).contiguous()
+        return e.forward(x, ts)
