@@ -136,6 +136,12 @@ ROHM_API int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B, i
 ROHM_API int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                          void* stream);
 
+/* Same as rohm_posenet_forward but with CUDA events recorded on `stream` around every kernel launch; synchronises the
+ * stream and returns, per category {0: tensor-core GEMM, 1: attention, 2: LayerNorm, 3: pack/unpack/time-token}, the
+ * summed device milliseconds (host float[4]) and the number of launches (host int[4]).  For bench.py's roofline. */
+ROHM_API int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
+                         void* stream, float* ms_by_category, int* launches_by_category);
+
 /* Kernel launches issued by the last forward (for bench.py's gpu_launches accounting). */
 ROHM_API int rohm_posenet_launches_per_forward(const rohm_posenet* pn);
 

@@ -337,10 +337,31 @@ struct rohm_posenet {
   float* cond_traj = nullptr;  // [B, traj, T] copy of cond[:, :traj] taken by set_cond (output channels [0,traj))
   int cond_B = -1, cond_T = -1;
   int launches = 0;
+  // optional per-kernel event timing (rohm_posenet_profile): category -> list of (start, stop) events
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_cat;
   // GEMM parameter blocks (tensor maps are built once; only the grid depends on B*S)
   GemmParams g_in{}, g_cond{}, g_out{};
   std::vector<GemmParams> g_qkv, g_proj, g_ff1, g_ff2;
 };
+
+enum ProfCat { kCatGemm = 0, kCatAttention = 1, kCatLayerNorm = 2, kCatOther = 3, kNumCats = 4 };
+
+static void prof_begin(rohm_posenet* pn, int cat, cudaStream_t st) {
+  if (!pn->profiling) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  pn->prof_events.push_back(a);
+  pn->prof_events.push_back(b);
+  pn->prof_cat.push_back(cat);
+  cudaEventRecord(a, st);
+}
+static void prof_end(rohm_posenet* pn, cudaStream_t st) {
+  if (!pn->profiling) return;
+  cudaEventRecord(pn->prof_events.back(), st);
+}
 
 static int pick_block_n(int N) {
   if (N % 128 == 0) return 128;
@@ -412,7 +433,9 @@ static int setup_linear(rohm_posenet* pn, GemmParams* g, const float* a_hi, cons
 
 static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int rows, cudaStream_t st) {
   g.M = rows;
+  prof_begin(pn, kCatGemm, st);
   ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st));
+  prof_end(pn, st);
   pn->launches++;
   return ROHM_OK;
 }
@@ -425,6 +448,7 @@ static void launch_ln(const float* in, const float* g, const float* b, float* ou
 
 static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
            cudaStream_t st) {
+  prof_begin(pn, kCatLayerNorm, st);
   switch (pn->D) {
     case 128: launch_ln<128>(in, g, b, out, oh, ol, rows, st); break;
     case 256: launch_ln<256>(in, g, b, out, oh, ol, rows, st); break;
@@ -432,6 +456,7 @@ static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float
     case 1024: launch_ln<1024>(in, g, b, out, oh, ol, rows, st); break;
     default: return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported d_model %d for LayerNorm", pn->D);
   }
+  prof_end(pn, st);
   ROHM_CUDA(pn->ctx, cudaGetLastError());
   pn->launches++;
   return ROHM_OK;
@@ -441,6 +466,7 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   const int dh = pn->D / pn->H;
   const size_t smem = attention_smem_bytes(S, dh);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  prof_begin(pn, kCatAttention, st);
   if (dh == 128) {
     attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
   } else if (dh == 64) {
@@ -448,6 +474,7 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   } else {
     return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
   }
+  prof_end(pn, st);
   ROHM_CUDA(pn->ctx, cudaGetLastError());
   pn->launches++;
   return ROHM_OK;
@@ -638,12 +665,16 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   int rc;
 
   dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
+  prof_begin(pn, kCatOther, st);
   pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p);
+  prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
   if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
+  prof_begin(pn, kCatOther, st);
   time_token_kernel<<<B, 256, 2 * D * sizeof(float), st>>>(timesteps, pn->pe, pn->pe_len, pn->t0_w, pn->t0_b, pn->t2_w,
                                                           pn->t2_b, pn->X, pn->Xh, pn->Xl, S, D);
+  prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
 
@@ -659,9 +690,39 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   }
   if ((rc = run_gemm(pn, pn->g_out, pn->w_out, rows, st)) != ROHM_OK) return rc;
   dim3 grid_o((T + 31) / 32, (pn->Cout + 31) / 32, B);
+  prof_begin(pn, kCatOther, st);
   unpack_tokens_kernel<<<grid_o, dim3(32, 8), 0, st>>>(pn->OUT, pn->cond_traj, out, pn->C, pn->Cout, pn->traj, T, S,
                                                       pn->Cout);
+  prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
+  return ROHM_OK;
+}
+
+// One forward with CUDA events around every kernel launch (on `stream`, the launching stream); synchronises and
+// returns the summed device time and launch count per category {GEMM, attention, LayerNorm, other}.
+extern "C" int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
+                                    int T, void* stream, float* ms_by_category, int* launches_by_category) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  if (ms_by_category == nullptr || launches_by_category == nullptr)
+    return fail(pn->ctx, ROHM_ERR_INVALID, "rohm_posenet_profile: null output");
+  pn->profiling = true;
+  pn->prof_events.clear();
+  pn->prof_cat.clear();
+  int rc = rohm_posenet_forward(pn, x_t, timesteps, out, B, T, stream);
+  pn->profiling = false;
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  for (int c = 0; c < kNumCats; ++c) ms_by_category[c] = 0.0f, launches_by_category[c] = 0;
+  for (size_t i = 0; i < pn->prof_cat.size(); ++i) {
+    float ms = 0.0f;
+    if (rc == ROHM_OK && e == cudaSuccess) cudaEventElapsedTime(&ms, pn->prof_events[2 * i], pn->prof_events[2 * i + 1]);
+    ms_by_category[pn->prof_cat[i]] += ms;
+    launches_by_category[pn->prof_cat[i]]++;
+  }
+  for (cudaEvent_t ev : pn->prof_events) cudaEventDestroy(ev);
+  pn->prof_events.clear();
+  pn->prof_cat.clear();
+  if (rc != ROHM_OK) return rc;
+  ROHM_CUDA(pn->ctx, e);
   return ROHM_OK;
 }

@@ -1,0 +1,3 @@
+"""Shadows the reference's diffusion/gaussian_diffusion_trajnet.py with the B200 implementation."""
+from rohm_b200.diffusion import (GaussianDiffusionTrajNet, LossType, ModelMeanType, ModelVarType,  # noqa: F401
+                                 betas_for_alpha_bar, get_named_beta_schedule)

@@ -100,6 +100,18 @@ class PoseNetEngine:
         _lib.check(rc, self.ctx)
         return out
 
+    def profile(self, x_t, timesteps):
+        """One forward with per-kernel CUDA-event timing -> ({category: ms}, {category: launches})."""
+        B, _, _, T = x_t.shape
+        out = torch.empty_like(x_t)
+        ms = (C.c_float * 4)()
+        n = (C.c_int * 4)()
+        rc = self.lib.rohm_posenet_profile(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(timesteps.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), B, T, self._stream(), ms, n)
+        _lib.check(rc, self.ctx)
+        names = ("gemm", "attention", "layernorm", "other")
+        return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
     @property
     def launches_per_forward(self):
         return int(self.lib.rohm_posenet_launches_per_forward(self.handle))

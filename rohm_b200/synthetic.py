@@ -90,7 +90,7 @@ def plausible_motion(B, T, seed, dataset=None):
     x = torch.randn(B, T, BODY_FEAT_DIM, generator=g)
     aa = 0.3 * torch.randn(B, T, 22, 3, generator=g)
     # smooth over time so that foot velocities are moderate
-    aa = torch.cumsum(aa, dim=1) / np.sqrt(np.arange(1, T + 1, dtype=np.float32))[None, :, None, None]
+    aa = torch.cumsum(aa, dim=1) / torch.from_numpy(np.sqrt(np.arange(1, T + 1, dtype=np.float32)))[None, :, None, None]
     ang = aa.norm(dim=-1, keepdim=True).clamp_min(1e-8)
     k = aa / ang
     K = torch.zeros(B, T, 22, 3, 3)
