@@ -124,11 +124,17 @@ def cpu_port_clips_per_s(sd, n_clips, n_steps, threads):
     return n_clips / (dt / n_steps * DIFFUSION_STEPS), dt
 
 
+def host_threads():
+    """Threads for the CPU legs: every core up to 32 (torch's intra-op pool stops scaling, then collapses, on this
+    workload's GEMM sizes beyond that -- measured 25 s/step with 128 threads on the 128-core GPU host)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     _, sd = build_posenet(None)
     n_clips, n_steps = B_PER_GPU, 4
     vals = []
@@ -295,11 +301,11 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, dt = cpu_port_clips_per_s(sd, B, 12, cores)
+        cores = host_threads()
+        v, dt = cpu_port_clips_per_s(sd, B, 8, cores)
         cpu_baseline = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                        "sample": f"{B} clips x 12 consecutive DDPM steps of the oracle port ({dt:.1f} s), extrapolated "
-                                  f"linearly to 1000 steps"}
+                        "sample": f"{B} clips x 8 consecutive DDPM steps of the oracle port ({dt:.1f} s, {cores} of "
+                                  f"{os.cpu_count()} host threads), extrapolated linearly to 1000 steps"}
 
     if rank == 0:
         line = {

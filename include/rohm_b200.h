@@ -142,6 +142,10 @@ ROHM_API int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int6
 ROHM_API int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                          void* stream, float* ms_by_category, int* launches_by_category);
 
+/* Options: 0 = replay the forward as a CUDA graph (default 1; the graph is captured on first use per (B, T) and its
+ * three caller-memory pointers are patched per call). */
+ROHM_API int rohm_posenet_set_option(rohm_posenet* pn, int option, int value);
+
 /* Kernel launches issued by the last forward (for bench.py's gpu_launches accounting). */
 ROHM_API int rohm_posenet_launches_per_forward(const rohm_posenet* pn);
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "rohm_posenet_set_cond": (_i, [_p, _p, _i, _i, _p]),
     "rohm_posenet_forward": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "rohm_posenet_profile": (_i, [_p, _p, _p, _p, _i, _i, _p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "rohm_posenet_set_option": (_i, [_p, _i, _i]),
     "rohm_posenet_launches_per_forward": (_i, [_p]),
 }
 

@@ -10,7 +10,8 @@ namespace rohm {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSmemBudget = 200 * 1024;  // ring buffer budget; + 1 KB alignment slack stays below 227 KB
 
 template <int BLOCK_N, int PASSES>
@@ -22,12 +23,16 @@ struct TileCfg {
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-  // PASSES == 3 keeps two accumulators: columns [0, BLOCK_N) take the leading hi*hi products, columns
+  // PASSES == 3 keeps two accumulators per stage: columns [0, BLOCK_N) take the leading hi*hi products, columns
   // [BLOCK_N, 2*BLOCK_N) the two small cross terms.  The tensor core truncates when it adds into the
   // accumulator, so keeping the ~2^-11-sized terms out of the big sum cuts the rounding count of the main
   // accumulator by 3x (measured: error grows linearly with the number of accumulating MMAs).
   static constexpr int kAccCols = (PASSES == 3 ? 2 : 1) * BLOCK_N;
-  static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
+  // two accumulator stages: the epilogue drains tile i while the MMA warp already accumulates tile i+1
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemNeed = kAccStages * kAccCols;
+  static constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "accumulators exceed TMEM");
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
   static_assert(BLOCK_N % 32 == 0, "epilogue walks TMEM in 32-column chunks");
@@ -46,13 +51,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
+// (N-tile index fastest, so CTAs running concurrently share the same A rows in L2).
 template <int BLOCK_N, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[Cfg::kStages];
   __shared__ uint64_t empty_bar[Cfg::kStages];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tmem_full_bar[Cfg::kAccStages];
+  __shared__ uint64_t tmem_empty_bar[Cfg::kAccStages];
   __shared__ uint32_t tmem_base_smem;
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -61,8 +69,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kGemmBlockM;
-  const int n0 = blockIdx.x * BLOCK_N;
+  const int tiles_n = (p.grid_n_cols + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (p.grid_m_rows + kGemmBlockM - 1) / kGemmBlockM;
+  const int num_tiles = tiles_m * tiles_n;
 
   int total_iters = 0;
   for (int s = 0; s < p.num_segs; ++s) total_iters += p.seg_kblocks[s];
@@ -78,7 +87,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
-    ptx::mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < Cfg::kAccStages; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -96,20 +108,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int s = 0; s < p.num_segs; ++s) {
-        const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
-        const int nkb = p.seg_kblocks[s];
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int stage = it % Cfg::kStages;
-          const uint32_t phase = (it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kGemmBlockK, row);
-          ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], it * kGemmBlockK, n0);
-          if (PASSES == 3) {
-            ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kGemmBlockK, row);
-            ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], it * kGemmBlockK, n0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kGemmBlockM;
+        const int n0 = (tile % tiles_n) * BLOCK_N;
+        int kcol = 0;
+        for (int s = 0; s < p.num_segs; ++s) {
+          const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
+          const int nkb = p.seg_kblocks[s];
+          for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kGemmBlockK) {
+            const int stage = it % Cfg::kStages;
+            const uint32_t phase = (it / Cfg::kStages) & 1;
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kGemmBlockK, row);
+            ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], kcol, n0);
+            if (PASSES == 3) {
+              ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kGemmBlockK, row);
+              ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], kcol, n0);
+            }
           }
         }
       }
@@ -118,176 +135,205 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc(/*TF32*/ 2, kGemmBlockM, BLOCK_N);
-      for (int it = 0; it < total_iters; ++it) {
-        const int stage = it % Cfg::kStages;
-        const uint32_t phase = (it / Cfg::kStages) & 1;
-        ptx::mbar_wait(&full_bar[stage], phase);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc_stage = tcount % Cfg::kAccStages;
+        const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after_sync();
-        const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t a_hi = ptx::make_desc_sw128_kmajor(st);
-        const uint64_t b_hi = ptx::make_desc_sw128_kmajor(st + Cfg::kSplit * Cfg::kABytes);
-        const uint64_t a_lo = ptx::make_desc_sw128_kmajor(st + Cfg::kABytes);
-        const uint64_t b_lo = ptx::make_desc_sw128_kmajor(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols);
+        for (int ki = 0; ki < total_iters; ++ki, ++it) {
+          const int stage = it % Cfg::kStages;
+          const uint32_t phase = (it / Cfg::kStages) & 1;
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = ptx::make_desc_sw128_kmajor(st);
+          const uint64_t b_hi = ptx::make_desc_sw128_kmajor(st + Cfg::kSplit * Cfg::kABytes);
+          const uint64_t a_lo = ptx::make_desc_sw128_kmajor(st + Cfg::kABytes);
+          const uint64_t b_lo = ptx::make_desc_sw128_kmajor(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
-        for (int k = 0; k < kGemmBlockK / 8; ++k) {
-          // advancing K by 8 fp32 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
-          const uint64_t koff = static_cast<uint64_t>(k * 2);
-          if (PASSES == 3) {
-            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            ptx::mma_tf32_ss(tmem_base + BLOCK_N, a_lo + koff, b_hi + koff, idesc, first);
-            ptx::mma_tf32_ss(tmem_base + BLOCK_N, a_hi + koff, b_lo + koff, idesc, 1u);
-            ptx::mma_tf32_ss(tmem_base, a_hi + koff, b_hi + koff, idesc, first);
-          } else {
-            ptx::mma_tf32_ss(tmem_base, a_hi + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kGemmBlockK / 8; ++k) {
+            // advancing K by 8 fp32 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
+            const uint64_t koff = static_cast<uint64_t>(k * 2);
+            const uint32_t first = (ki > 0 || k > 0) ? 1u : 0u;
+            if (PASSES == 3) {
+              ptx::mma_tf32_ss(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, first);
+              ptx::mma_tf32_ss(acc + BLOCK_N, a_hi + koff, b_lo + koff, idesc, 1u);
+              ptx::mma_tf32_ss(acc, a_hi + koff, b_hi + koff, idesc, first);
+            } else {
+              ptx::mma_tf32_ss(acc, a_hi + koff, b_hi + koff, idesc, first);
+            }
           }
+          ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
-        ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
       }
-      ptx::mma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-    ptx::mbar_wait(&tmem_full_bar, 0);
-    ptx::tc_fence_after_sync();
-
-    const bool row_ok = m < p.M;
-    bool row_real = true;
-    int clip = 0;
-    if (p.clip_rows > 0) {
-      clip = m / p.clip_rows;
-      row_real = (m - clip * p.clip_rows) < p.clip_valid;
-    }
-    const int64_t orow = static_cast<int64_t>(m) * p.out_row_mul + p.out_row_add;
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lane quarter = warp_idx % 4 (hardware rule); the two warps sharing a quarter alternate 32-column chunks.
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;
     const bool vec_ok = ((p.N & 3) == 0);
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / tiles_n) * kGemmBlockM;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      const int acc_stage = tcount % Cfg::kAccStages;
+      const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
+      const int m = m0 + q * 32 + lane;
+      ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      ptx::tc_fence_after_sync();
+
+      const bool row_ok = m < p.M;
+      bool row_real = true;
+      int clip = 0;
+      if (p.clip_rows > 0) {
+        clip = m / p.clip_rows;
+        row_real = (m - clip * p.clip_rows) < p.clip_valid;
+      }
+      const int64_t orow = static_cast<int64_t>(m) * p.out_row_mul + p.out_row_add;
 
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t raw[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-      ptx::tmem_ld_32x32(taddr, raw);
-      ptx::tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (PASSES == 3) {
-        ptx::tmem_ld_32x32(taddr + BLOCK_N, raw);
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
+                               (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+        ptx::tmem_ld_32x32(taddr, raw);
         ptx::tmem_ld_wait();
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
-      }
-      const int nb = n0 + c0;
-      if (nb >= p.N) continue;  // warp-uniform
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (PASSES == 3) {
+          ptx::tmem_ld_32x32(taddr + BLOCK_N, raw);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
+        }
+        const int nb = n0 + c0;
+        if (nb >= p.N) continue;  // warp-uniform
+        const bool full = vec_ok && (nb + 32 <= p.N);
 
-      if (row_ok) {
-        if (p.bias != nullptr) {
+        if (row_ok) {
+          if (p.bias != nullptr) {
+            if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
-        }
-        if (p.act != kActNone) {
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                v[j] += t4.x, v[j + 1] += t4.y, v[j + 2] += t4.z, v[j + 3] += t4.w;
+              }
+            } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-        }
-        if (p.residual != nullptr) {
-          const float* r = p.residual + orow * p.ldr + nb;
-          if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(r + j);
-              v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
             }
-          } else {
+          }
+          if (p.act != kActNone) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) v[j] += r[j];
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.residual != nullptr) {
+            const float* r = p.residual + orow * p.ldr + nb;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(r + j);
+                v[j] += t4.x, v[j + 1] += t4.y, v[j + 2] += t4.z, v[j + 3] += t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) v[j] += r[j];
+            }
+          }
+          if (!row_real) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
           }
         }
-        if (!row_real) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-        }
-      }
 
-      // ---- GroupNorm partial statistics over real rows ----
-      if (p.gn_stats != nullptr) {
-        const int gs = p.gn_group_size;
-        const bool contrib = row_ok && row_real;
-        const int clip0 = __shfl_sync(0xffffffffu, clip, 0);
-        const bool uniform = __all_sync(0xffffffffu, clip == clip0);
-        for (int jg = 0; jg < 32 && nb + jg < p.N; jg += (gs < 32 ? gs : 32)) {
-          const int span = gs < 32 ? gs : 32;
-          float s1 = 0.0f, s2 = 0.0f;
-          if (contrib) {
+        // ---- GroupNorm partial statistics over real rows ----
+        if (p.gn_stats != nullptr) {
+          const int gs = p.gn_group_size;
+          const bool contrib = row_ok && row_real;
+          const int clip0 = __shfl_sync(0xffffffffu, clip, 0);
+          const bool uniform = __all_sync(0xffffffffu, clip == clip0);
+          for (int jg = 0; jg < 32 && nb + jg < p.N; jg += (gs < 32 ? gs : 32)) {
+            const int span = gs < 32 ? gs : 32;
+            float s1 = 0.0f, s2 = 0.0f;
+            if (contrib) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j >= jg && j < jg + span && nb + j < p.N) {
-                s1 += v[j];
-                s2 += v[j] * v[j];
+              for (int j = 0; j < 32; ++j) {
+                if (j >= jg && j < jg + span && nb + j < p.N) {
+                  s1 += v[j];
+                  s2 += v[j] * v[j];
+                }
               }
             }
-          }
-          const int g = (nb + jg) / gs;
-          if (uniform) {
+            const int g = (nb + jg) / gs;
+            if (uniform) {
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-              s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-            }
-            if (lane == 0) {
-              double* dst = p.gn_stats + (static_cast<int64_t>(clip0) * p.gn_groups + g) * 2;
+              for (int off = 16; off > 0; off >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+              }
+              if (lane == 0) {
+                double* dst = p.gn_stats + (static_cast<int64_t>(clip0) * p.gn_groups + g) * 2;
+                atomicAdd(dst, static_cast<double>(s1));
+                atomicAdd(dst + 1, static_cast<double>(s2));
+              }
+            } else if (contrib) {
+              double* dst = p.gn_stats + (static_cast<int64_t>(clip) * p.gn_groups + g) * 2;
               atomicAdd(dst, static_cast<double>(s1));
               atomicAdd(dst + 1, static_cast<double>(s2));
             }
-          } else if (contrib) {
-            double* dst = p.gn_stats + (static_cast<int64_t>(clip) * p.gn_groups + g) * 2;
-            atomicAdd(dst, static_cast<double>(s1));
-            atomicAdd(dst + 1, static_cast<double>(s2));
           }
         }
-      }
 
-      if (row_ok) {
-        const bool full = vec_ok && (nb + 32 <= p.N);
-        if (p.out != nullptr) {
-          float* o = p.out + orow * p.ldo + nb;
-          if (full) {
+        if (row_ok) {
+          if (p.out != nullptr) {
+            float* o = p.out + orow * p.ldo + nb;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) o[j] = v[j];
-          }
-        }
-        if (p.out_hi != nullptr) {
-          float* oh = p.out_hi + orow * p.lds + nb;
-          float* ol = p.out_lo + orow * p.lds + nb;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 h, l;
-              h.x = ptx::to_tf32(v[j]), h.y = ptx::to_tf32(v[j + 1]);
-              h.z = ptx::to_tf32(v[j + 2]), h.w = ptx::to_tf32(v[j + 3]);
-              l.x = v[j] - h.x, l.y = v[j + 1] - h.y, l.z = v[j + 2] - h.z, l.w = v[j + 3] - h.w;
-              *reinterpret_cast<float4*>(oh + j) = h;
-              *reinterpret_cast<float4*>(ol + j) = l;
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) o[j] = v[j];
             }
-          } else {
+          }
+          if (p.out_hi != nullptr) {
+            float* oh = p.out_hi + orow * p.lds + nb;
+            float* ol = p.out_lo + orow * p.lds + nb;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) {
-                const float h = ptx::to_tf32(v[j]);
-                oh[j] = h;
-                ol[j] = v[j] - h;
+              for (int j = 0; j < 32; j += 4) {
+                float4 h, l;
+                h.x = ptx::to_tf32(v[j]), h.y = ptx::to_tf32(v[j + 1]);
+                h.z = ptx::to_tf32(v[j + 2]), h.w = ptx::to_tf32(v[j + 3]);
+                l.x = v[j] - h.x, l.y = v[j + 1] - h.y, l.z = v[j + 2] - h.z, l.w = v[j + 3] - h.w;
+                *reinterpret_cast<float4*>(oh + j) = h;
+                *reinterpret_cast<float4*>(ol + j) = l;
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) {
+                  const float h = ptx::to_tf32(v[j]);
+                  oh[j] = h;
+                  ol[j] = v[j] - h;
+                }
+            }
           }
         }
       }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above): hand it back
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
     }
-    ptx::tc_fence_before_sync();
   }
 
   __syncthreads();
@@ -327,13 +373,23 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   auto kern = gemm_tile_kernel<BLOCK_N, PASSES>;
   static bool attr_set = false;
-  if (!attr_set) {
+  if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  GemmParams q = p;
+  q.grid_m_rows = m_rows;
+  q.grid_n_cols = n_cols;
+  const int tiles = ((n_cols + BLOCK_N - 1) / BLOCK_N) * ((m_rows + kGemmBlockM - 1) / kGemmBlockM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((n_cols + BLOCK_N - 1) / BLOCK_N, (m_rows + kGemmBlockM - 1) / kGemmBlockM, 1);
+  cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -342,7 +398,7 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, p);
+  return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
 }  // namespace
@@ -378,6 +434,25 @@ cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n
       return cudaErrorInvalidValue;
   }
 #undef ROHM_GEMM_CASE
+}
+
+template <int BLOCK_N, int PASSES>
+static cudaError_t set_attr() {
+  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+}
+
+cudaError_t gemm_init_attributes() {
+  cudaError_t e;
+  if ((e = set_attr<32, 1>()) != cudaSuccess) return e;
+  if ((e = set_attr<32, 3>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
+  if ((e = set_attr<96, 1>()) != cudaSuccess) return e;
+  if ((e = set_attr<96, 3>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {

@@ -12,10 +12,11 @@
 // * PASSES == 3: D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (drops only the lo*lo term, ~2^-22 relative).
 //   PASSES == 1: D += A_hi*W_hi (plain TF32, ~2^-11 relative) -- the documented fast mode.
 //
-// Kernel shape: one 128 x BLOCK_N output tile per CTA, 192 threads:
+// Kernel shape: persistent, grid = min(#tiles, #SMs), 128 x BLOCK_N output tiles, 320 threads per CTA:
 //   warp 0   : TMA producer (one elected lane)        smem ring: full[]/empty[] mbarriers
-//   warp 1   : TMEM allocator + tcgen05.mma issuer    accumulator: BLOCK_N fp32 columns x 128 lanes in TMEM
-//   warps 2-5: epilogue (tcgen05.ld -> bias/act/residual -> global, optional hi/lo split for the next GEMM)
+//   warp 1   : TMEM allocator + tcgen05.mma issuer    two accumulator stages in TMEM (tmem_full[]/tmem_empty[])
+//   warps 2-9: epilogue (tcgen05.ld -> bias/act/residual -> global, optional hi/lo split for the next GEMM),
+//              draining tile i while the MMA warp already accumulates tile i+1
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -60,6 +61,9 @@ struct alignas(64) GemmParams {
   double* gn_stats;  // [num_clips, gn_groups, 2] or nullptr
   int gn_groups;
   int gn_group_size;  // channels per group
+  // filled in by launch_gemm: extent of the tile grid
+  int grid_m_rows;
+  int grid_n_cols;
 };
 
 // Host side ------------------------------------------------------------------------------------
@@ -73,6 +77,10 @@ int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
 // grid = ceil(M_tiles) x ceil(N_tiles) where M_tiles covers `m_rows` GEMM rows.
 cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n, int passes, cudaStream_t stream,
                         bool pdl = false);
+
+// Raises the dynamic shared-memory limit of every kernel instantiation (call once per process, outside any stream
+// capture).
+cudaError_t gemm_init_attributes();
 
 // fp32 -> (hi, lo) TF32 split, elementwise; n elements.
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);

@@ -82,51 +82,31 @@ __global__ void pe_rows_kernel(const float* __restrict__ pe, float* __restrict__
   reinterpret_cast<float4*>(rows)[i] = reinterpret_cast<const float4*>(pe)[static_cast<int64_t>(s) * d4 + c];
 }
 
-// TimestepEmbedder (heads.py:132-146): e = W2 silu(W0 pe[t_b] + b0) + b2; token row (b, 0) = e + pe[0].
-// One CTA per clip, 8 warps, each output is a warp-wide dot product.
-__global__ void __launch_bounds__(256) time_token_kernel(const int64_t* __restrict__ timesteps,
-                                                         const float* __restrict__ pe, int pe_len,
-                                                         const float* __restrict__ w0, const float* __restrict__ b0,
-                                                         const float* __restrict__ w2, const float* __restrict__ b2,
-                                                         float* __restrict__ X, float* __restrict__ Xh,
-                                                         float* __restrict__ Xl, int S, int D) {
-  extern __shared__ float sm[];  // v[D], h[D]
-  float* v = sm;
-  float* h = sm + D;
+// TimestepEmbedder (heads.py:132-146): e(t) = W2 silu(W0 pe[t] + b0) + b2 depends on the timestep only, so the whole
+// table TE[t] = e(t) + pe[0] (the positional row of token 0) is computed once per weight set at create time (two GEMMs
+// over all pe_len timesteps); per step the token row (b, 0) is a gather.
+__global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, const float* __restrict__ table,
+                                         int table_rows, float* __restrict__ X, float* __restrict__ Xh,
+                                         float* __restrict__ Xl, int S, int D) {
   const int b = blockIdx.x;
   int64_t t = timesteps[b];
-  if (t < 0) t = 0;
-  if (t >= pe_len) t = pe_len - 1;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) v[i] = pe[t * D + i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < D; n += nw) {
-    const float* w = w0 + static_cast<int64_t>(n) * D;
-    float acc = 0.0f;
-    for (int k = lane; k < D; k += 32) acc = fmaf(w[k], v[k], acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      const float z = acc + b0[n];
-      h[n] = z / (1.0f + expf(-z));
-    }
+  t = t < 0 ? 0 : (t >= table_rows ? table_rows - 1 : t);
+  const float4* src = reinterpret_cast<const float4*>(table + t * D);
+  const int64_t o = static_cast<int64_t>(b) * S * D;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 v = src[i];
+    float4 h, l;
+    h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
+    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    reinterpret_cast<float4*>(X + o)[i] = v;
+    reinterpret_cast<float4*>(Xh + o)[i] = h;
+    reinterpret_cast<float4*>(Xl + o)[i] = l;
   }
-  __syncthreads();
-  for (int n = warp; n < D; n += nw) {
-    const float* w = w2 + static_cast<int64_t>(n) * D;
-    float acc = 0.0f;
-    for (int k = lane; k < D; k += 32) acc = fmaf(w[k], h[k], acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      const float e = (acc + b2[n]) + pe[n];  // + pe[0][n]
-      const int64_t o = static_cast<int64_t>(b) * S * D + n;
-      const float hh = ptx::to_tf32(e);
-      X[o] = e;
-      Xh[o] = hh;
-      Xl[o] = e - hh;
-    }
-  }
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
 }
 
 // LayerNorm over the last dim (eps 1e-5), one warp per row; writes fp32 and the TF32 hi/lo pair.
@@ -299,6 +279,170 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
 }
 
+// ---- tensor-core attention (v2) -------------------------------------------------------------------------------
+// One CTA per (clip, head); warp w owns query rows [16w, 16w+16).  S = Q K^T and O = P V run on mma.sync m16n8k8
+// TF32 with the same 3-pass hi/lo error compensation as the GEMMs; logits, softmax and P never leave registers
+// (the S accumulator fragment is reused as the A fragment of P V by enumerating the 8 keys of a k-step in the
+// order the accumulator holds them, so no shuffle or shared-memory round trip is needed).
+// K and V of the head are staged once in shared memory with a 132-float row pitch (conflict-free fragment loads);
+// Q fragments are read straight from global/L2 (each value is used exactly once).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const float h = ptx::to_tf32(x);
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(x - h);
+}
+
+constexpr int kAttnPitch = 132;
+
+template <int DH, int NT>  // NT = number of 8-key tiles (keys padded to 8*NT), rows padded to 16 * warps
+__global__ void __launch_bounds__(32 * ((NT + 1) / 2)) attention_mma_kernel(const float* __restrict__ qkv,
+                                                                          float* __restrict__ ctx_hi,
+                                                                          float* __restrict__ ctx_lo, int S, int D,
+                                                                          int H, float scale) {
+  extern __shared__ float sm[];
+  float* Ks = sm;                          // [8*NT][kAttnPitch]
+  float* Vs = Ks + 8 * NT * kAttnPitch;    // [8*NT][kAttnPitch]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t base = static_cast<int64_t>(b) * S;
+  const int ld = 3 * D;
+
+  for (int i = threadIdx.x; i < 8 * NT * (DH / 4); i += blockDim.x) {
+    const int s = i / (DH / 4), c = i % (DH / 4);
+    float4 k = make_float4(0.f, 0.f, 0.f, 0.f), v = k;
+    if (s < S) {
+      const float* row = qkv + (base + s) * ld + h * DH + c * 4;
+      k = *reinterpret_cast<const float4*>(row + D);
+      v = *reinterpret_cast<const float4*>(row + 2 * D);
+    }
+    *reinterpret_cast<float4*>(Ks + s * kAttnPitch + c * 4) = k;
+    *reinterpret_cast<float4*>(Vs + s * kAttnPitch + c * 4) = v;
+  }
+
+  const int r0 = warp * 16;
+  const int rowA = min(r0 + g, S - 1), rowB = min(r0 + g + 8, S - 1);
+  const float* qA = qkv + (base + rowA) * ld + h * DH;
+  const float* qB = qkv + (base + rowB) * ld + h * DH;
+  // all Q fragments of this warp: [k-step][a0..a3] = Q[rowA][8k+t], Q[rowB][8k+t], Q[rowA][8k+t+4], Q[rowB][8k+t+4]
+  float qf[DH / 8][4];
+#pragma unroll
+  for (int k = 0; k < DH / 8; ++k) {
+    qf[k][0] = __ldg(qA + 8 * k + t);
+    qf[k][1] = __ldg(qB + 8 * k + t);
+    qf[k][2] = __ldg(qA + 8 * k + t + 4);
+    qf[k][3] = __ldg(qB + 8 * k + t + 4);
+  }
+  __syncthreads();
+
+  // ---- S = Q K^T ----
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < DH / 8; ++k) {
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(qf[k][i], ah[i], al[i]);
+    const float* kp = Ks + g * kAttnPitch + 8 * k + t;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      uint32_t bh[2], bl[2];
+      split_tf32(kp[j * 8 * kAttnPitch], bh[0], bl[0]);
+      split_tf32(kp[j * 8 * kAttnPitch + 4], bh[1], bl[1]);
+      mma_tf32_16x8x8(acc[j], al, bh);
+      mma_tf32_16x8x8(acc[j], ah, bl);
+      mma_tf32_16x8x8(acc[j], ah, bh);
+    }
+  }
+
+  // ---- softmax over keys (rows rowA: elements [0],[1]; rowB: [2],[3]; columns 8j + 2t + {0,1}) ----
+  float mxA = -INFINITY, mxB = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = (8 * j + 2 * t + e) < S;
+      acc[j][e] = ok ? acc[j][e] * scale : -INFINITY;
+      acc[j][2 + e] = ok ? acc[j][2 + e] * scale : -INFINITY;
+      mxA = fmaxf(mxA, acc[j][e]);
+      mxB = fmaxf(mxB, acc[j][2 + e]);
+    }
+  }
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+  float sumA = 0.0f, sumB = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      acc[j][e] = expf(acc[j][e] - mxA);      // exp(-inf) = 0 for padded keys
+      acc[j][2 + e] = expf(acc[j][2 + e] - mxB);
+      sumA += acc[j][e];
+      sumB += acc[j][2 + e];
+    }
+  }
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
+  const float invA = 1.0f / sumA, invB = 1.0f / sumB;
+
+  // ---- O = P V ----
+  // A fragment of k-step j (keys 8j..8j+7, enumerated as column t -> key 8j+2t, column t+4 -> key 8j+2t+1):
+  //   a0 = P[rowA][8j+2t] = acc[j][0], a1 = P[rowB][8j+2t] = acc[j][2], a2 = acc[j][1], a3 = acc[j][3]
+  // B fragment for output dims 8n..8n+7:  b0 = V[8j+2t][8n+g], b1 = V[8j+2t+1][8n+g]
+  float o[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    uint32_t ah[4], al[4];
+    split_tf32(acc[j][0] * invA, ah[0], al[0]);
+    split_tf32(acc[j][2] * invB, ah[1], al[1]);
+    split_tf32(acc[j][1] * invA, ah[2], al[2]);
+    split_tf32(acc[j][3] * invB, ah[3], al[3]);
+    const float* vp = Vs + (8 * j + 2 * t) * kAttnPitch + g;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      uint32_t bh[2], bl[2];
+      split_tf32(vp[8 * n], bh[0], bl[0]);
+      split_tf32(vp[8 * n + kAttnPitch], bh[1], bl[1]);
+      mma_tf32_16x8x8(o[n], al, bh);
+      mma_tf32_16x8x8(o[n], ah, bl);
+      mma_tf32_16x8x8(o[n], ah, bh);
+    }
+  }
+
+  // ---- store ctx as TF32 hi/lo (o[n][0..1] = row rowA, cols 8n+2t,+1; o[n][2..3] = row rowB) ----
+  const bool okA = (r0 + g) < S, okB = (r0 + g + 8) < S;
+  const int64_t oA = (base + r0 + g) * D + h * DH + 2 * t;
+  const int64_t oB = oA + static_cast<int64_t>(8) * D;
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) {
+    if (okA) {
+      const float h0 = ptx::to_tf32(o[n][0]), h1 = ptx::to_tf32(o[n][1]);
+      *reinterpret_cast<float2*>(ctx_hi + oA + 8 * n) = make_float2(h0, h1);
+      *reinterpret_cast<float2*>(ctx_lo + oA + 8 * n) = make_float2(o[n][0] - h0, o[n][1] - h1);
+    }
+    if (okB) {
+      const float h2 = ptx::to_tf32(o[n][2]), h3 = ptx::to_tf32(o[n][3]);
+      *reinterpret_cast<float2*>(ctx_hi + oB + 8 * n) = make_float2(h2, h3);
+      *reinterpret_cast<float2*>(ctx_lo + oB + 8 * n) = make_float2(o[n][2] - h2, o[n][3] - h3);
+    }
+  }
+}
+
+size_t attention_mma_smem_bytes(int NT) { return sizeof(float) * 2 * 8 * NT * kAttnPitch; }
+
 size_t attention_smem_bytes(int S, int DH) {
   const int Sp = (S + 31) & ~31;
   return sizeof(float) * (static_cast<size_t>(S) * (DH + 4) + static_cast<size_t>(S) * DH + 8 * DH + 8 * Sp);
@@ -328,7 +472,7 @@ struct rohm_posenet {
   // weights
   PackedWeight w_in, w_cond, w_out;
   float *in_b = nullptr, *cond_b = nullptr, *out_b = nullptr, *pe = nullptr;
-  float *t0_w = nullptr, *t0_b = nullptr, *t2_w = nullptr, *t2_b = nullptr;
+  float* time_table = nullptr;  // [pe_len, D]: TimestepEmbedder(t) + pe[0]
   std::vector<PoseNetLayerDev> layers;
   // activations
   float *Ain_h = nullptr, *Ain_l = nullptr;
@@ -337,6 +481,23 @@ struct rohm_posenet {
   float* cond_traj = nullptr;  // [B, traj, T] copy of cond[:, :traj] taken by set_cond (output channels [0,traj))
   int cond_B = -1, cond_T = -1;
   int launches = 0;
+  // CUDA graph of one forward per (B, T): 61 launches become one cudaGraphLaunch; the three nodes that touch caller
+  // memory (pack: x_t, time-token gather: timesteps, unpack: out) get their pointers patched before every replay.
+  struct FwdGraph {
+    int B = 0, T = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t n_pack = nullptr, n_time = nullptr, n_unpack = nullptr;
+    cudaKernelNodeParams p_pack{}, p_time{}, p_unpack{};
+  };
+  std::vector<FwdGraph> graphs;
+  bool use_graph = true;
+  ~rohm_posenet() {
+    for (auto& g : graphs) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      if (g.graph) cudaGraphDestroy(g.graph);
+    }
+  }
   // optional per-kernel event timing (rohm_posenet_profile): category -> list of (start, stop) events
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -462,21 +623,85 @@ static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float
   return ROHM_OK;
 }
 
+template <int DH, int NT>
+static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float scale, cudaStream_t st) {
+  auto kern = attention_mma_kernel<DH, NT>;
+  static bool attr_set = false;
+  const size_t smem = attention_mma_smem_bytes(NT);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int warps = (S + 15) / 16;
+  kern<<<B * pn->H, 32 * warps, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+  return cudaGetLastError();
+}
+
 static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   const int dh = pn->D / pn->H;
-  const size_t smem = attention_smem_bytes(S, dh);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   prof_begin(pn, kCatAttention, st);
-  if (dh == 128) {
-    attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
-  } else if (dh == 64) {
-    attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
-  } else {
-    return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
+  const int nt = (S + 7) / 8;
+  cudaError_t e = cudaSuccess;
+  bool done = true;
+  // tensor-core path: S <= 160 tokens (register budget of the S/P fragment); wider clips use the SIMT kernel
+  if (dh == 128 && nt <= 4) e = launch_attention_mma<128, 4>(pn, B, S, scale, st);
+  else if (dh == 128 && nt <= 8) e = launch_attention_mma<128, 8>(pn, B, S, scale, st);
+  else if (dh == 128 && nt <= 12) e = launch_attention_mma<128, 12>(pn, B, S, scale, st);
+  else if (dh == 128 && nt <= 16) e = launch_attention_mma<128, 16>(pn, B, S, scale, st);
+  else if (dh == 128 && nt <= 20) e = launch_attention_mma<128, 20>(pn, B, S, scale, st);
+  else if (dh == 64 && nt <= 8) e = launch_attention_mma<64, 8>(pn, B, S, scale, st);
+  else if (dh == 64 && nt <= 20) e = launch_attention_mma<64, 20>(pn, B, S, scale, st);
+  else done = false;
+  if (!done) {
+    const size_t smem = attention_smem_bytes(S, dh);
+    if (dh == 128) {
+      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+    } else if (dh == 64) {
+      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+    } else {
+      return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
+    }
+    e = cudaGetLastError();
   }
   prof_end(pn, st);
-  ROHM_CUDA(pn->ctx, cudaGetLastError());
+  ROHM_CUDA(pn->ctx, e);
   pn->launches++;
+  return ROHM_OK;
+}
+
+// TE = (silu(PE W0^T + b0)) W2^T + (b2 + pe[0]) over all pe_len rows, with the engine's own GEMM kernel.
+static int build_time_table(rohm_posenet* pn, const rohm_posenet_weights* w) {
+  const int D = pn->D, R = pn->pe_len;
+  const int64_t n = static_cast<int64_t>(R) * D;
+  pn->time_table = pn->pool.floats(n);
+  if (pn->time_table == nullptr) return fail(pn->ctx, ROHM_ERR_CUDA, "time table alloc failed");
+  DevicePool tmp;  // freed on return
+  PackedWeight w0, w2;
+  float* pe_h = tmp.floats(n);
+  float* pe_l = tmp.floats(n);
+  float* h_h = tmp.floats(n);
+  float* h_l = tmp.floats(n);
+  float* bias2 = tmp.floats(D);
+  if (!pe_h || !pe_l || !h_h || !h_l || !bias2) return fail(pn->ctx, ROHM_ERR_CUDA, "time table scratch alloc failed");
+  int rc;
+  if ((rc = pack_weight(pn, w->t0_w, D, D, &w0)) != ROHM_OK) return rc;  // small (2 x 2 MB), kept in the pool
+  if ((rc = pack_weight(pn, w->t2_w, D, D, &w2)) != ROHM_OK) return rc;
+  ROHM_CUDA(pn->ctx, launch_split_tf32(pn->pe, pe_h, pe_l, n, 0));
+  add_vec_kernel<<<(D + 255) / 256, 256>>>(w->t2_b, pn->pe, bias2, D);  // b2 + pe[0]
+  ROHM_CUDA(pn->ctx, cudaGetLastError());
+  GemmParams g1{}, g2{};
+  if ((rc = setup_linear(pn, &g1, pe_h, pe_l, R, D, D, w0, w->t0_b)) != ROHM_OK) return rc;
+  g1.act = kActSilu;
+  g1.out_hi = h_h, g1.out_lo = h_l, g1.lds = D;
+  g1.M = R;
+  ROHM_CUDA(pn->ctx, launch_gemm(g1, R, D, w0.block_n, 3, 0));
+  if ((rc = setup_linear(pn, &g2, h_h, h_l, R, D, D, w2, bias2)) != ROHM_OK) return rc;
+  g2.out = pn->time_table, g2.ldo = D;
+  g2.M = R;
+  ROHM_CUDA(pn->ctx, launch_gemm(g2, R, D, w2.block_n, 3, 0));
+  ROHM_CUDA(pn->ctx, cudaDeviceSynchronize());
   return ROHM_OK;
 }
 
@@ -523,10 +748,7 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   TRY(copy_vec(pn, w->cond_b, D, &pn->cond_b));
   TRY(copy_vec(pn, w->out_b, pn->Cout, &pn->out_b));
   TRY(copy_vec(pn, w->pe, static_cast<int64_t>(pn->pe_len) * D, &pn->pe));
-  TRY(copy_vec(pn, w->t0_w, static_cast<int64_t>(D) * D, &pn->t0_w));
-  TRY(copy_vec(pn, w->t0_b, D, &pn->t0_b));
-  TRY(copy_vec(pn, w->t2_w, static_cast<int64_t>(D) * D, &pn->t2_w));
-  TRY(copy_vec(pn, w->t2_b, D, &pn->t2_b));
+  TRY(build_time_table(pn, w));
   pn->layers.resize(pn->L);
   for (int l = 0; l < pn->L; ++l) {
     const rohm_posenet_layer& s = w->layers[l];
@@ -591,6 +813,25 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   }
 #undef TRY
 
+  {
+    cudaError_t ea = gemm_init_attributes();
+    auto set_mma = [&](auto kern, int nt) {
+      if (ea == cudaSuccess)
+        ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(attention_mma_smem_bytes(nt)));
+    };
+    set_mma(attention_mma_kernel<128, 4>, 4);
+    set_mma(attention_mma_kernel<128, 8>, 8);
+    set_mma(attention_mma_kernel<128, 12>, 12);
+    set_mma(attention_mma_kernel<128, 16>, 16);
+    set_mma(attention_mma_kernel<128, 20>, 20);
+    set_mma(attention_mma_kernel<64, 8>, 8);
+    set_mma(attention_mma_kernel<64, 20>, 20);
+    if (ea != cudaSuccess) {
+      delete pn;
+      return fail(ctx, ROHM_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ea));
+    }
+  }
   // attention kernels need > 48 KB of dynamic shared memory
   const size_t smem_max = attention_smem_bytes(max_frames + 1, dh);
   if (smem_max > 227 * 1024) {
@@ -649,16 +890,10 @@ extern "C" int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B,
   return ROHM_OK;
 }
 
-extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
-                                    int T, void* stream) {
-  if (pn == nullptr) return ROHM_ERR_INVALID;
+// The raw launch sequence of one forward (what gets captured into the graph).
+static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
+                            cudaStream_t st) {
   rohm_ctx* ctx = pn->ctx;
-  if (x_t == nullptr || timesteps == nullptr || out == nullptr)
-    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_forward: null pointer");
-  if (B != pn->cond_B || T != pn->cond_T)
-    return fail(ctx, ROHM_ERR_STATE, "rohm_posenet_forward: B=%d T=%d but set_cond was called with B=%d T=%d", B, T,
-                pn->cond_B, pn->cond_T);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = T + 1, D = pn->D;
   const int rows = B * S;
   pn->launches = 0;
@@ -672,8 +907,7 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   pn->launches++;
   if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
   prof_begin(pn, kCatOther, st);
-  time_token_kernel<<<B, 256, 2 * D * sizeof(float), st>>>(timesteps, pn->pe, pn->pe_len, pn->t0_w, pn->t0_b, pn->t2_w,
-                                                          pn->t2_b, pn->X, pn->Xh, pn->Xl, S, D);
+  time_token_gather_kernel<<<B, 128, 0, st>>>(timesteps, pn->time_table, pn->pe_len, pn->X, pn->Xh, pn->Xl, S, D);
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
@@ -698,6 +932,9 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   pn->launches++;
   return ROHM_OK;
 }
+
+extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
+                                    int T, void* stream);
 
 // One forward with CUDA events around every kernel launch (on `stream`, the launching stream); synchronises and
 // returns the summed device time and launch count per category {GEMM, attention, LayerNorm, other}.
@@ -725,4 +962,108 @@ extern "C" int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const in
   if (rc != ROHM_OK) return rc;
   ROHM_CUDA(pn->ctx, e);
   return ROHM_OK;
+}
+
+static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
+                               cudaStream_t st, rohm_posenet::FwdGraph* fg) {
+  rohm_ctx* ctx = pn->ctx;
+  ROHM_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = forward_launches(pn, x_t, timesteps, out, B, T, st);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != ROHM_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  ROHM_CUDA(ctx, e);
+  size_t n = 0;
+  ROHM_CUDA(ctx, cudaGraphGetNodes(graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  ROHM_CUDA(ctx, cudaGraphGetNodes(graph, nodes.data(), &n));
+  fg->B = B, fg->T = T, fg->graph = graph;
+  for (cudaGraphNode_t node : nodes) {
+    cudaGraphNodeType ty;
+    ROHM_CUDA(ctx, cudaGraphNodeGetType(node, &ty));
+    if (ty != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp{};
+    ROHM_CUDA(ctx, cudaGraphKernelNodeGetParams(node, &kp));
+    if (kp.func == reinterpret_cast<void*>(pack_tokens_kernel)) fg->n_pack = node, fg->p_pack = kp;
+    else if (kp.func == reinterpret_cast<void*>(time_token_gather_kernel)) fg->n_time = node, fg->p_time = kp;
+    else if (kp.func == reinterpret_cast<void*>(unpack_tokens_kernel)) fg->n_unpack = node, fg->p_unpack = kp;
+  }
+  if (!fg->n_pack || !fg->n_time || !fg->n_unpack) {
+    cudaGraphDestroy(graph);
+    fg->graph = nullptr;
+    return fail(ctx, ROHM_ERR_CUDA, "forward graph: could not locate the boundary kernel nodes");
+  }
+  ROHM_CUDA(ctx, cudaGraphInstantiate(&fg->exec, graph, 0));
+  return ROHM_OK;
+}
+
+extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
+                                    int T, void* stream) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = pn->ctx;
+  if (x_t == nullptr || timesteps == nullptr || out == nullptr)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_forward: null pointer");
+  if (B != pn->cond_B || T != pn->cond_T)
+    return fail(ctx, ROHM_ERR_STATE, "rohm_posenet_forward: B=%d T=%d but set_cond was called with B=%d T=%d", B, T,
+                pn->cond_B, pn->cond_T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  ROHM_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
+  if (!pn->use_graph || pn->profiling || cap != cudaStreamCaptureStatusNone)
+    return forward_launches(pn, x_t, timesteps, out, B, T, st);
+
+  rohm_posenet::FwdGraph* fg = nullptr;
+  for (auto& g : pn->graphs)
+    if (g.B == B && g.T == T) fg = &g;
+  if (fg == nullptr) {
+    rohm_posenet::FwdGraph ng;
+    int rc = build_forward_graph(pn, x_t, timesteps, out, B, T, st, &ng);
+    if (rc != ROHM_OK) return rc;
+    if (pn->graphs.size() >= 8) {  // bounded cache
+      if (pn->graphs.front().exec) cudaGraphExecDestroy(pn->graphs.front().exec);
+      if (pn->graphs.front().graph) cudaGraphDestroy(pn->graphs.front().graph);
+      pn->graphs.erase(pn->graphs.begin());
+    }
+    pn->graphs.push_back(ng);
+    fg = &pn->graphs.back();
+  }
+  // patch the caller-memory pointers (argument 0 of pack / time-token, arguments 0.. of unpack: tok, cond, out)
+  const void* a_x = x_t;
+  const void* a_t = timesteps;
+  void* a_o = out;
+  {
+    cudaKernelNodeParams kp = fg->p_pack;
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 7);
+    args[0] = &a_x;
+    kp.kernelParams = args.data();
+    ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_pack, &kp));
+  }
+  {
+    cudaKernelNodeParams kp = fg->p_time;
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 8);
+    args[0] = &a_t;
+    kp.kernelParams = args.data();
+    ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_time, &kp));
+  }
+  {
+    cudaKernelNodeParams kp = fg->p_unpack;
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 9);
+    args[2] = &a_o;
+    kp.kernelParams = args.data();
+    ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_unpack, &kp));
+  }
+  ROHM_CUDA(ctx, cudaGraphLaunch(fg->exec, st));
+  return ROHM_OK;
+}
+
+extern "C" int rohm_posenet_set_option(rohm_posenet* pn, int option, int value) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  if (option == 0) {
+    pn->use_graph = value != 0;
+    return ROHM_OK;
+  }
+  return fail(pn->ctx, ROHM_ERR_INVALID, "rohm_posenet_set_option: unknown option %d", option);
 }

@@ -103,8 +103,9 @@ def ddpm_coef_rows(tables):
     rows = np.zeros((n, 8), dtype=np.float32)
     rows[:, 0] = tables["posterior_mean_coef1"].astype(np.float32)
     rows[:, 1] = tables["posterior_mean_coef2"].astype(np.float32)
-    logvar = tables["posterior_log_variance_clipped"].astype(np.float32)
-    sigma = np.exp(np.float32(0.5) * logvar).astype(np.float32)
+    import torch
+    logvar = torch.from_numpy(tables["posterior_log_variance_clipped"]).float()
+    sigma = torch.exp(0.5 * logvar).numpy().copy()  # torch's fp32 exp, the function the reference calls
     sigma[0] = 0.0
     rows[:, 2] = sigma
     rows[:, 3] = tables["posterior_variance"].astype(np.float32)

@@ -93,7 +93,7 @@ def test_weight_reload_is_picked_up(posenet, cuda_device):
     x = torch.randn(B, 294, 1, T)
     cond = synthetic.posenet_batch(B, T, 1)['cond']
     ts = torch.tensor([10])
-    sd2 = synthetic.synth_state_dict(m, 2)
+    sd2 = {k: v.cpu() for k, v in synthetic.synth_state_dict(m, 2).items()}
     m.load_state_dict(sd2)
     y = m({'x_t': x.to(cuda_device), 'cond': cond.to(cuda_device)}, ts.to(cuda_device)).cpu()
     assert float((y - posenet_oracle.posenet_forward(sd2, x, cond, ts)).abs().max()) < TOL
