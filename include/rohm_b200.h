@@ -149,6 +149,32 @@ ROHM_API int rohm_posenet_set_option(rohm_posenet* pn, int option, int value);
 /* Kernel launches issued by the last forward (for bench.py's gpu_launches accounting). */
 ROHM_API int rohm_posenet_launches_per_forward(const rohm_posenet* pn);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * TrajNet denoiser + TrajControl branch (model/trajnet.py:10-75, 177-275; blocks model/heads.py:20-106)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Parameters are handed over by their reference state-dict key ("diff_enc1.blocks.0.block.0.weight",
+ * "controlnet.control_zero_conv_0.bias", "time_mlp.1.weight", ...): `names[i]` (host strings), `ptrs[i]` (device fp32),
+ * `numels[i]`.  Every key the architecture needs must be present with the reference's shape; extra keys (e.g. the
+ * never-evaluated cond_downsample4.*) are ignored.  `frames` must be a multiple of 16.  The library repacks all
+ * convolution weights into GEMM layout (TF32 hi/lo, tap-major K) and owns its copies. */
+ROHM_API int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* const* names, const float* const* ptrs,
+                                 const int64_t* numels, int time_dim, int cond_dim, int traj_feat_dim, int mid_dim,
+                                 int trajcontrol, int control_cond_dim, int max_batch, int frames, int precision,
+                                 rohm_trajnet** out);
+ROHM_API void rohm_trajnet_destroy(rohm_trajnet* tn);
+
+/* Step-invariant part of TrajNet.forward: the condition pyramid cond_enc1..4 (trajnet.py:192-208) and, with
+ * TrajControl, control_zero_conv_0(control_cond) (:51-52).  cond: [B, frames, cond_dim]; control_cond:
+ * [B, frames, control_cond_dim] or NULL for the vanilla network.  Call whenever batch['cond'] / ['control_cond'] change. */
+ROHM_API int rohm_trajnet_set_cond(rohm_trajnet* tn, const float* cond, const float* control_cond, int B, void* stream);
+
+/* TrajNet.forward (trajnet.py:177-275).  x_t: [B, frames, traj_feat_dim]; time: int64 [B]; out: same shape as x_t. */
+ROHM_API int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
+                                  void* stream);
+ROHM_API int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value); /* 0: CUDA-graph replay (default 1) */
+ROHM_API int rohm_trajnet_launches_per_forward(const rohm_trajnet* tn);
+
 #ifdef __cplusplus
 }
 #endif

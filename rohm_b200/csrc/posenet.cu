@@ -298,10 +298,19 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - h);
 }
 
+// Same split, but opaque to the optimiser: used inside the rolled P V loop, where hoisting the loop-invariant split of
+// the whole P fragment out of the loop would double its register footprint (and spill).
+__device__ __forceinline__ void split_tf32_pinned(float x, uint32_t& hi, uint32_t& lo) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  hi = r;
+  lo = __float_as_uint(x - __uint_as_float(r));
+}
+
 constexpr int kAttnPitch = 132;
 
 template <int DH, int NT>  // NT = number of 8-key tiles (keys padded to 8*NT), rows padded to 16 * warps
-__global__ void __launch_bounds__(32 * ((NT + 1) / 2)) attention_mma_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(const float* __restrict__ qkv,
                                                                           float* __restrict__ ctx_hi,
                                                                           float* __restrict__ ctx_lo, int S, int D,
                                                                           int H, float scale) {
@@ -330,26 +339,27 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2)) attention_mma_kernel(cons
   const int rowA = min(r0 + g, S - 1), rowB = min(r0 + g + 8, S - 1);
   const float* qA = qkv + (base + rowA) * ld + h * DH;
   const float* qB = qkv + (base + rowB) * ld + h * DH;
-  // all Q fragments of this warp: [k-step][a0..a3] = Q[rowA][8k+t], Q[rowB][8k+t], Q[rowA][8k+t+4], Q[rowB][8k+t+4]
-  float qf[DH / 8][4];
-#pragma unroll
-  for (int k = 0; k < DH / 8; ++k) {
-    qf[k][0] = __ldg(qA + 8 * k + t);
-    qf[k][1] = __ldg(qB + 8 * k + t);
-    qf[k][2] = __ldg(qA + 8 * k + t + 4);
-    qf[k][3] = __ldg(qB + 8 * k + t + 4);
-  }
   __syncthreads();
 
-  // ---- S = Q K^T ----
+  // ---- S = Q K^T ----  (k loop deliberately NOT unrolled: the fully unrolled kernel was instruction-cache bound,
+  // ncu: stall_no_instruction 5.1 of 11.3 cycles per issued instruction)
   float acc[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
-#pragma unroll
+  // Q fragment of k-step k: a0..a3 = Q[rowA][8k+t], Q[rowB][8k+t], Q[rowA][8k+t+4], Q[rowB][8k+t+4]; prefetched one
+  // k-step ahead (each value is used once, straight from L2)
+  float qn[4] = {__ldg(qA + t), __ldg(qB + t), __ldg(qA + t + 4), __ldg(qB + t + 4)};
+#pragma unroll 1
   for (int k = 0; k < DH / 8; ++k) {
     uint32_t ah[4], al[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_tf32(qf[k][i], ah[i], al[i]);
+    for (int i = 0; i < 4; ++i) split_tf32(qn[i], ah[i], al[i]);
+    if (k + 1 < DH / 8) {
+      qn[0] = __ldg(qA + 8 * (k + 1) + t);
+      qn[1] = __ldg(qB + 8 * (k + 1) + t);
+      qn[2] = __ldg(qA + 8 * (k + 1) + t + 4);
+      qn[3] = __ldg(qB + 8 * (k + 1) + t + 4);
+    }
     const float* kp = Ks + g * kAttnPitch + 8 * k + t;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -400,43 +410,46 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2)) attention_mma_kernel(cons
   // A fragment of k-step j (keys 8j..8j+7, enumerated as column t -> key 8j+2t, column t+4 -> key 8j+2t+1):
   //   a0 = P[rowA][8j+2t] = acc[j][0], a1 = P[rowB][8j+2t] = acc[j][2], a2 = acc[j][1], a3 = acc[j][3]
   // B fragment for output dims 8n..8n+7:  b0 = V[8j+2t][8n+g], b1 = V[8j+2t+1][8n+g]
-  float o[DH / 8][4];
-#pragma unroll
-  for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f;
+  // The loop over the 8-wide output tiles is rolled (P lives in registers and needs static indexing, O does not):
+  // each iteration produces and stores one 16 x 8 output tile.
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    uint32_t ah[4], al[4];
-    split_tf32(acc[j][0] * invA, ah[0], al[0]);
-    split_tf32(acc[j][2] * invB, ah[1], al[1]);
-    split_tf32(acc[j][1] * invA, ah[2], al[2]);
-    split_tf32(acc[j][3] * invB, ah[3], al[3]);
-    const float* vp = Vs + (8 * j + 2 * t) * kAttnPitch + g;
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) {
-      uint32_t bh[2], bl[2];
-      split_tf32(vp[8 * n], bh[0], bl[0]);
-      split_tf32(vp[8 * n + kAttnPitch], bh[1], bl[1]);
-      mma_tf32_16x8x8(o[n], al, bh);
-      mma_tf32_16x8x8(o[n], ah, bl);
-      mma_tf32_16x8x8(o[n], ah, bh);
-    }
+    acc[j][0] *= invA, acc[j][1] *= invA;
+    acc[j][2] *= invB, acc[j][3] *= invB;
   }
-
-  // ---- store ctx as TF32 hi/lo (o[n][0..1] = row rowA, cols 8n+2t,+1; o[n][2..3] = row rowB) ----
   const bool okA = (r0 + g) < S, okB = (r0 + g + 8) < S;
   const int64_t oA = (base + r0 + g) * D + h * DH + 2 * t;
   const int64_t oB = oA + static_cast<int64_t>(8) * D;
-#pragma unroll
+#pragma unroll 1
   for (int n = 0; n < DH / 8; ++n) {
+    float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float os[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // small cross terms accumulate separately (shorter dependency chains)
+    const float* vp = Vs + 2 * t * kAttnPitch + g + 8 * n;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      split_tf32_pinned(acc[j][0], ah[0], al[0]);
+      split_tf32_pinned(acc[j][2], ah[1], al[1]);
+      split_tf32_pinned(acc[j][1], ah[2], al[2]);
+      split_tf32_pinned(acc[j][3], ah[3], al[3]);
+      split_tf32(vp[8 * j * kAttnPitch], bh[0], bl[0]);
+      split_tf32(vp[(8 * j + 1) * kAttnPitch], bh[1], bl[1]);
+      mma_tf32_16x8x8(os, al, bh);
+      mma_tf32_16x8x8(os, ah, bl);
+      mma_tf32_16x8x8(o, ah, bh);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] += os[i];
+    // store ctx as TF32 hi/lo (o[0..1] = row rowA, cols 8n+2t,+1; o[2..3] = row rowB)
     if (okA) {
-      const float h0 = ptx::to_tf32(o[n][0]), h1 = ptx::to_tf32(o[n][1]);
+      const float h0 = ptx::to_tf32(o[0]), h1 = ptx::to_tf32(o[1]);
       *reinterpret_cast<float2*>(ctx_hi + oA + 8 * n) = make_float2(h0, h1);
-      *reinterpret_cast<float2*>(ctx_lo + oA + 8 * n) = make_float2(o[n][0] - h0, o[n][1] - h1);
+      *reinterpret_cast<float2*>(ctx_lo + oA + 8 * n) = make_float2(o[0] - h0, o[1] - h1);
     }
     if (okB) {
-      const float h2 = ptx::to_tf32(o[n][2]), h3 = ptx::to_tf32(o[n][3]);
+      const float h2 = ptx::to_tf32(o[2]), h3 = ptx::to_tf32(o[3]);
       *reinterpret_cast<float2*>(ctx_hi + oB + 8 * n) = make_float2(h2, h3);
-      *reinterpret_cast<float2*>(ctx_lo + oB + 8 * n) = make_float2(o[n][2] - h2, o[n][3] - h3);
+      *reinterpret_cast<float2*>(ctx_lo + oB + 8 * n) = make_float2(o[2] - h2, o[3] - h3);
     }
   }
 }
@@ -492,7 +505,9 @@ struct rohm_posenet {
   };
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
+  cudaStream_t capture_stream = nullptr;
   ~rohm_posenet() {
+    if (capture_stream) cudaStreamDestroy(capture_stream);
     for (auto& g : graphs) {
       if (g.exec) cudaGraphExecDestroy(g.exec);
       if (g.graph) cudaGraphDestroy(g.graph);
@@ -967,10 +982,16 @@ extern "C" int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const in
 static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                                cudaStream_t st, rohm_posenet::FwdGraph* fg) {
   rohm_ctx* ctx = pn->ctx;
-  ROHM_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int rc = forward_launches(pn, x_t, timesteps, out, B, T, st);
+  // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
+  // Nothing executes during capture; the instantiated graph is then launched on the caller's stream.
+  (void)st;
+  if (pn->capture_stream == nullptr)
+    ROHM_CUDA(ctx, cudaStreamCreateWithFlags(&pn->capture_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = pn->capture_stream;
+  ROHM_CUDA(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = forward_launches(pn, x_t, timesteps, out, B, T, cs);
   cudaGraph_t graph = nullptr;
-  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
   if (rc != ROHM_OK) {
     if (graph) cudaGraphDestroy(graph);
     return rc;

@@ -114,6 +114,7 @@ class TrajNet(nn.Module):
 
         self.precision = None
         self._engine = None
+        self._engine_fingerprint = None
 
     def invalidate_engine(self):
         self._engine = None

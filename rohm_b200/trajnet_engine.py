@@ -1,0 +1,114 @@
+"""Python side of the TrajNet CUDA engine: hands the module's parameters to ``rohm_trajnet_create`` by their reference
+state-dict keys, tracks the step-invariant condition and runs ``rohm_trajnet_forward``."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RohmB200Error
+from .posenet import _precision_from_env
+
+
+class TrajNetEngine:
+    def __init__(self, module, device, max_batch, frames, precision):
+        self.lib = _lib.load()
+        self.ctx = _lib.ctx(device.index)
+        self.device = device
+        self.max_batch, self.frames, self.precision = max_batch, frames, precision
+        sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in module.state_dict().items()
+              if v.is_floating_point()}
+        n = len(sd)
+        names = (C.c_char_p * n)(*[k.encode() for k in sd])
+        ptrs = (C.c_void_p * n)(*[v.data_ptr() for v in sd.values()])
+        numels = (C.c_int64 * n)(*[v.numel() for v in sd.values()])
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.rohm_trajnet_create(self.ctx, n, names, ptrs, numels, module.time_dim, module.cond_dim,
+                                              module.traj_feat_dim, module.mid_dim, int(module.trajcontrol),
+                                              module.control_cond_dim, max_batch, frames, precision, C.byref(handle))
+        _lib.check(rc, self.ctx)
+        self.handle = handle
+        self.cond_key = None
+        del sd
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.rohm_trajnet_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_cond(self, cond, control_cond):
+        rc = self.lib.rohm_trajnet_set_cond(self.handle, C.c_void_p(cond.data_ptr()),
+                                            C.c_void_p(control_cond.data_ptr() if control_cond is not None else 0),
+                                            cond.shape[0], self._stream())
+        _lib.check(rc, self.ctx)
+
+    def forward(self, x_t, time):
+        out = torch.empty_like(x_t)
+        rc = self.lib.rohm_trajnet_forward(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(time.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), x_t.shape[0], self._stream())
+        _lib.check(rc, self.ctx)
+        return out
+
+    @property
+    def launches_per_forward(self):
+        return int(self.lib.rohm_trajnet_launches_per_forward(self.handle))
+
+
+def _fingerprint(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def _tensor_key(t):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+
+
+def _f32c(t):
+    return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+
+
+def get_engine(module, B, T, device):
+    if module.training:
+        raise RohmB200Error("TrajNet: the CUDA engine implements the inference path (model.eval()); training is out of "
+                            "scope")
+    prec = module.precision if module.precision is not None else _precision_from_env()
+    e = module._engine
+    if e is None or e.device != device or B > e.max_batch or T != e.frames or e.precision != prec:
+        mb = max(B, e.max_batch if (e is not None and e.device == device and e.frames == T) else 0)
+        module._engine = None
+        e = TrajNetEngine(module, device, mb, T, prec)
+        module._engine = e
+        module._engine_fingerprint = _fingerprint(module)
+    return e
+
+
+def run_forward(module, batch, time):
+    x_t, cond = batch['x_t'], batch['cond']
+    if x_t.device.type != "cuda":
+        raise RohmB200Error("TrajNet: batch tensors must live on a CUDA device (no CPU path)")
+    if x_t.dim() != 3 or x_t.shape[-1] != module.traj_feat_dim or cond.shape[:2] != x_t.shape[:2] or \
+            cond.shape[-1] != module.cond_dim:
+        raise RohmB200Error(f"TrajNet: expected x_t [B, T, {module.traj_feat_dim}] and cond [B, T, {module.cond_dim}], "
+                            f"got {tuple(x_t.shape)} / {tuple(cond.shape)}")
+    B, T, _ = x_t.shape
+    if T % 16 != 0:
+        raise RohmB200Error(f"TrajNet: the number of frames ({T}) must be a multiple of 16 (four stride-2 stages)")
+    control = batch.get('control_cond') if module.trajcontrol else None
+    if module.trajcontrol and (control is None or tuple(control.shape) != (B, T, module.control_cond_dim)):
+        raise RohmB200Error(f"TrajNet(trajcontrol=True): batch['control_cond'] must be [B, T, {module.control_cond_dim}]")
+    e = get_engine(module, B, T, x_t.device)
+    key = (_tensor_key(cond), _tensor_key(control), B)
+    if e.cond_key != key:
+        if _fingerprint(module) != module._engine_fingerprint:  # parameters changed since the weights were packed
+            module._engine = None
+            e = get_engine(module, B, T, x_t.device)
+        e.set_cond(_f32c(cond), _f32c(control) if control is not None else None)
+        e.cond_key = key
+    ts = time.to(device=x_t.device, dtype=torch.int64).contiguous()
+    return e.forward(_f32c(x_t), ts)
