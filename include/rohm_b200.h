@@ -175,6 +175,40 @@ ROHM_API int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int6
 ROHM_API int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value); /* 0: CUDA-graph replay (default 1) */
 ROHM_API int rohm_trajnet_launches_per_forward(const rohm_trajnet* tn);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * SMPL-X body model: joints FK, skating guidance, full LBS
+ * (third-party smplx==0.1.28 lbs.py / body_models.py as called from data_loaders/motion_representation.py:373-398,
+ *  model/posenet.py:196-257; see DESIGN.md for provenance -- the body model is not part of the reference tree)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* v_template [V,3], shapedirs [V,3,shape_comps] (first 10 components = betas), posedirs [486, V*3],
+ * J_regressor [55,V], lbs_weights [V,55] (device fp32); parents_host: host int[55] (-1 for the root).
+ * max_frames: capacity in frames (B*T) of the per-call workspace.  with_vertices = 0 skips the LBS data (joints and
+ * guidance only; posedirs / lbs_weights may then be NULL). */
+ROHM_API int rohm_body_create(rohm_ctx* ctx, const float* v_template, const float* shapedirs, int shape_comps,
+                              const float* posedirs, const float* J_regressor, const float* lbs_weights,
+                              const int* parents_host, int num_verts, int64_t max_frames, int with_vertices,
+                              int precision, rohm_body** out);
+ROHM_API void rohm_body_destroy(rohm_body* bd);
+
+/* SMPLX.forward with jaw / eyes / hands / expression = 0 (exactly how RoHM calls it): global_orient [N,3], body_pose
+ * [N,63] axis-angle, betas [N,10], transl [N,3] -> joints [N, num_joints, 3] (first num_joints <= 55 posed joints +
+ * transl; NULL to skip) and vertices [N, V, 3] (NULL to skip). */
+ROHM_API int rohm_body_forward(rohm_body* bd, const float* global_orient, const float* body_pose, const float* betas,
+                               const float* transl, int64_t N, float* joints, int num_joints, float* vertices,
+                               void* stream);
+
+/* recover_from_repr_smpl(recover_mode='smplx_params') on a normalised representation x [B,294,1,T] with the dataset's
+ * mean/std [294]: denormalise, rot6d -> rotmat -> axis-angle (kornia route), then rohm_body_forward. */
+ROHM_API int rohm_body_from_repr(rohm_body* bd, const float* x, const float* mean, const float* stdv, int B, int T,
+                                 float* joints, int num_joints, float* vertices, void* stream);
+
+/* PoseNet.guide_skating_with_smpl(compute_grad='x_0'): grad [B,294,1,T] = d(-(loss_smpl + loss_abs))/d x0 with the
+ * channels [0,22) and the 4 contact channels zero.  Analytic VJP (no autograd); all-zero if nothing skates.
+ * loss_out: optional device float[4] = {sum_abs, count_abs, sum_smpl, count_smpl}. */
+ROHM_API int rohm_skating_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                   float* grad, float* loss_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

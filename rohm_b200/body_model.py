@@ -5,20 +5,112 @@ shapedirs[..., 10:], posedirs, J_regressor, lbs_weights, parents) and evaluates 
 kernels of the library (rohm_fk22_* / rohm_lbs_forward).  See DESIGN.md for the provenance of the algorithm
 (smplx==0.1.28, not vendored by the reference).
 """
+import ctypes as C
 import os
 
 import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _lib, synthetic
 from ._lib import RohmB200Error
-from . import synthetic
 
 
 class BodyOutput:
+    """Mirror of smplx's output object: the attributes RoHM reads (``joints``, ``vertices``)."""
+
     def __init__(self, joints=None, vertices=None):
         self.joints = joints
         self.vertices = vertices
+
+
+class BodyKernels:
+    """One rohm_body handle (device copies of the model + per-call workspace for up to ``max_frames`` frames)."""
+
+    def __init__(self, model, device, max_frames, with_vertices, precision=_lib.PRECISION_TF32X3):
+        self.lib = _lib.load()
+        self.ctx = _lib.ctx(device.index)
+        self.device, self.max_frames, self.with_vertices = device, int(max_frames), bool(with_vertices)
+        g = lambda n: getattr(model, n).detach().to(device=device, dtype=torch.float32).contiguous()
+        vt, sd, jr = g("v_template"), g("shapedirs"), g("J_regressor")
+        if sd.shape[-1] < 10:
+            raise RohmB200Error("body model: shapedirs must hold at least 10 shape components")
+        pd = g("posedirs") if with_vertices else None
+        lw = g("lbs_weights") if with_vertices else None
+        parents = [int(p) for p in getattr(model, "parents").tolist()]
+        parents[0] = -1
+        if len(parents) != 55 or (with_vertices and tuple(pd.shape) != (486, vt.shape[0] * 3)):
+            raise RohmB200Error("body model: expected an SMPL-X layout (55 joints, posedirs [486, V*3])")
+        self.V = int(vt.shape[0])
+        arr = (C.c_int * 55)(*parents)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.rohm_body_create(self.ctx, C.c_void_p(vt.data_ptr()), C.c_void_p(sd.data_ptr()), int(sd.shape[-1]),
+                                           C.c_void_p(pd.data_ptr() if pd is not None else 0), C.c_void_p(jr.data_ptr()),
+                                           C.c_void_p(lw.data_ptr() if lw is not None else 0), arr, self.V,
+                                           self.max_frames, int(with_vertices), precision, C.byref(handle))
+        _lib.check(rc, self.ctx)
+        self.handle = handle
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.rohm_body_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, global_orient, body_pose, betas, transl, want_vertices, num_joints=55):
+        N = global_orient.shape[0]
+        f = lambda t, w: t.reshape(N, w).to(device=self.device, dtype=torch.float32).contiguous()
+        go, bp, be, tr = f(global_orient, 3), f(body_pose, 63), f(betas, 10), f(transl, 3)
+        joints = torch.empty(N, num_joints, 3, device=self.device)
+        verts = torch.empty(N, self.V, 3, device=self.device) if want_vertices else None
+        rc = self.lib.rohm_body_forward(self.handle, C.c_void_p(go.data_ptr()), C.c_void_p(bp.data_ptr()),
+                                        C.c_void_p(be.data_ptr()), C.c_void_p(tr.data_ptr()), N,
+                                        C.c_void_p(joints.data_ptr()), num_joints,
+                                        C.c_void_p(verts.data_ptr() if verts is not None else 0), self._stream())
+        _lib.check(rc, self.ctx)
+        return joints, verts
+
+    def from_repr(self, x, mean, std, want_vertices, num_joints=22):
+        """x: normalised [B, 294, 1, T] -> joints [B, T, num_joints, 3] (+ vertices [B, T, V, 3])."""
+        B, _, _, T = x.shape
+        joints = torch.empty(B * T, num_joints, 3, device=self.device)
+        verts = torch.empty(B * T, self.V, 3, device=self.device) if want_vertices else None
+        rc = self.lib.rohm_body_from_repr(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(mean.data_ptr()),
+                                          C.c_void_p(std.data_ptr()), B, T, C.c_void_p(joints.data_ptr()), num_joints,
+                                          C.c_void_p(verts.data_ptr() if verts is not None else 0), self._stream())
+        _lib.check(rc, self.ctx)
+        joints = joints.reshape(B, T, num_joints, 3)
+        return (joints, verts.reshape(B, T, self.V, 3)) if want_vertices else joints
+
+    def skating_guidance(self, x0, mean, std, want_loss=False):
+        B, _, _, T = x0.shape
+        grad = torch.empty_like(x0)
+        loss = torch.empty(4, device=self.device) if want_loss else None
+        rc = self.lib.rohm_skating_guidance(self.handle, C.c_void_p(x0.data_ptr()), C.c_void_p(mean.data_ptr()),
+                                            C.c_void_p(std.data_ptr()), B, T, C.c_void_p(grad.data_ptr()),
+                                            C.c_void_p(loss.data_ptr() if loss is not None else 0), self._stream())
+        _lib.check(rc, self.ctx)
+        return (grad, loss) if want_loss else grad
+
+
+def kernels_for(model, device, frames, with_vertices):
+    """The (cached) BodyKernels of a body-model module -- the package's BodyModel or a real ``smplx`` module (same
+    buffer names).  Capacity grows on demand."""
+    cache = model.__dict__.setdefault("_rohm_kernels", {})
+    key = (str(device), bool(with_vertices))
+    k = cache.get(key)
+    if k is None or k.max_frames < frames:
+        cache[key] = None
+        k = BodyKernels(model, torch.device(device), max(int(frames), 1), with_vertices)
+        cache[key] = k
+    return k
 
 
 class BodyModel(nn.Module):
@@ -57,5 +149,18 @@ class BodyModel(nn.Module):
         return {"v_template": self.v_template, "shapedirs": self.shapedirs, "posedirs": self.posedirs,
                 "J_regressor": self.J_regressor, "lbs_weights": self.lbs_weights, "parents": self.parents.tolist()}
 
-    def forward(self, **params):  # filled in with the FK / LBS kernels
-        raise RohmB200Error("BodyModel.forward: FK/LBS kernels are not built into this library version")
+    def _apply(self, fn, *a, **k):
+        self.__dict__.pop("_rohm_kernels", None)
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, transl=None, global_orient=None, body_pose=None, betas=None, return_verts=True, **zeros):
+        """Call-compatible with ``smplx_model(**smplx_params_dict)`` as RoHM uses it
+        (motion_representation.py:379-389): jaw / eye / hand poses and expression are accepted and must be zero.
+        Returns an object with ``.joints`` [N, 55, 3] and ``.vertices`` [N, V, 3]."""
+        dev = self.v_template.device
+        if dev.type != "cuda":
+            raise RohmB200Error("BodyModel: the model must live on a CUDA device (no CPU path)")
+        N = global_orient.shape[0]
+        k = kernels_for(self, dev, N, with_vertices=return_verts)
+        joints, verts = k.forward(global_orient, body_pose, betas, transl, return_verts)
+        return BodyOutput(joints=joints, vertices=verts)

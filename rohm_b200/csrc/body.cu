@@ -1,0 +1,818 @@
+// SMPL-X body model kernels: joints-only forward kinematics, the foot-skating guidance gradient (analytic VJP, no
+// autograd), and full linear-blend skinning.
+//
+// Algorithm provenance: the body model arithmetic is third-party smplx==0.1.28 (lbs.py: blend_shapes,
+// vertices2joints, batch_rodrigues, batch_rigid_transform, lbs; body_models.py: SMPLX.forward) -- NOT part of the
+// reference tree (reference environment.yml:198; call sites model/posenet.py:57-58,
+// data_loaders/motion_representation.py:373-398).  The code around it restates the reference:
+//   rot6d_to_rotmat                 data_loaders/common/quaternion.py:482-501
+//   rotation_matrix_to_angle_axis   utils/konia_transform.py:317-340, 350-444, 561-631
+//   recover_from_repr_smpl          data_loaders/motion_representation.py:285-398
+//   guide_skating_with_smpl         model/posenet.py:196-257
+//
+// Guidance design.  The reference differentiates  x0 -> denorm -> {abs-traj joints, 6D -> R -> quat -> aa ->
+// Rodrigues -> FK joints} -> foot velocity -> masked mean  with autograd and then zeroes channels [0, traj) and the
+// 4 contact channels.  Only feet (joints 7, 10, 8, 11) enter the loss, so only the two leg chains
+// 0-1-4-7-10 / 0-2-5-8-11 are evaluated; only local_positions of the 4 foot joints, the 6-D rotations of body joints
+// {1,2,4,5,7,8} and betas receive a non-zero gradient.  R -> axis-angle -> Rodrigues is the identity on SO(3), and the
+// Gram-Schmidt output only moves inside SO(3), so its Jacobian contribution is the identity: the VJP goes straight
+// from the joint rotation matrices to the 6-D inputs (differences to the reference's autograd: its eps clamps below
+// ~2e-3 rad and fp32 round-off of the round trip).
+#include <cmath>
+#include <new>
+
+#include "common.h"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace rohm {
+namespace {
+
+constexpr int kJ = 55;        // SMPL-X joints
+constexpr int kBodyJ = 22;    // global + 21 body joints
+constexpr int kBetas = 10;
+constexpr int kPoseFeat = 189;  // (22 - 1) * 9 non-zero pose-corrective features (hands / jaw / eyes are identity)
+constexpr int kBlendK = 224;    // 189 pose features + 10 betas + 1 (template) padded to a multiple of 32
+constexpr int kMaxBones = 8;    // compressed skinning weights per vertex
+
+__constant__ int c_parents[kJ];
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+struct M3 {  // columns
+  V3 c0, c1, c2;
+};
+__device__ __forceinline__ V3 mul(const M3& R, V3 v) { return v.x * R.c0 + v.y * R.c1 + v.z * R.c2; }
+__device__ __forceinline__ V3 mulT(const M3& R, V3 v) { return {dot(R.c0, v), dot(R.c1, v), dot(R.c2, v)}; }
+__device__ __forceinline__ M3 mul(const M3& A, const M3& B) { return {mul(A, B.c0), mul(A, B.c1), mul(A, B.c2)}; }
+
+// rot6d (row-major 3x2: a1 = x[0,2,4], a2 = x[1,3,5]) -> rotation matrix with columns b1, b2, b3.
+__device__ __forceinline__ M3 rot6d_to_mat(const float* x, float* n1 = nullptr, float* n2 = nullptr, float* s = nullptr) {
+  const V3 a1 = {x[0], x[2], x[4]}, a2 = {x[1], x[3], x[5]};
+  const float l1 = fmaxf(sqrtf(dot(a1, a1)), 1e-12f);
+  const V3 b1 = (1.0f / l1) * a1;
+  const float d = dot(b1, a2);
+  const V3 u2 = a2 - d * b1;
+  const float l2 = fmaxf(sqrtf(dot(u2, u2)), 1e-12f);
+  const V3 b2 = (1.0f / l2) * u2;
+  if (n1) *n1 = l1, *n2 = l2, *s = d;
+  return {b1, b2, cross(b1, b2)};
+}
+
+// VJP of rot6d_to_mat: G = dL/dR (columns g1, g2, g3) -> dL/dx[6].
+__device__ __forceinline__ void rot6d_backward(const float* x, const M3& G, float* gx) {
+  float l1, l2, s;
+  const M3 R = rot6d_to_mat(x, &l1, &l2, &s);
+  const V3 a2 = {x[1], x[3], x[5]};
+  V3 gb1 = G.c0 + cross(R.c1, G.c2);   // b3 = b1 x b2
+  V3 gb2 = G.c1 + cross(G.c2, R.c0);
+  const V3 gu2 = (1.0f / l2) * (gb2 - dot(gb2, R.c1) * R.c1);
+  const V3 ga2 = gu2 - dot(R.c0, gu2) * R.c0;
+  gb1 = gb1 - s * gu2 - dot(gu2, R.c0) * a2;
+  const V3 ga1 = (1.0f / l1) * (gb1 - dot(gb1, R.c0) * R.c0);
+  gx[0] = ga1.x, gx[2] = ga1.y, gx[4] = ga1.z;
+  gx[1] = ga2.x, gx[3] = ga2.y, gx[5] = ga2.z;
+}
+
+// rotation matrix -> axis-angle through the reference's quaternion route (kornia WXYZ, eps = 1e-6 everywhere)
+__device__ __forceinline__ float safe_div(float n, float d) { return n / (fabsf(d) < 1e-6f ? d + 1e-6f : d); }
+__device__ __forceinline__ float safe_atan2(float y, float x) {
+  if (fabsf(y) < 1e-6f && fabsf(x) < 1e-6f) y += 1e-6f;
+  return atan2f(y, x);
+}
+__device__ __forceinline__ V3 mat_to_aa(const M3& R) {
+  const float m00 = R.c0.x, m10 = R.c0.y, m20 = R.c0.z, m01 = R.c1.x, m11 = R.c1.y, m21 = R.c1.z, m02 = R.c2.x,
+              m12 = R.c2.y, m22 = R.c2.z;
+  const float trace = m00 + m11 + m22;
+  float qw, qx, qy, qz;
+  if (trace > 0.0f) {
+    const float sq = sqrtf(fmaxf(trace + 1.0f, 1e-6f)) * 2.0f;
+    qw = 0.25f * sq, qx = safe_div(m21 - m12, sq), qy = safe_div(m02 - m20, sq), qz = safe_div(m10 - m01, sq);
+  } else if (m00 > m11 && m00 > m22) {
+    const float sq = sqrtf(fmaxf(1.0f + m00 - m11 - m22, 1e-6f)) * 2.0f;
+    qw = safe_div(m21 - m12, sq), qx = 0.25f * sq, qy = safe_div(m01 + m10, sq), qz = safe_div(m02 + m20, sq);
+  } else if (m11 > m22) {
+    const float sq = sqrtf(fmaxf(1.0f + m11 - m00 - m22, 1e-6f)) * 2.0f;
+    qw = safe_div(m02 - m20, sq), qx = safe_div(m01 + m10, sq), qy = 0.25f * sq, qz = safe_div(m12 + m21, sq);
+  } else {
+    const float sq = sqrtf(fmaxf(1.0f + m22 - m00 - m11, 1e-6f)) * 2.0f;
+    qw = safe_div(m10 - m01, sq), qx = safe_div(m02 + m20, sq), qy = safe_div(m12 + m21, sq), qz = 0.25f * sq;
+  }
+  const float s2 = qx * qx + qy * qy + qz * qz;
+  const float sn = sqrtf(fmaxf(s2, 1e-6f));
+  const float two_theta = 2.0f * (qw < 0.0f ? safe_atan2(-sn, -qw) : safe_atan2(sn, qw));
+  const float k = s2 > 0.0f ? safe_div(two_theta, sn) : 2.0f;
+  return {qx * k, qy * k, qz * k};
+}
+// smplx batch_rodrigues: the 1e-8 is added to the VECTOR before the norm
+__device__ __forceinline__ M3 rodrigues(V3 r) {
+  const V3 e = {r.x + 1e-8f, r.y + 1e-8f, r.z + 1e-8f};
+  const float ang = sqrtf(dot(e, e));
+  const V3 k = (1.0f / ang) * r;
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  const float c1 = 1.0f - cs;
+  // I + sin K + (1 - cos) K^2
+  M3 R;
+  R.c0 = {1.0f + c1 * (-k.z * k.z - k.y * k.y), sn * k.z + c1 * k.x * k.y, -sn * k.y + c1 * k.x * k.z};
+  R.c1 = {-sn * k.z + c1 * k.x * k.y, 1.0f + c1 * (-k.z * k.z - k.x * k.x), sn * k.x + c1 * k.y * k.z};
+  R.c2 = {sn * k.y + c1 * k.x * k.z, -sn * k.x + c1 * k.y * k.z, 1.0f + c1 * (-k.y * k.y - k.x * k.x)};
+  return R;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model preparation
+// ---------------------------------------------------------------------------------------------------------------
+// Jt[j][k] = sum_v Jreg[j][v] * v_template[v][k];  Jd[j][k][l] = sum_v Jreg[j][v] * shapedirs[v][k][l]  (l < 10)
+__global__ void joint_regress_kernel(const float* __restrict__ Jreg, const float* __restrict__ vt,
+                                     const float* __restrict__ sdirs, int V, int sd_comps, float* __restrict__ Jt,
+                                     float* __restrict__ Jd) {
+  const int j = blockIdx.x;       // joint
+  const int q = blockIdx.y;       // 0..2: template xyz; 3..32: dirs (k*10 + l)
+  float acc = 0.0f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float w = Jreg[static_cast<int64_t>(j) * V + v];
+    if (w != 0.0f) {
+      const float val = q < 3 ? vt[static_cast<int64_t>(v) * 3 + q]
+                              : sdirs[(static_cast<int64_t>(v) * 3 + (q - 3) / kBetas) * sd_comps + (q - 3) % kBetas];
+      acc = fmaf(w, val, acc);
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (q < 3) Jt[j * 3 + q] = red[0];
+    else Jd[j * 30 + (q - 3)] = red[0];
+  }
+}
+
+// Blend matrix for the GEMM: Wb[n = v*3 + k][col]: cols [0,189) posedirs[col][n], [189,199) shapedirs[v][k][l],
+// col 199 = v_template[v][k], rest 0; stored as TF32 hi/lo.
+__global__ void build_blend_kernel(const float* __restrict__ posedirs, const float* __restrict__ sdirs,
+                                   const float* __restrict__ vt, int V, int sd_comps, float* __restrict__ hi,
+                                   float* __restrict__ lo, int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int col = static_cast<int>(i % kBlendK);
+  const int64_t n = i / kBlendK;
+  float v = 0.0f;
+  if (n < static_cast<int64_t>(V) * 3) {
+    if (col < kPoseFeat) v = posedirs[static_cast<int64_t>(col) * V * 3 + n];
+    else if (col < kPoseFeat + kBetas) v = sdirs[n * sd_comps + (col - kPoseFeat)];
+    else if (col == kPoseFeat + kBetas) v = vt[n];
+  }
+  const float h = ptx::to_tf32(v);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+// up to kMaxBones (index, weight) pairs per vertex; overflow flag if a vertex has more non-zeros
+__global__ void compress_weights_kernel(const float* __restrict__ W, int V, int* __restrict__ idx, float* __restrict__ wt,
+                                        int* __restrict__ overflow) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int n = 0;
+  for (int j = 0; j < kJ; ++j) {
+    const float w = W[static_cast<int64_t>(v) * kJ + j];
+    if (w != 0.0f) {
+      if (n < kMaxBones) idx[v * kMaxBones + n] = j, wt[v * kMaxBones + n] = w;
+      ++n;
+    }
+  }
+  for (int k = n; k < kMaxBones; ++k) idx[v * kMaxBones + k] = 0, wt[v * kMaxBones + k] = 0.0f;
+  if (n > kMaxBones) atomicExch(overflow, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward kinematics of all 55 joints + pose features + skinning transforms, one thread per frame
+// ---------------------------------------------------------------------------------------------------------------
+// go [N,3], bp [N,63] axis-angle, betas [N,10], transl [N,3].  Outputs (each optional):
+//   joints [N, nj, 3] (posed joints + transl, nj <= 55), A [N, 55, 12] (rows of the 3x4 skinning transform),
+//   feat hi/lo [N, kBlendK] (pose_feature | betas | 1 | 0...) for the blend GEMM.
+__global__ void __launch_bounds__(128) fk_full_kernel(const float* __restrict__ go, const float* __restrict__ bp,
+                                                      const float* __restrict__ betas, const float* __restrict__ transl,
+                                                      const float* __restrict__ Jt, const float* __restrict__ Jd,
+                                                      int N, float* __restrict__ joints, int nj, float* __restrict__ A,
+                                                      float* __restrict__ feat_hi, float* __restrict__ feat_lo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float be[kBetas];
+#pragma unroll
+  for (int l = 0; l < kBetas; ++l) be[l] = betas[static_cast<int64_t>(n) * kBetas + l];
+  const V3 tr = {transl[n * 3], transl[n * 3 + 1], transl[n * 3 + 2]};
+  // world transforms of the joints processed so far (55 x (R, t)) live in local memory; parents precede children
+  M3 Wr[kJ];
+  V3 Wt[kJ];
+  V3 Jrest[kJ];
+  for (int j = 0; j < kJ; ++j) {
+    V3 J = {Jt[j * 3], Jt[j * 3 + 1], Jt[j * 3 + 2]};
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) {
+      J.x = fmaf(Jd[j * 30 + l], be[l], J.x);
+      J.y = fmaf(Jd[j * 30 + 10 + l], be[l], J.y);
+      J.z = fmaf(Jd[j * 30 + 20 + l], be[l], J.z);
+    }
+    Jrest[j] = J;
+    M3 R = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    if (j < kBodyJ) {
+      const float* r = (j == 0) ? go + static_cast<int64_t>(n) * 3 : bp + static_cast<int64_t>(n) * 63 + (j - 1) * 3;
+      R = rodrigues({r[0], r[1], r[2]});
+      if (j > 0 && feat_hi != nullptr) {
+        const float pf[9] = {R.c0.x - 1.f, R.c1.x, R.c2.x, R.c0.y, R.c1.y - 1.f, R.c2.y, R.c0.z, R.c1.z, R.c2.z - 1.f};
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+          const float h = ptx::to_tf32(pf[e]);
+          feat_hi[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = h;
+          feat_lo[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = pf[e] - h;
+        }
+      }
+    }
+    const int p = c_parents[j];
+    if (p < 0) {
+      Wr[j] = R, Wt[j] = J;
+    } else {
+      Wr[j] = mul(Wr[p], R);
+      Wt[j] = Wt[p] + mul(Wr[p], J - Jrest[p]);
+    }
+    if (joints != nullptr && j < nj) {
+      float* o = joints + (static_cast<int64_t>(n) * nj + j) * 3;
+      o[0] = Wt[j].x + tr.x, o[1] = Wt[j].y + tr.y, o[2] = Wt[j].z + tr.z;
+    }
+    if (A != nullptr) {  // A_j = [W_r | W_t - W_r J_rest], translation folded in
+      const V3 t = Wt[j] - mul(Wr[j], J) + tr;
+      float* o = A + (static_cast<int64_t>(n) * kJ + j) * 12;
+      o[0] = Wr[j].c0.x, o[1] = Wr[j].c1.x, o[2] = Wr[j].c2.x, o[3] = t.x;
+      o[4] = Wr[j].c0.y, o[5] = Wr[j].c1.y, o[6] = Wr[j].c2.y, o[7] = t.y;
+      o[8] = Wr[j].c0.z, o[9] = Wr[j].c1.z, o[10] = Wr[j].c2.z, o[11] = t.z;
+    }
+  }
+  if (feat_hi != nullptr) {
+    float* fh = feat_hi + static_cast<int64_t>(n) * kBlendK;
+    float* fl = feat_lo + static_cast<int64_t>(n) * kBlendK;
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) {
+      const float h = ptx::to_tf32(be[l]);
+      fh[kPoseFeat + l] = h, fl[kPoseFeat + l] = be[l] - h;
+    }
+    fh[kPoseFeat + kBetas] = 1.0f, fl[kPoseFeat + kBetas] = 0.0f;
+    for (int c = kPoseFeat + kBetas + 1; c < kBlendK; ++c) fh[c] = 0.0f, fl[c] = 0.0f;
+  }
+}
+
+// verts[n][v] = sum_k w_k A[n][j_k] [v_posed[n][v]; 1]   (translation already folded into A)
+__global__ void __launch_bounds__(256) skin_kernel(const float* __restrict__ vposed, int64_t vp_pitch,
+                                                   const float* __restrict__ A, const int* __restrict__ idx,
+                                                   const float* __restrict__ wt, int V, float* __restrict__ verts) {
+  __shared__ float sA[kJ * 12];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < kJ * 12; i += blockDim.x) sA[i] = A[static_cast<int64_t>(n) * kJ * 12 + i];
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float* p = vposed + static_cast<int64_t>(n) * vp_pitch + static_cast<int64_t>(v) * 3;
+  const float x = p[0], y = p[1], z = p[2];
+  float T[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kMaxBones; ++k) {
+    const float w = wt[v * kMaxBones + k];
+    if (w != 0.0f) {
+      const float* a = sA + idx[v * kMaxBones + k] * 12;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[e] = fmaf(w, a[e], T[e]);
+    }
+  }
+  float* o = verts + (static_cast<int64_t>(n) * V + v) * 3;
+  o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+  o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+  o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+}
+
+// dense fallback when a vertex has more than kMaxBones non-zero weights
+__global__ void __launch_bounds__(256) skin_dense_kernel(const float* __restrict__ vposed, int64_t vp_pitch,
+                                                         const float* __restrict__ A, const float* __restrict__ W, int V,
+                                                         float* __restrict__ verts) {
+  __shared__ float sA[kJ * 12];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < kJ * 12; i += blockDim.x) sA[i] = A[static_cast<int64_t>(n) * kJ * 12 + i];
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float* p = vposed + static_cast<int64_t>(n) * vp_pitch + static_cast<int64_t>(v) * 3;
+  const float x = p[0], y = p[1], z = p[2];
+  float T[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+  for (int j = 0; j < kJ; ++j) {
+    const float w = W[static_cast<int64_t>(v) * kJ + j];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = fmaf(w, sA[j * 12 + e], T[e]);
+  }
+  float* o = verts + (static_cast<int64_t>(n) * V + v) * 3;
+  o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+  o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+  o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// motion representation [B, 294, 1, T] -> SMPL-X parameters (rot6d -> R -> axis-angle), one thread per (frame, joint)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kC = 294;
+constexpr int kChAngle = 0, kChRootPos = 2, kChHeight = 6, kChRot6d = 7, kChTrans = 16, kChLocalPos = 22,
+              kChBodyPose = 154, kChBetas = 280, kChContact = 290;
+
+__global__ void repr_to_smplx_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ stdv, int B, int T, float* __restrict__ go,
+                                     float* __restrict__ bp, float* __restrict__ betas, float* __restrict__ transl) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t frames = static_cast<int64_t>(B) * T;
+  if (i >= frames * kBodyJ) return;
+  const int j = static_cast<int>(i % kBodyJ);
+  const int64_t f = i / kBodyJ;
+  const int b = static_cast<int>(f / T), t = static_cast<int>(f % T);
+  auto ch = [&](int c) { return x[(static_cast<int64_t>(b) * kC + c) * T + t] * stdv[c] + mean[c]; };
+  const int c0 = (j == 0) ? kChRot6d : kChBodyPose + (j - 1) * 6;
+  float r6[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) r6[e] = ch(c0 + e);
+  const V3 aa = mat_to_aa(rot6d_to_mat(r6));
+  float* o = (j == 0) ? go + f * 3 : bp + f * 63 + (j - 1) * 3;
+  o[0] = aa.x, o[1] = aa.y, o[2] = aa.z;
+  if (j == 0) {
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) betas[f * kBetas + l] = ch(kChBetas + l);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) transl[f * 3 + k] = ch(kChTrans + k);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// skating guidance (posenet.py:196-257), one thread per frame
+// ---------------------------------------------------------------------------------------------------------------
+// leg chains: joints 0-1-4-7-10 (left) and 0-2-5-8-11 (right); foot joints in the reference's order [7, 10, 8, 11]
+struct LegFK {
+  M3 W[4];  // world rotations of joints (0, hip, knee, ankle)
+  V3 p[5];  // world positions of (0, hip, knee, ankle, toe)
+  V3 d[5];  // rest offsets J_j - J_parent (d[0] = J_0)
+};
+
+__device__ __forceinline__ void leg_forward(const M3& R0, const M3* R, const V3* d, LegFK& L) {
+  L.W[0] = R0;
+  L.p[0] = d[0];
+  for (int k = 1; k <= 4; ++k) {
+    L.p[k] = L.p[k - 1] + mul(L.W[k - 1], d[k]);
+    if (k <= 3) L.W[k] = mul(L.W[k - 1], R[k - 1]);
+  }
+}
+
+struct GuideWs {
+  float* foot;   // [2 paths][B*T][4][3] foot joint positions (path 0: abs traj, 1: SMPL-X)
+  float* gdir;   // [2][B*T][4][3] dL/dposition before the 1/count normalisation
+  float* sums;   // [4]: sum_abs, cnt_abs, sum_smpl, cnt_smpl
+};
+
+__device__ __forceinline__ float ld_ch(const float* x, const float* mean, const float* stdv, int b, int t, int T, int c) {
+  return x[(static_cast<int64_t>(b) * kC + c) * T + t] * stdv[c] + mean[c];
+}
+
+// pass 1: foot joint positions of both recovery paths
+__global__ void __launch_bounds__(128) guide_forward_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ stdv, const float* __restrict__ Jt,
+                                                            const float* __restrict__ Jd, int B, int T, GuideWs ws) {
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t frames = static_cast<int64_t>(B) * T;
+  if (f >= frames) return;
+  const int b = static_cast<int>(f / T), t = static_cast<int>(f % T);
+  auto ch = [&](int c) { return ld_ch(x, mean, stdv, b, t, T, c); };
+  // ---- abs-traj path: p = Rz(-2a) lp + (rx, ry, 0)  (qrot(qinv(q)), q = (cos a, 0, 0, sin a)) ----
+  {
+    const float a = ch(kChAngle), rx = ch(kChRootPos), ry = ch(kChRootPos + 1);
+    float sn, cs;
+    sincosf(a, &sn, &cs);
+    const int feet[4] = {7, 10, 8, 11};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const V3 v = {ch(kChLocalPos + feet[k] * 3), ch(kChLocalPos + feet[k] * 3 + 1), ch(kChLocalPos + feet[k] * 3 + 2)};
+      // v + 2 (w (qv x v) + qv x (qv x v)), qv = (0, 0, -sin a), w = cos a
+      const V3 qv = {0.0f, 0.0f, -sn};
+      const V3 uv = cross(qv, v);
+      const V3 uuv = cross(qv, uv);
+      const V3 p = {v.x + 2.0f * (cs * uv.x + uuv.x) + rx, v.y + 2.0f * (cs * uv.y + uuv.y) + ry,
+                    v.z + 2.0f * (cs * uv.z + uuv.z)};
+      float* o = ws.foot + (f * 4 + k) * 3;
+      o[0] = p.x, o[1] = p.y, o[2] = p.z;
+    }
+  }
+  // ---- SMPL-X path ----
+  {
+    float be[kBetas];
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) be[l] = ch(kChBetas + l);
+    auto restJ = [&](int j) {
+      V3 J = {Jt[j * 3], Jt[j * 3 + 1], Jt[j * 3 + 2]};
+#pragma unroll
+      for (int l = 0; l < kBetas; ++l) {
+        J.x = fmaf(Jd[j * 30 + l], be[l], J.x);
+        J.y = fmaf(Jd[j * 30 + 10 + l], be[l], J.y);
+        J.z = fmaf(Jd[j * 30 + 20 + l], be[l], J.z);
+      }
+      return J;
+    };
+    auto rotJ = [&](int j) {
+      float r6[6];
+      const int c0 = (j == 0) ? kChRot6d : kChBodyPose + (j - 1) * 6;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) r6[e] = ch(c0 + e);
+      return rodrigues(mat_to_aa(rot6d_to_mat(r6)));  // the reference's 6D -> R -> axis-angle -> R round trip
+    };
+    const V3 tr = {ch(kChTrans), ch(kChTrans + 1), ch(kChTrans + 2)};
+    const M3 R0 = rotJ(0);
+    const V3 J0 = restJ(0);
+    const int chain[2][4] = {{1, 4, 7, 10}, {2, 5, 8, 11}};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      M3 R[3];
+      V3 d[5];
+      d[0] = J0;
+      V3 prev = J0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const V3 J = restJ(chain[s][k]);
+        d[k + 1] = J - prev;
+        prev = J;
+        if (k < 3) R[k] = rotJ(chain[s][k]);
+      }
+      LegFK L;
+      leg_forward(R0, R, d, L);
+      float* o = ws.foot + ((frames + f) * 4 + s * 2) * 3;  // [ankle, toe] of this side: order 7,10 | 8,11
+      o[0] = L.p[3].x + tr.x, o[1] = L.p[3].y + tr.y, o[2] = L.p[3].z + tr.z;
+      o[3] = L.p[4].x + tr.x, o[4] = L.p[4].y + tr.y, o[5] = L.p[4].z + tr.z;
+    }
+  }
+}
+
+// pass 2: foot speeds, masks, loss sums, and dL/dposition directions
+__global__ void __launch_bounds__(128) guide_loss_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                         const float* __restrict__ stdv, int B, int T, GuideWs ws) {
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t frames = static_cast<int64_t>(B) * T;
+  float lsum[2] = {0.f, 0.f}, lcnt[2] = {0.f, 0.f};
+  if (f < frames) {
+    const int b = static_cast<int>(f / T), t = static_cast<int>(f % T);
+#pragma unroll
+    for (int path = 0; path < 2; ++path) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // gradient on p(t) = +m(t-1) vhat(t-1) - m(t) vhat(t), each scaled by fps (d|v|/dp)
+        V3 g = {0.f, 0.f, 0.f};
+        const float* p0 = ws.foot + ((path * frames + f) * 4 + k) * 3;
+        if (t + 1 < T) {
+          const float* p1 = p0 + 12;
+          const V3 v = {(p1[0] - p0[0]) * 30.0f, (p1[1] - p0[1]) * 30.0f, (p1[2] - p0[2]) * 30.0f};
+          const float sp = sqrtf(dot(v, v));
+          const float contact = ld_ch(x, mean, stdv, b, t, T, kChContact + k) > 0.5f ? 1.0f : 0.0f;
+          if (sp - 0.1f > 0.0f && contact > 0.0f) {
+            lsum[path] += sp, lcnt[path] += 1.0f;
+            g = g - (30.0f / sp) * v;
+          }
+        }
+        if (t > 0) {
+          const float* pm = p0 - 12;
+          const V3 v = {(p0[0] - pm[0]) * 30.0f, (p0[1] - pm[1]) * 30.0f, (p0[2] - pm[2]) * 30.0f};
+          const float sp = sqrtf(dot(v, v));
+          const float contact = ld_ch(x, mean, stdv, b, t - 1, T, kChContact + k) > 0.5f ? 1.0f : 0.0f;
+          if (sp - 0.1f > 0.0f && contact > 0.0f) g = g + (30.0f / sp) * v;
+        }
+        float* o = ws.gdir + ((path * frames + f) * 4 + k) * 3;
+        o[0] = g.x, o[1] = g.y, o[2] = g.z;
+      }
+    }
+  }
+  // block reduction of the four scalars, then one atomic each
+  __shared__ float red[4][128];
+  red[0][threadIdx.x] = lsum[0], red[1][threadIdx.x] = lcnt[0], red[2][threadIdx.x] = lsum[1], red[3][threadIdx.x] = lcnt[1];
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int q = 0; q < 4; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4 && red[threadIdx.x][0] != 0.0f) atomicAdd(ws.sums + threadIdx.x, red[threadIdx.x][0]);
+}
+
+// pass 3: VJP to the normalised representation; grad = d(-(loss_smpl + loss_abs))/dx0, channels [0,traj) and the
+// contact channels are zero (the output buffer was cleared; only the channels with a non-zero gradient are written)
+__global__ void __launch_bounds__(128) guide_backward_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ stdv, const float* __restrict__ Jt,
+                                                             const float* __restrict__ Jd, int B, int T, GuideWs ws,
+                                                             float* __restrict__ grad) {
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t frames = static_cast<int64_t>(B) * T;
+  if (f >= frames) return;
+  const int b = static_cast<int>(f / T), t = static_cast<int>(f % T);
+  auto ch = [&](int c) { return ld_ch(x, mean, stdv, b, t, T, c); };
+  auto put = [&](int c, float g) { grad[(static_cast<int64_t>(b) * kC + c) * T + t] = g * stdv[c]; };
+  const float cnt_abs = ws.sums[1], cnt_smpl = ws.sums[3];
+  const float sc_abs = cnt_abs != 0.0f ? -1.0f / cnt_abs : 0.0f;   // loss enters as -(loss)
+  const float sc_smpl = cnt_smpl != 0.0f ? -1.0f / cnt_smpl : 0.0f;
+  // ---- abs path: p = Rz(-2a) lp + ...;  dL/dlp = Rz(-2a)^T g ----
+  {
+    const float a = ch(kChAngle);
+    float sn, cs;
+    sincosf(2.0f * a, &sn, &cs);  // Rz(-2a) = [[c, s, 0], [-s, c, 0], [0, 0, 1]]
+    const int feet[4] = {7, 10, 8, 11};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* g = ws.gdir + (f * 4 + k) * 3;
+      const float gx = sc_abs * g[0], gy = sc_abs * g[1], gz = sc_abs * g[2];
+      put(kChLocalPos + feet[k] * 3, cs * gx - sn * gy);
+      put(kChLocalPos + feet[k] * 3 + 1, sn * gx + cs * gy);
+      put(kChLocalPos + feet[k] * 3 + 2, gz);
+    }
+  }
+  // ---- SMPL-X path ----
+  {
+    float be[kBetas], gbe[kBetas];
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) be[l] = ch(kChBetas + l), gbe[l] = 0.0f;
+    auto restJ = [&](int j) {
+      V3 J = {Jt[j * 3], Jt[j * 3 + 1], Jt[j * 3 + 2]};
+#pragma unroll
+      for (int l = 0; l < kBetas; ++l) {
+        J.x = fmaf(Jd[j * 30 + l], be[l], J.x);
+        J.y = fmaf(Jd[j * 30 + 10 + l], be[l], J.y);
+        J.z = fmaf(Jd[j * 30 + 20 + l], be[l], J.z);
+      }
+      return J;
+    };
+    // dL/dbeta += (dJ_j/dbeta)^T g  for a gradient g on the rest position of joint j (sign: +1 for J_j, -1 for parent)
+    auto acc_beta = [&](int j, V3 g, float sign) {
+#pragma unroll
+      for (int l = 0; l < kBetas; ++l)
+        gbe[l] += sign * (Jd[j * 30 + l] * g.x + Jd[j * 30 + 10 + l] * g.y + Jd[j * 30 + 20 + l] * g.z);
+    };
+    float r6[7][6];  // joints 0, then (1,4,7), (2,5,8)
+    const int rot_joint[7] = {0, 1, 4, 7, 2, 5, 8};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const int c0 = (rot_joint[q] == 0) ? kChRot6d : kChBodyPose + (rot_joint[q] - 1) * 6;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) r6[q][e] = ch(c0 + e);
+    }
+    const M3 R0 = rot6d_to_mat(r6[0]);
+    const V3 J0 = restJ(0);
+    const int chain[2][4] = {{1, 4, 7, 10}, {2, 5, 8, 11}};
+    V3 a0 = {0.f, 0.f, 0.f};  // gradient reaching the root position (-> betas through J_0)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      M3 R[3];
+      V3 d[5];
+      d[0] = J0;
+      V3 prev = J0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const V3 J = restJ(chain[s][k]);
+        d[k + 1] = J - prev;
+        prev = J;
+        if (k < 3) R[k] = rot6d_to_mat(r6[1 + s * 3 + k]);
+      }
+      LegFK L;
+      leg_forward(R0, R, d, L);
+      const float* g = ws.gdir + ((frames + f) * 4 + s * 2) * 3;
+      const V3 g_ankle = {sc_smpl * g[0], sc_smpl * g[1], sc_smpl * g[2]};
+      const V3 g_toe = {sc_smpl * g[3], sc_smpl * g[4], sc_smpl * g[5]};
+      // a[k]: gradient w.r.t. the world position of chain node k (0 root, 1 hip, 2 knee, 3 ankle, 4 toe)
+      const V3 a4 = g_toe, a3 = g_ankle + g_toe;
+      const V3 a2 = a3, a1 = a3;
+      a0 = a0 + a1;
+      const V3 a[5] = {a1, a1, a2, a3, a4};
+      // rest offsets: p_k = p_{k-1} + W_{k-1} d_k  ->  dL/dd_k = W_{k-1}^T a_k
+#pragma unroll
+      for (int k = 1; k <= 4; ++k) {
+        const V3 gd = mulT(L.W[k - 1], a[k]);
+        acc_beta(chain[s][k - 1], gd, 1.0f);
+        acc_beta(k == 1 ? 0 : chain[s][k - 2], gd, -1.0f);
+      }
+      // world-rotation gradients, leaf to root: GW_k = a_{k+1} d_{k+1}^T + GW_{k+1} R_{k+1}^T ; dL/dR_k = W_{k-1}^T GW_k
+      // (outer product u v^T stored by columns: column c = v_c * u)
+      M3 GW = {d[4].x * a[4], d[4].y * a[4], d[4].z * a[4]};  // node 3 (ankle joint rotation)
+#pragma unroll
+      for (int k = 3; k >= 1; --k) {
+        // gradient of the local rotation of chain node k (joint chain[s][k-1])
+        const M3 GR = {mulT(L.W[k - 1], GW.c0), mulT(L.W[k - 1], GW.c1), mulT(L.W[k - 1], GW.c2)};
+        float gx[6];
+        rot6d_backward(r6[1 + s * 3 + (k - 1)], GR, gx);
+        const int c0 = kChBodyPose + (chain[s][k - 1] - 1) * 6;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) put(c0 + e, gx[e]);
+        if (k > 1) {
+          // GW_{k-1} = a_k d_k^T + GW_k R_k^T ; (GW R^T) column c = sum_m R[c][m] GW.col(m) = GW * (row c of R)
+          const M3& Rk = R[k - 1];
+          const M3 GWR = {Rk.c0.x * GW.c0 + Rk.c1.x * GW.c1 + Rk.c2.x * GW.c2,
+                          Rk.c0.y * GW.c0 + Rk.c1.y * GW.c1 + Rk.c2.y * GW.c2,
+                          Rk.c0.z * GW.c0 + Rk.c1.z * GW.c1 + Rk.c2.z * GW.c2};
+          GW = {d[k].x * a[k] + GWR.c0, d[k].y * a[k] + GWR.c1, d[k].z * a[k] + GWR.c2};
+        }
+      }
+    }
+    acc_beta(0, a0, 1.0f);
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) put(kChBetas + l, gbe[l]);
+  }
+}
+
+}  // namespace
+}  // namespace rohm
+
+using namespace rohm;
+
+struct rohm_body {
+  rohm_ctx* ctx = nullptr;
+  DevicePool pool;
+  int V = 0, sd_comps = 0, passes = 3;
+  int64_t max_frames = 0;
+  float *Jt = nullptr, *Jd = nullptr;
+  const float* lbs_w = nullptr;  // dense weights copy
+  float* lbs_w_copy = nullptr;
+  int* bone_idx = nullptr;
+  float* bone_w = nullptr;
+  bool sparse_ok = true;
+  PackedWeight blend;  // [V*3 (padded), 224]
+  // per-frame workspace
+  float *go = nullptr, *bp = nullptr, *betas = nullptr, *transl = nullptr, *A = nullptr, *feat_h = nullptr,
+        *feat_l = nullptr, *vposed = nullptr;
+  float *foot = nullptr, *gdir = nullptr, *sums = nullptr;
+  GemmParams g_blend{};
+};
+
+extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const float* shapedirs, int shape_comps,
+                                const float* posedirs, const float* J_regressor, const float* lbs_weights,
+                                const int* parents_host, int num_verts, int64_t max_frames, int with_vertices,
+                                int precision, rohm_body** out) {
+  if (ctx == nullptr) return ROHM_ERR_INVALID;
+  if (!v_template || !shapedirs || !J_regressor || !parents_host || !out || num_verts <= 0 || max_frames <= 0 ||
+      shape_comps < kBetas || (with_vertices && (!posedirs || !lbs_weights)))
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_body_create: bad arguments");
+  for (int j = 0; j < kJ; ++j)
+    if (parents_host[j] >= j) return fail(ctx, ROHM_ERR_INVALID, "rohm_body_create: parents must precede children");
+  ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
+  rohm_body* bd = new (std::nothrow) rohm_body();
+  if (!bd) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
+  bd->ctx = ctx, bd->V = num_verts, bd->sd_comps = shape_comps, bd->max_frames = max_frames, bd->passes = precision;
+  ROHM_CUDA(ctx, cudaMemcpyToSymbol(c_parents, parents_host, sizeof(int) * kJ));
+  const int V = num_verts;
+  const int64_t F = max_frames;
+  bd->Jt = bd->pool.floats(kJ * 3);
+  bd->Jd = bd->pool.floats(kJ * 30);
+  bd->foot = bd->pool.floats(2 * F * 12);
+  bd->gdir = bd->pool.floats(2 * F * 12);
+  bd->sums = bd->pool.floats(4);
+  bd->go = bd->pool.floats(F * 3), bd->bp = bd->pool.floats(F * 63), bd->betas = bd->pool.floats(F * kBetas);
+  bd->transl = bd->pool.floats(F * 3);
+  bool ok = bd->Jt && bd->Jd && bd->foot && bd->gdir && bd->sums && bd->go && bd->bp && bd->betas && bd->transl;
+  if (ok && with_vertices) {
+    bd->A = bd->pool.floats(F * kJ * 12);
+    bd->feat_h = bd->pool.floats(F * kBlendK), bd->feat_l = bd->pool.floats(F * kBlendK);
+    bd->vposed = bd->pool.floats(F * round_up(V * 3, 128));  // row pitch padded to the GEMM tile: vector stores
+    bd->bone_idx = static_cast<int*>(bd->pool.bytes(static_cast<int64_t>(V) * kMaxBones * sizeof(int)));
+    bd->bone_w = bd->pool.floats(static_cast<int64_t>(V) * kMaxBones);
+    bd->lbs_w_copy = bd->pool.floats(static_cast<int64_t>(V) * kJ);
+    bd->blend.N = V * 3, bd->blend.K = kBlendK, bd->blend.Kp = kBlendK, bd->blend.block_n = 128;
+    bd->blend.Np = static_cast<int>(round_up(V * 3, 128));
+    bd->blend.hi = bd->pool.floats(static_cast<int64_t>(bd->blend.Np) * kBlendK);
+    bd->blend.lo = bd->pool.floats(static_cast<int64_t>(bd->blend.Np) * kBlendK);
+    ok = bd->A && bd->feat_h && bd->feat_l && bd->vposed && bd->bone_idx && bd->bone_w && bd->lbs_w_copy && bd->blend.hi &&
+         bd->blend.lo;
+  }
+  if (!ok) {
+    const int rc = fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: alloc failed: %s", cudaGetErrorString(bd->pool.last_error()));
+    delete bd;
+    return rc;
+  }
+  joint_regress_kernel<<<dim3(kJ, 33), 256>>>(J_regressor, v_template, shapedirs, V, shape_comps, bd->Jt, bd->Jd);
+  if (with_vertices) {
+    int* overflow = static_cast<int*>(bd->pool.bytes(sizeof(int)));
+    cudaMemcpy(bd->lbs_w_copy, lbs_weights, sizeof(float) * V * kJ, cudaMemcpyDeviceToDevice);
+    compress_weights_kernel<<<(V + 255) / 256, 256>>>(lbs_weights, V, bd->bone_idx, bd->bone_w, overflow);
+    const int64_t total = static_cast<int64_t>(bd->blend.Np) * kBlendK;
+    build_blend_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(posedirs, shapedirs, v_template, V,
+                                                                            shape_comps, bd->blend.hi, bd->blend.lo, total);
+    int h_over = 0;
+    cudaError_t e = cudaMemcpy(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      delete bd;
+      return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: %s", cudaGetErrorString(e));
+    }
+    bd->sparse_ok = (h_over == 0);
+    cudaError_t ea = gemm_init_attributes();
+    GemmParams& g = bd->g_blend;
+    g = GemmParams{};
+    int rc = make_tmap_2d(&g.a_hi[0], bd->feat_h, F, kBlendK, kBlendK, kGemmBlockM);
+    rc |= make_tmap_2d(&g.a_lo[0], bd->feat_l, F, kBlendK, kBlendK, kGemmBlockM);
+    rc |= make_tmap_2d(&g.b_hi, bd->blend.hi, bd->blend.Np, kBlendK, kBlendK, 128);
+    rc |= make_tmap_2d(&g.b_lo, bd->blend.lo, bd->blend.Np, kBlendK, kBlendK, 128);
+    if (rc != 0 || ea != cudaSuccess) {
+      delete bd;
+      return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: GEMM setup failed (%d)", rc);
+    }
+    g.num_segs = 1, g.seg_kblocks[0] = kBlendK / kGemmBlockK, g.seg_row_mul[0] = 1;
+    g.out = bd->vposed, g.ldo = bd->blend.Np, g.N = bd->blend.Np, g.out_row_mul = 1;  // padded columns are exact zeros
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    delete bd;
+    return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: %s", cudaGetErrorString(e));
+  }
+  *out = bd;
+  return ROHM_OK;
+}
+
+extern "C" void rohm_body_destroy(rohm_body* bd) { delete bd; }
+
+// SMPLX.forward as RoHM calls it (jaw / eyes / hands / expression zero).  global_orient [N,3], body_pose [N,63]
+// (axis-angle), betas [N,10], transl [N,3] -> joints [N, num_joints<=55, 3] and (optionally) vertices [N, V, 3].
+extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, const float* body_pose, const float* betas,
+                                 const float* transl, int64_t N, float* joints, int num_joints, float* vertices,
+                                 void* stream) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = bd->ctx;
+  if (!global_orient || !body_pose || !betas || !transl || N <= 0 || N > bd->max_frames || num_joints < 0 ||
+      num_joints > kJ || (joints == nullptr && vertices == nullptr))
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_body_forward: bad arguments (N=%lld, capacity %lld)",
+                static_cast<long long>(N), static_cast<long long>(bd->max_frames));
+  if (vertices != nullptr && bd->vposed == nullptr)
+    return fail(ctx, ROHM_ERR_STATE, "rohm_body_forward: handle was created without vertex support");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool verts = vertices != nullptr;
+  fk_full_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(
+      global_orient, body_pose, betas, transl, bd->Jt, bd->Jd, static_cast<int>(N), joints, num_joints,
+      verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  if (verts) {
+    GemmParams g = bd->g_blend;
+    g.M = static_cast<int>(N);
+    ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 128, bd->passes, st));
+    dim3 grid((bd->V + 255) / 256, static_cast<unsigned>(N));
+    if (bd->sparse_ok)
+      skin_kernel<<<grid, 256, 0, st>>>(bd->vposed, bd->blend.Np, bd->A, bd->bone_idx, bd->bone_w, bd->V, vertices);
+    else
+      skin_dense_kernel<<<grid, 256, 0, st>>>(bd->vposed, bd->blend.Np, bd->A, bd->lbs_w_copy, bd->V, vertices);
+    ROHM_CUDA(ctx, cudaGetLastError());
+  }
+  return ROHM_OK;
+}
+
+// recover_from_repr_smpl(recover_mode='smplx_params') on a normalised representation x [B, 294, 1, T]:
+// joints [B*T, num_joints, 3] and optionally vertices [B*T, V, 3].
+extern "C" int rohm_body_from_repr(rohm_body* bd, const float* x, const float* mean, const float* stdv, int B, int T,
+                                   float* joints, int num_joints, float* vertices, void* stream) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = bd->ctx;
+  const int64_t N = static_cast<int64_t>(B) * T;
+  if (!x || !mean || !stdv || B <= 0 || T <= 0 || N > bd->max_frames)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_body_from_repr: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = N * kBodyJ;
+  repr_to_smplx_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, mean, stdv, B, T, bd->go, bd->bp,
+                                                                                 bd->betas, bd->transl);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  return rohm_body_forward(bd, bd->go, bd->bp, bd->betas, bd->transl, N, joints, num_joints, vertices, stream);
+}
+
+// guide_skating_with_smpl (posenet.py:196-257): grad [B, 294, 1, T] = d(-(loss_smpl + loss_abs))/dx0 with the
+// trajectory and contact channels zeroed.  If nothing skates the gradient is all zeros (the reference returns a
+// scalar 0 in that case; adding weight*variance*0 is the same update).  loss_out (device float[4], optional) receives
+// {sum_abs, count_abs, sum_smpl, count_smpl}.
+extern "C" int rohm_skating_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                     float* grad, float* loss_out, void* stream) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = bd->ctx;
+  const int64_t N = static_cast<int64_t>(B) * T;
+  if (!x0 || !mean || !stdv || !grad || B <= 0 || T <= 0 || N > bd->max_frames)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_skating_guidance: bad arguments (B*T=%lld, capacity %lld)",
+                static_cast<long long>(N), static_cast<long long>(bd->max_frames));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GuideWs ws{bd->foot, bd->gdir, bd->sums};
+  ROHM_CUDA(ctx, cudaMemsetAsync(bd->sums, 0, 4 * sizeof(float), st));
+  ROHM_CUDA(ctx, cudaMemsetAsync(grad, 0, sizeof(float) * N * kC, st));
+  const unsigned blocks = static_cast<unsigned>((N + 127) / 128);
+  guide_forward_kernel<<<blocks, 128, 0, st>>>(x0, mean, stdv, bd->Jt, bd->Jd, B, T, ws);
+  guide_loss_kernel<<<blocks, 128, 0, st>>>(x0, mean, stdv, B, T, ws);
+  guide_backward_kernel<<<blocks, 128, 0, st>>>(x0, mean, stdv, bd->Jt, bd->Jd, B, T, ws, grad);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  if (loss_out != nullptr)
+    ROHM_CUDA(ctx, cudaMemcpyAsync(loss_out, bd->sums, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return ROHM_OK;
+}

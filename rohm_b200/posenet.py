@@ -234,6 +234,40 @@ class PoseNet(nn.Module):
             e.cond_key = key
         return e
 
+    # ---------------------------------------------------------------- test-time guidance
+    def _norm_stats(self, device):
+        key = (str(device), id(self.dataset))
+        if getattr(self, "_norm_cache_key", None) != key:
+            self._norm_cache = (torch.from_numpy(np.ascontiguousarray(self.dataset.Mean, dtype=np.float32)).to(device),
+                                torch.from_numpy(np.ascontiguousarray(self.dataset.Std, dtype=np.float32)).to(device))
+            self._norm_cache_key = key
+        return self._norm_cache
+
+    def guide_skating_with_smpl(self, batch, out, denoise_t, compute_grad='x_t'):
+        """Gradient of -(foot-skating loss from SMPL-X joints + from the joint-based representation) w.r.t. x_t or the
+        predicted x_0 (reference posenet.py:196-257), [bs, body_feat_dim, 1, T], trajectory and contact channels zero.
+        One fused analytic forward+VJP (rohm_skating_guidance) instead of autograd through the body model; when nothing
+        skates the result is an all-zero tensor (the reference returns a 0-dim zero), so no host sync is needed."""
+        from .body_model import kernels_for
+        x = batch['x_t'] if compute_grad == 'x_t' else out['pred_xstart']
+        x = x.detach()
+        x = x if (x.is_contiguous() and x.dtype == torch.float32) else x.contiguous().float()
+        if self.dataset.traj_feat_dim != 22 or x.shape[1] != 294:
+            raise RohmB200Error("guide_skating_with_smpl: implemented for the 294-channel representation with the "
+                                "22-channel trajectory block (the configuration RoHM ships)")
+        B, _, _, T = x.shape
+        mean, std = self._norm_stats(x.device)
+        k = kernels_for(self.smplx_model, x.device, B * T, with_vertices=False)
+        return k.skating_guidance(x, mean, std)
+
+    def guide_2d_projection_with_smpl(self, batch, out, denoise_t, compute_grad='x_t'):
+        raise NotImplementedError("2-D reprojection guidance (grad_type='prox') is a listed next row (SURVEY.md 8f N2), "
+                                  "not part of this build")
+
+    def compute_losses_with_smpl(self, batch, model_output, smplx_model=None, epoch=0):
+        raise NotImplementedError("training / evaluation losses are out of scope of the inference hot path; call "
+                                  "eval_losses(..., compute_loss=False) as test_amass_full.py does")
+
     # ---------------------------------------------------------------- forward
     def forward(self, batch, timesteps):
         """batch['x_t'], batch['cond']: [bs, body_feat_dim, 1, T]; timesteps: [bs] int -> [bs, body_feat_dim, 1, T]

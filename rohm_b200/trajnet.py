@@ -127,6 +127,10 @@ class TrajNet(nn.Module):
         self._engine = None
         return super().load_state_dict(*a, **k)
 
+    def compute_losses_with_smpl(self, batch, model_output, smplx_model=None):
+        raise NotImplementedError("training / evaluation losses are out of scope of the inference hot path; call "
+                                  "eval_losses(..., compute_loss=False) as test_amass_full.py does")
+
     def forward(self, batch, time):
         """batch['x_t'], batch['cond']: [bs, T, traj_dim]; batch['control_cond']: [bs, T, 272] when trajcontrol;
         time: [bs] int -> [bs, T, traj_dim] (reconstructed trajectory representation at timestep 0)."""
