@@ -183,9 +183,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       const int acc_stage = tcount % Cfg::kAccStages;
       const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
       const int m = m0 + q * 32 + lane;
-      ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
-      ptx::tc_fence_after_sync();
-
       const bool row_ok = m < p.M;
       bool row_real = true;
       int clip = 0;
@@ -195,21 +192,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       }
       const int64_t orow = static_cast<int64_t>(m) * p.out_row_mul + p.out_row_add;
 
+      // The residual tile comes from L2/HBM: fetch the first chunk while the MMA warp is still accumulating (these
+      // warps are otherwise idle), and each following chunk while the current one is being processed.
+      float4 rcur[8], rnext[8];
+      auto residual_vec_ok = [&](int c0) {
+        const int nb = n0 + c0;
+        return p.residual != nullptr && row_ok && vec_ok && c0 < BLOCK_N && nb + 32 <= p.N;
+      };
+      auto fetch_residual = [&](int c0, float4(&dst)[8]) {
+        const float4* r = reinterpret_cast<const float4*>(p.residual + orow * p.ldr + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = r[j];
+      };
+      if (residual_vec_ok(half * 32)) fetch_residual(half * 32, rcur);
+
+      ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      ptx::tc_fence_after_sync();
+
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
-        uint32_t raw[32];
+        uint32_t raw[32], raw2[32];
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
                                (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
         ptx::tmem_ld_32x32(taddr, raw);
+        if (PASSES == 3) ptx::tmem_ld_32x32(taddr + BLOCK_N, raw2);
+        const bool have_res = residual_vec_ok(c0);
+        const bool next_res = residual_vec_ok(c0 + 64);
+        if (next_res) fetch_residual(c0 + 64, rnext);
         ptx::tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         if (PASSES == 3) {
-          ptx::tmem_ld_32x32(taddr + BLOCK_N, raw);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
         }
         const int nb = n0 + c0;
         if (nb >= p.N) continue;  // warp-uniform
@@ -234,14 +250,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           }
           if (p.residual != nullptr) {
-            const float* r = p.residual + orow * p.ldr + nb;
-            if (full) {
+            if (have_res) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(r + j);
-                v[j] += t4.x, v[j + 1] += t4.y, v[j + 2] += t4.z, v[j + 3] += t4.w;
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += rcur[j].x, v[4 * j + 1] += rcur[j].y, v[4 * j + 2] += rcur[j].z, v[4 * j + 3] += rcur[j].w;
               }
             } else {
+              const float* r = p.residual + orow * p.ldr + nb;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (nb + j < p.N) v[j] += r[j];
@@ -251,6 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0f;
           }
+        }
+        if (next_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
         }
 
         // ---- GroupNorm partial statistics over real rows ----
