@@ -12,7 +12,8 @@ namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kSmemBudget = 200 * 1024;  // ring buffer budget; + 1 KB alignment slack stays below 227 KB
+constexpr int kSmemBudget = 192 * 1024;  // operand ring budget (3 stages of 64 KB at BLOCK_N = 128, PASSES = 3)
+constexpr int kEpiTileFloats = 32 * 32;   // per-epilogue-warp staging tile (32 x 32, XOR-swizzled columns): coalesced stores
 
 template <int BLOCK_N, int PASSES>
 struct TileCfg {
@@ -22,7 +23,7 @@ struct TileCfg {
   static constexpr int kStageBytes = kSplit * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiTileFloats * 4;
   // PASSES == 3 keeps two accumulators per stage: columns [0, BLOCK_N) take the leading hi*hi products, columns
   // [BLOCK_N, 2*BLOCK_N) the two small cross terms.  The tensor core truncates when it adds into the
   // accumulator, so keeping the ~2^-11-sized terms out of the big sum cuts the rounding count of the main
@@ -38,6 +39,14 @@ struct TileCfg {
   static_assert(BLOCK_N % 32 == 0, "epilogue walks TMEM in 32-column chunks");
 };
 
+__device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
+  if (p.debug_ts != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.debug_ts[slot] = t;
+  }
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActGelu) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // exact (erf) GELU, nn.GELU default
@@ -51,9 +60,22 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+struct EpiParams {
+  const float* bias;
+  const float* residual;
+  float* out;
+  float* out_hi;
+  float* out_lo;
+  double* gn_stats;
+  int ldr, ldo, lds, act, M, N, out_row_mul, out_row_add, clip_rows, clip_valid, gn_groups, gn_group_size;
+};
+
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
 // (N-tile index fastest, so CTAs running concurrently share the same A rows in L2).
-template <int BLOCK_N, int PASSES>
+// LEAN epilogue: bias + residual + fp32 / hi-lo stores only (the PoseNet linears); the full epilogue adds activations,
+// padded-clip row masks and GroupNorm partial sums.  Two instantiations keep the hot variant's code small (the full
+// epilogue is ~7000 SASS instructions, most of them predicated-off activation code when unused).
+template <int BLOCK_N, int PASSES, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   extern __shared__ uint8_t smem_raw[];
@@ -62,6 +84,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   __shared__ uint64_t tmem_full_bar[Cfg::kAccStages];
   __shared__ uint64_t tmem_empty_bar[Cfg::kAccStages];
   __shared__ uint32_t tmem_base_smem;
+  // Epilogue parameters are copied from the (3 KB, tensor-map dominated) kernel parameter block into shared memory
+  // once: reading them late from the constant bank cost ~0.7 us per first touch (measured with %globaltimer stamps).
+  __shared__ EpiParams epi_s;
+  __shared__ float bias_s[Cfg::kAccStages][BLOCK_N];
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -69,6 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) stamp(p, 0);
   const int tiles_n = (p.grid_n_cols + BLOCK_N - 1) / BLOCK_N;
   const int tiles_m = (p.grid_m_rows + kGemmBlockM - 1) / kGemmBlockM;
   const int num_tiles = tiles_m * tiles_n;
@@ -96,11 +123,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   if (warp_idx == 1) {
     ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
   }
+  if (warp_idx == 2 && lane == 0) {
+    epi_s.bias = p.bias, epi_s.residual = p.residual, epi_s.ldr = p.ldr, epi_s.out = p.out, epi_s.ldo = p.ldo;
+    epi_s.out_hi = p.out_hi, epi_s.out_lo = p.out_lo, epi_s.lds = p.lds, epi_s.act = p.act, epi_s.M = p.M, epi_s.N = p.N;
+    epi_s.out_row_mul = p.out_row_mul, epi_s.out_row_add = p.out_row_add, epi_s.clip_rows = p.clip_rows;
+    epi_s.clip_valid = p.clip_valid, epi_s.gn_stats = p.gn_stats, epi_s.gn_groups = p.gn_groups;
+    epi_s.gn_group_size = p.gn_group_size;
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
 
+  if (threadIdx.x == 0) stamp(p, 1);
   // Everything above overlaps the tail of the previous kernel under programmatic dependent launch.
   ptx::pdl_wait_prior_grid();
 
@@ -119,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             const int stage = it % Cfg::kStages;
             const uint32_t phase = (it / Cfg::kStages) & 1;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (it == 0) stamp(p, 2);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kGemmBlockK, row);
@@ -146,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           const int stage = it % Cfg::kStages;
           const uint32_t phase = (it / Cfg::kStages) & 1;
           ptx::mbar_wait(&full_bar[stage], phase);
+          if (it == 0) stamp(p, 3);
           ptx::tc_fence_after_sync();
           const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t a_hi = ptx::make_desc_sw128_kmajor(st);
@@ -168,45 +205,51 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
         ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
+        if (tcount == 0) stamp(p, 4);
       }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // TMEM lane quarter = warp_idx % 4 (hardware rule); the two warps sharing a quarter alternate 32-column chunks.
+    // Data path: TMEM -> registers (one row per thread) -> bias / activation / row mask / GroupNorm sums -> 32x32
+    // staging tile in shared memory -> re-read with 8 lanes per row -> residual add -> 128-byte-coalesced float4
+    // stores (fp32 and/or TF32 hi/lo).  The row-per-thread layout the TMEM load dictates would make every store
+    // instruction touch 32 different rows (measured: 11 us per 128x128 tile with three outputs).
+    const EpiParams e = epi_s;  // registers
     const int q = warp_idx & 3;
     const int half = (warp_idx - 2) >> 2;
-    const bool vec_ok = ((p.N & 3) == 0);
+    const bool vec_ok = ((e.N & 3) == 0);
+    float* tile = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes) + (warp_idx - 2) * kEpiTileFloats;
+    const int tr = lane >> 3, tc = (lane & 7) * 4;  // transposed mapping: rows tr, tr+4, ..., columns tc..tc+3
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int m0 = (tile / tiles_n) * kGemmBlockM;
-      const int n0 = (tile % tiles_n) * BLOCK_N;
+    for (int tile_idx = blockIdx.x; tile_idx < num_tiles; tile_idx += gridDim.x, ++tcount) {
+      const int m0 = (tile_idx / tiles_n) * kGemmBlockM;
+      const int n0 = (tile_idx % tiles_n) * BLOCK_N;
       const int acc_stage = tcount % Cfg::kAccStages;
       const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
       const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < e.M;
       bool row_real = true;
       int clip = 0;
-      if (p.clip_rows > 0) {
-        clip = m / p.clip_rows;
-        row_real = (m - clip * p.clip_rows) < p.clip_valid;
+      if (!LEAN && e.clip_rows > 0) {
+        clip = m / e.clip_rows;
+        row_real = (m - clip * e.clip_rows) < e.clip_valid;
       }
-      const int64_t orow = static_cast<int64_t>(m) * p.out_row_mul + p.out_row_add;
+      const int64_t orow = static_cast<int64_t>(m) * e.out_row_mul + e.out_row_add;
 
-      // The residual tile comes from L2/HBM: fetch the first chunk while the MMA warp is still accumulating (these
-      // warps are otherwise idle), and each following chunk while the current one is being processed.
-      float4 rcur[8], rnext[8];
-      auto residual_vec_ok = [&](int c0) {
-        const int nb = n0 + c0;
-        return p.residual != nullptr && row_ok && vec_ok && c0 < BLOCK_N && nb + 32 <= p.N;
-      };
-      auto fetch_residual = [&](int c0, float4(&dst)[8]) {
-        const float4* r = reinterpret_cast<const float4*>(p.residual + orow * p.ldr + n0 + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = r[j];
-      };
-      if (residual_vec_ok(half * 32)) fetch_residual(half * 32, rcur);
-
+      // stage this tile's bias slice (and warm the residual lines) while the MMA warp is still accumulating
+      {
+        const int i = (warp_idx - 2) * 32 + lane;
+        if (e.bias != nullptr && i < BLOCK_N) bias_s[acc_stage][i] = (n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.0f;
+        if (e.residual != nullptr && row_ok) {
+          const float* r = e.residual + orow * e.ldr + n0 + half * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+          if (BLOCK_N > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 64));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
+      }
       ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 5);
       ptx::tc_fence_after_sync();
 
 #pragma unroll 1
@@ -216,10 +259,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
                                (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
         ptx::tmem_ld_32x32(taddr, raw);
         if (PASSES == 3) ptx::tmem_ld_32x32(taddr + BLOCK_N, raw2);
-        const bool have_res = residual_vec_ok(c0);
-        const bool next_res = residual_vec_ok(c0 + 64);
-        if (next_res) fetch_residual(c0 + 64, rnext);
+        const int nb = n0 + c0;
+        const bool full = vec_ok && (nb + 32 <= e.N);
+        // residual in the transposed (coalesced) layout: loads are issued before waiting on TMEM
+        float4 res[8];
+        const bool use_res = e.residual != nullptr && full;
+        if (use_res) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int mr = m0 + q * 32 + rr * 4 + tr;
+            res[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mr < e.M)
+              res[rr] = *reinterpret_cast<const float4*>(
+                  e.residual + (static_cast<int64_t>(mr) * e.out_row_mul + e.out_row_add) * e.ldr + nb + tc);
+          }
+        }
         ptx::tmem_ld_wait();
+        if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 8);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -227,64 +283,51 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
         }
-        const int nb = n0 + c0;
-        if (nb >= p.N) continue;  // warp-uniform
-        const bool full = vec_ok && (nb + 32 <= p.N);
+        if (nb >= e.N) continue;  // warp-uniform
 
         if (row_ok) {
-          if (p.bias != nullptr) {
-            if (full) {
+          if (e.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v[j] += t4.x, v[j + 1] += t4.y, v[j + 2] += t4.z, v[j + 3] += t4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
-            }
+            for (int j = 0; j < 32; ++j) v[j] += bias_s[acc_stage][c0 + j];  // smem broadcast; zero beyond N
           }
-          if (p.act != kActNone) {
+          // one warp-uniform branch per activation: a per-element switch compiles to ~3000 predicated-off
+          // instructions per chunk that are still issued when act == none (measured: 0.6 us per chunk)
+          if (LEAN) {
+          } else if (e.act == kActGelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+          } else if (e.act == kActSilu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + expf(-v[j]));
+          } else if (e.act == kActMish) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], kActMish);
           }
-          if (p.residual != nullptr) {
-            if (have_res) {
+          if (e.residual != nullptr && !full) {  // ragged N tail: row-per-thread scalar path
+            const float* r = e.residual + orow * e.ldr + nb;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] += rcur[j].x, v[4 * j + 1] += rcur[j].y, v[4 * j + 2] += rcur[j].z, v[4 * j + 3] += rcur[j].w;
-              }
-            } else {
-              const float* r = p.residual + orow * p.ldr + nb;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) v[j] += r[j];
-            }
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) v[j] += r[j];
           }
-          if (!row_real) {
+          if (!LEAN && !row_real) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0f;
           }
         }
-        if (next_res) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
-        }
 
         // ---- GroupNorm partial statistics over real rows ----
-        if (p.gn_stats != nullptr) {
-          const int gs = p.gn_group_size;
+        if (!LEAN && e.gn_stats != nullptr) {
+          const int gs = e.gn_group_size;
           const bool contrib = row_ok && row_real;
           const int clip0 = __shfl_sync(0xffffffffu, clip, 0);
           const bool uniform = __all_sync(0xffffffffu, clip == clip0);
-          for (int jg = 0; jg < 32 && nb + jg < p.N; jg += (gs < 32 ? gs : 32)) {
+          for (int jg = 0; jg < 32 && nb + jg < e.N; jg += (gs < 32 ? gs : 32)) {
             const int span = gs < 32 ? gs : 32;
             float s1 = 0.0f, s2 = 0.0f;
             if (contrib) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                if (j >= jg && j < jg + span && nb + j < p.N) {
+                if (j >= jg && j < jg + span && nb + j < e.N) {
                   s1 += v[j];
                   s2 += v[j] * v[j];
                 }
@@ -298,59 +341,76 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
                 s2 += __shfl_xor_sync(0xffffffffu, s2, off);
               }
               if (lane == 0) {
-                double* dst = p.gn_stats + (static_cast<int64_t>(clip0) * p.gn_groups + g) * 2;
+                double* dst = e.gn_stats + (static_cast<int64_t>(clip0) * e.gn_groups + g) * 2;
                 atomicAdd(dst, static_cast<double>(s1));
                 atomicAdd(dst + 1, static_cast<double>(s2));
               }
             } else if (contrib) {
-              double* dst = p.gn_stats + (static_cast<int64_t>(clip) * p.gn_groups + g) * 2;
+              double* dst = e.gn_stats + (static_cast<int64_t>(clip) * e.gn_groups + g) * 2;
               atomicAdd(dst, static_cast<double>(s1));
               atomicAdd(dst + 1, static_cast<double>(s2));
             }
           }
         }
 
-        if (row_ok) {
-          if (p.out != nullptr) {
-            float* o = p.out + orow * p.ldo + nb;
-            if (full) {
+        if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 9);
+        if (full) {
+          // ---- coalesced path through the staging tile ----
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+          for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = v[j];  // column ^ row: conflict-free both ways
+          __syncwarp();
+          if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 10);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) o[j] = v[j];
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = rr * 4 + tr;
+            const int mr = m0 + q * 32 + r;
+            float4 w;
+            w.x = tile[r * 32 + (tc ^ r)], w.y = tile[r * 32 + ((tc + 1) ^ r)];
+            w.z = tile[r * 32 + ((tc + 2) ^ r)], w.w = tile[r * 32 + ((tc + 3) ^ r)];
+            if (mr < e.M) {
+              if (use_res) {
+                bool real = true;
+                if (!LEAN && e.clip_rows > 0) real = (mr % e.clip_rows) < e.clip_valid;
+                if (real) w.x += res[rr].x, w.y += res[rr].y, w.z += res[rr].z, w.w += res[rr].w;
+              }
+              const int64_t orr = static_cast<int64_t>(mr) * e.out_row_mul + e.out_row_add;
+              if (e.out != nullptr) *reinterpret_cast<float4*>(e.out + orr * e.ldo + nb + tc) = w;
+              if (e.out_hi != nullptr) {
+                float4 h, l;
+                h.x = ptx::to_tf32(w.x), h.y = ptx::to_tf32(w.y), h.z = ptx::to_tf32(w.z), h.w = ptx::to_tf32(w.w);
+                l.x = w.x - h.x, l.y = w.y - h.y, l.z = w.z - h.z, l.w = w.w - h.w;
+                *reinterpret_cast<float4*>(e.out_hi + orr * e.lds + nb + tc) = h;
+                *reinterpret_cast<float4*>(e.out_lo + orr * e.lds + nb + tc) = l;
+              }
             }
           }
-          if (p.out_hi != nullptr) {
-            float* oh = p.out_hi + orow * p.lds + nb;
-            float* ol = p.out_lo + orow * p.lds + nb;
-            if (full) {
+          __syncwarp();
+          if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 11);
+        } else if (row_ok) {
+          // ---- ragged N tail: scalar row-per-thread stores ----
+          if (e.out != nullptr) {
+            float* o = e.out + orow * e.ldo + nb;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 h, l;
-                h.x = ptx::to_tf32(v[j]), h.y = ptx::to_tf32(v[j + 1]);
-                h.z = ptx::to_tf32(v[j + 2]), h.w = ptx::to_tf32(v[j + 3]);
-                l.x = v[j] - h.x, l.y = v[j + 1] - h.y, l.z = v[j + 2] - h.z, l.w = v[j + 3] - h.w;
-                *reinterpret_cast<float4*>(oh + j) = h;
-                *reinterpret_cast<float4*>(ol + j) = l;
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) o[j] = v[j];
+          }
+          if (e.out_hi != nullptr) {
+            float* oh = e.out_hi + orow * e.lds + nb;
+            float* ol = e.out_lo + orow * e.lds + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) {
+                const float h = ptx::to_tf32(v[j]);
+                oh[j] = h;
+                ol[j] = v[j] - h;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) {
-                  const float h = ptx::to_tf32(v[j]);
-                  oh[j] = h;
-                  ol[j] = v[j] - h;
-                }
-            }
           }
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above): hand it back
       ptx::tc_fence_before_sync();
       __syncwarp();
+      if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 6);
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
     }
   }
@@ -361,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 32) stamp(p, 7);
 }
 
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
@@ -388,12 +449,22 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 template <int BLOCK_N, int PASSES>
+static cudaError_t set_attr() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+}
+
+template <int BLOCK_N, int PASSES>
 cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t stream, bool pdl) {
   using Cfg = TileCfg<BLOCK_N, PASSES>;
-  auto kern = gemm_tile_kernel<BLOCK_N, PASSES>;
+  const bool lean = p.act == kActNone && p.clip_rows == 0 && p.gn_stats == nullptr;
+  auto kern = lean ? gemm_tile_kernel<BLOCK_N, PASSES, true> : gemm_tile_kernel<BLOCK_N, PASSES, false>;
   static bool attr_set = false;
   if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = set_attr<BLOCK_N, PASSES>();
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -453,12 +524,6 @@ cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n
       return cudaErrorInvalidValue;
   }
 #undef ROHM_GEMM_CASE
-}
-
-template <int BLOCK_N, int PASSES>
-static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TileCfg<BLOCK_N, PASSES>::kSmemBytes);
 }
 
 cudaError_t gemm_init_attributes() {

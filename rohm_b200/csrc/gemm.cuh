@@ -61,6 +61,8 @@ struct alignas(64) GemmParams {
   double* gn_stats;  // [num_clips, gn_groups, 2] or nullptr
   int gn_groups;
   int gn_group_size;  // channels per group
+  // optional: CTA 0 records %globaltimer at 8 milestones (developer instrumentation, see tools/gemm_selftest)
+  unsigned long long* debug_ts;
   // filled in by launch_gemm: extent of the tile grid
   int grid_m_rows;
   int grid_n_cols;

@@ -242,12 +242,71 @@ static void case_conv(int B, int T_in, int Tp_in, int Cin, int Cout, int ks, int
   for (size_t i = 0; i < rs.size(); ++i) maxstat = std::fmax(maxstat, std::fabs(rs[i] - stats[i]) / (1.0 + std::fabs(rs[i])));
   char name[160];
   snprintf(name, sizeof name, "conv B%d T%d/%d Cin%d Cout%d k%d s%d bn%d", B, T_in, Tp_in, Cin, Cout, ks, stride, block_n);
-  report(name, maxerr, maxref, 2e-5);
+  report(name, maxerr, maxref, ks * Cin > 2048 ? 1e-4 : 2e-5);
   report("  pad rows written as zero", maxpad, 0, 0.0);
-  report("  GroupNorm sum/sumsq (relative)", maxstat, 1, 1e-5);
+  report("  GroupNorm sum/sumsq (relative)", maxstat, 1, ks * Cin > 2048 ? 2e-4 : 1e-5);
   cudaFree(dx), cudaFree(dW), cudaFree(db), cudaFree(dy), cudaFree(dstats);
   cudaFree(sx.hi), cudaFree(sx.lo), cudaFree(sW.hi), cudaFree(sW.lo);
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-cost microbenchmark: where do the non-MMA microseconds of a launch go?
+// ------------------------------------------------------------------------------------------------
+static void bench_fixed(int M, int N, int K, int outputs /*0 none, 1 fp32, 2 hi/lo, 3 all*/, bool with_res, int passes) {
+  const int Kp = (K + 31) / 32 * 32;
+  std::vector<float> A((size_t)M * Kp, 0.5f), W((size_t)N * Kp, 0.25f), b(N, 0.1f), R((size_t)M * N, 1.0f);
+  float *dA = dev(A), *dW = dev(W), *db = dev(b), *dR = dev(R);
+  Split sA = split(dA, A.size()), sW = split(dW, W.size());
+  float* dC = dev_zero((size_t)M * N);
+  float* dCh = dev_zero((size_t)M * N);
+  float* dCl = dev_zero((size_t)M * N);
+  GemmParams p{};
+  make_tmap_2d(&p.a_hi[0], sA.hi, M, Kp, Kp, kGemmBlockM);
+  make_tmap_2d(&p.a_lo[0], sA.lo, M, Kp, Kp, kGemmBlockM);
+  make_tmap_2d(&p.b_hi, sW.hi, N, Kp, Kp, 128);
+  make_tmap_2d(&p.b_lo, sW.lo, N, Kp, Kp, 128);
+  p.num_segs = 1, p.seg_kblocks[0] = Kp / 32, p.seg_row_mul[0] = 1;
+  p.bias = db;
+  p.residual = with_res ? dR : nullptr, p.ldr = N;
+  if (outputs & 1) p.out = dC, p.ldo = N;
+  if (outputs & 2) p.out_hi = dCh, p.out_lo = dCl, p.lds = N;
+  p.M = M, p.N = N, p.out_row_mul = 1;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 5; ++i) CK(launch_gemm(p, M, N, 128, passes, 0));
+  CK(cudaEventRecord(e0));
+  const int iters = 100;
+  for (int i = 0; i < iters; ++i) CK(launch_gemm(p, M, N, 128, passes, 0));
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("fixed-cost M%d N%d K%-5d outputs=%d res=%d passes=%d : %.2f us/launch\n", M, N, K, outputs, (int)with_res, passes,
+         ms * 1000.0 / iters);
+  {
+    unsigned long long* dts;
+    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
+    p.debug_ts = dts;
+    CK(launch_gemm(p, M, N, 128, passes, 0));
+    CK(launch_gemm(p, M, N, 128, passes, 0));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[16];
+    CK(cudaMemcpy(h, dts, sizeof h, cudaMemcpyDeviceToHost));
+    printf("    CTA0 timeline (ns since kernel start): setup_done %llu | first_tma %llu | first_full %llu | mma_issued %llu | "
+           "epi_start %llu | epi_done %llu | end %llu\n", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0],
+           h[6] - h[0], h[7] - h[0]);
+    printf("      epilogue chunk0 of warp2: tmem_ld done %llu | math done %llu | staged %llu | stored %llu\n", h[8] - h[0],
+           h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+    p.debug_ts = nullptr;
+    cudaFree(dts);
+  }
+  cudaFree(dA), cudaFree(dW), cudaFree(db), cudaFree(dR), cudaFree(dC), cudaFree(dCh), cudaFree(dCl);
+  cudaFree(sA.hi), cudaFree(sA.lo), cudaFree(sW.hi), cudaFree(sW.lo);
+}
+
+__global__ void empty_kernel() {}
 
 int main() {
   int devcount = 0;
@@ -255,6 +314,30 @@ int main() {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s  sm_%d%d  SMs %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+
+  {
+    // launch-only floor: an empty kernel back to back
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 10; ++i) empty_kernel<<<148, 320>>>();
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 200; ++i) empty_kernel<<<148, 320>>>();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("empty kernel back-to-back: %.2f us/launch\n", ms * 1000.0 / 200);
+  }
+  for (int K : {32, 128, 512, 1024, 2048}) bench_fixed(4640, 512, K, 1, false, 3);
+  bench_fixed(4640, 512, 32, 0, false, 3);
+  bench_fixed(4640, 512, 32, 3, true, 3);
+  bench_fixed(4640, 512, 512, 0, false, 3);
+  bench_fixed(4640, 512, 512, 3, true, 3);
+  bench_fixed(128, 128, 32, 1, false, 3);
+  bench_fixed(128, 128, 512, 1, false, 3);
+  bench_fixed(4640, 1536, 512, 1, false, 3);
+  bench_fixed(4640, 1536, 32, 1, false, 3);
 
   // PoseNet shapes at B=32, S=145 (M = 4640)
   case_linear(4640, 512, 512, 128, kActNone, true, true);    // out-proj + residual
