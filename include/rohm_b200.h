@@ -143,7 +143,7 @@ ROHM_API int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const int6
                          void* stream, float* ms_by_category, int* launches_by_category);
 
 /* Options: 0 = replay the forward as a CUDA graph (default 1; the graph is captured on first use per (B, T) and its
- * three caller-memory pointers are patched per call). */
+ * three caller-memory pointers are patched per call); 1 = programmatic dependent launch on the GEMMs (default 1). */
 ROHM_API int rohm_posenet_set_option(rohm_posenet* pn, int option, int value);
 
 /* Kernel launches issued by the last forward (for bench.py's gpu_launches accounting). */

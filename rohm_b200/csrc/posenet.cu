@@ -361,14 +361,27 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(c
       qn[3] = __ldg(qB + 8 * (k + 1) + t + 4);
     }
     const float* kp = Ks + g * kAttnPitch + 8 * k + t;
+    // groups of 4 key tiles: all B fragments of the group are split first, then the three passes are issued pass-major,
+    // so consecutive MMAs hit different accumulators (the per-tile order lo*hi, hi*lo, hi*hi would serialise on one)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      uint32_t bh[2], bl[2];
-      split_tf32(kp[j * 8 * kAttnPitch], bh[0], bl[0]);
-      split_tf32(kp[j * 8 * kAttnPitch + 4], bh[1], bl[1]);
-      mma_tf32_16x8x8(acc[j], al, bh);
-      mma_tf32_16x8x8(acc[j], ah, bl);
-      mma_tf32_16x8x8(acc[j], ah, bh);
+    for (int j0 = 0; j0 < NT; j0 += 4) {
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < NT) {
+          split_tf32(kp[(j0 + u) * 8 * kAttnPitch], bh[u][0], bl[u][0]);
+          split_tf32(kp[(j0 + u) * 8 * kAttnPitch + 4], bh[u][1], bl[u][1]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < NT) mma_tf32_16x8x8(acc[j0 + u], al, bh[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < NT) mma_tf32_16x8x8(acc[j0 + u], ah, bl[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < NT) mma_tf32_16x8x8(acc[j0 + u], ah, bh[u]);
     }
   }
 
@@ -420,36 +433,54 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(c
   const bool okA = (r0 + g) < S, okB = (r0 + g + 8) < S;
   const int64_t oA = (base + r0 + g) * D + h * DH + 2 * t;
   const int64_t oB = oA + static_cast<int64_t>(8) * D;
+  // four 8-wide output tiles per iteration: the hi/lo split of the P fragment is shared by the four tiles and the
+  // eight accumulators (main + cross terms per tile) give the tensor pipe independent work
+  constexpr int NU = 4;
 #pragma unroll 1
-  for (int n = 0; n < DH / 8; ++n) {
-    float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    float os[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // small cross terms accumulate separately (shorter dependency chains)
-    const float* vp = Vs + 2 * t * kAttnPitch + g + 8 * n;
+  for (int n0 = 0; n0 < DH / 8; n0 += NU) {
+    float o[NU][4], os[NU][4];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.0f;
+      os[u][0] = os[u][1] = os[u][2] = os[u][3] = 0.0f;
+    }
+    const float* vp = Vs + 2 * t * kAttnPitch + g + 8 * n0;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      uint32_t ah[4], al[4], bh[2], bl[2];
+      uint32_t ah[4], al[4];
       split_tf32_pinned(acc[j][0], ah[0], al[0]);
       split_tf32_pinned(acc[j][2], ah[1], al[1]);
       split_tf32_pinned(acc[j][1], ah[2], al[2]);
       split_tf32_pinned(acc[j][3], ah[3], al[3]);
-      split_tf32(vp[8 * j * kAttnPitch], bh[0], bl[0]);
-      split_tf32(vp[(8 * j + 1) * kAttnPitch], bh[1], bl[1]);
-      mma_tf32_16x8x8(os, al, bh);
-      mma_tf32_16x8x8(os, ah, bl);
-      mma_tf32_16x8x8(o, ah, bh);
-    }
+      uint32_t bh[NU][2], bl[NU][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] += os[i];
-    // store ctx as TF32 hi/lo (o[0..1] = row rowA, cols 8n+2t,+1; o[2..3] = row rowB)
-    if (okA) {
-      const float h0 = ptx::to_tf32(o[0]), h1 = ptx::to_tf32(o[1]);
-      *reinterpret_cast<float2*>(ctx_hi + oA + 8 * n) = make_float2(h0, h1);
-      *reinterpret_cast<float2*>(ctx_lo + oA + 8 * n) = make_float2(o[0] - h0, o[1] - h1);
+      for (int u = 0; u < NU; ++u) {
+        split_tf32(vp[8 * j * kAttnPitch + 8 * u], bh[u][0], bl[u][0]);
+        split_tf32(vp[(8 * j + 1) * kAttnPitch + 8 * u], bh[u][1], bl[u][1]);
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32_16x8x8(os[u], al, bh[u]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32_16x8x8(o[u], ah, bh[u]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32_16x8x8(os[u], ah, bl[u]);
     }
-    if (okB) {
-      const float h2 = ptx::to_tf32(o[2]), h3 = ptx::to_tf32(o[3]);
-      *reinterpret_cast<float2*>(ctx_hi + oB + 8 * n) = make_float2(h2, h3);
-      *reinterpret_cast<float2*>(ctx_lo + oB + 8 * n) = make_float2(o[2] - h2, o[3] - h3);
+    // store ctx as TF32 hi/lo (o[.][0..1] = row rowA, cols 8n+2t,+1; o[.][2..3] = row rowB)
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int n = n0 + u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[u][i] += os[u][i];
+      if (okA) {
+        const float h0 = ptx::to_tf32(o[u][0]), h1 = ptx::to_tf32(o[u][1]);
+        *reinterpret_cast<float2*>(ctx_hi + oA + 8 * n) = make_float2(h0, h1);
+        *reinterpret_cast<float2*>(ctx_lo + oA + 8 * n) = make_float2(o[u][0] - h0, o[u][1] - h1);
+      }
+      if (okB) {
+        const float h2 = ptx::to_tf32(o[u][2]), h3 = ptx::to_tf32(o[u][3]);
+        *reinterpret_cast<float2*>(ctx_hi + oB + 8 * n) = make_float2(h2, h3);
+        *reinterpret_cast<float2*>(ctx_lo + oB + 8 * n) = make_float2(o[u][2] - h2, o[u][3] - h3);
+      }
     }
   }
 }
@@ -505,6 +536,7 @@ struct rohm_posenet {
   };
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
+  bool use_pdl = true;
   cudaStream_t capture_stream = nullptr;
   ~rohm_posenet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -610,7 +642,9 @@ static int setup_linear(rohm_posenet* pn, GemmParams* g, const float* a_hi, cons
 static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int rows, cudaStream_t st) {
   g.M = rows;
   prof_begin(pn, kCatGemm, st);
-  ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st));
+  // programmatic dependent launch: this GEMM's prologue (barrier init, TMEM alloc, tensor-map prefetch) overlaps the
+  // tail of the previous kernel; its griddepcontrol.wait orders all global reads/writes after that kernel
+  ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st, pn->use_pdl && !pn->profiling));
   prof_end(pn, st);
   pn->launches++;
   return ROHM_OK;
@@ -1084,6 +1118,15 @@ extern "C" int rohm_posenet_set_option(rohm_posenet* pn, int option, int value) 
   if (pn == nullptr) return ROHM_ERR_INVALID;
   if (option == 0) {
     pn->use_graph = value != 0;
+    return ROHM_OK;
+  }
+  if (option == 1) {  // programmatic dependent launch on the GEMMs (graphs are re-captured)
+    pn->use_pdl = value != 0;
+    for (auto& g : pn->graphs) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    pn->graphs.clear();
     return ROHM_OK;
   }
   return fail(pn->ctx, ROHM_ERR_INVALID, "rohm_posenet_set_option: unknown option %d", option);

@@ -72,6 +72,10 @@ class PoseNetEngine:
         _lib.check(rc, self.ctx)
         self.handle = handle
         self._keep = None  # the library owns its copies now
+        if os.environ.get("ROHM_B200_PDL", "1") == "0":
+            self.lib.rohm_posenet_set_option(handle, 1, 0)
+        if os.environ.get("ROHM_B200_GRAPH", "1") == "0":
+            self.lib.rohm_posenet_set_option(handle, 0, 0)
         self.cond_key = None
 
     def __del__(self):
