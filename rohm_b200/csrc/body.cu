@@ -200,22 +200,31 @@ __global__ void compress_weights_kernel(const float* __restrict__ W, int V, int*
 // go [N,3], bp [N,63] axis-angle, betas [N,10], transl [N,3].  Outputs (each optional):
 //   joints [N, nj, 3] (posed joints + transl, nj <= 55), A [N, 55, 12] (rows of the 3x4 skinning transform),
 //   feat hi/lo [N, kBlendK] (pose_feature | betas | 1 | 0...) for the blend GEMM.
-__global__ void __launch_bounds__(128) fk_full_kernel(const float* __restrict__ go, const float* __restrict__ bp,
-                                                      const float* __restrict__ betas, const float* __restrict__ transl,
-                                                      const float* __restrict__ Jt, const float* __restrict__ Jd,
-                                                      int N, float* __restrict__ joints, int nj, float* __restrict__ A,
-                                                      float* __restrict__ feat_hi, float* __restrict__ feat_lo) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// One WARP per frame: lane j (and j + 32) owns joint j; rest joints and local rotations are computed in parallel, the
+// kinematic tree is then walked level by level (a joint is composed once its parent's world transform is in shared
+// memory; SMPL-X depth is 12).  The thread-per-frame version kept 55 world transforms in local memory and ran at 36 CTAs.
+constexpr int kFkWarps = 8;
+__global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __restrict__ go, const float* __restrict__ bp,
+                                                                const float* __restrict__ betas,
+                                                                const float* __restrict__ transl,
+                                                                const float* __restrict__ Jt, const float* __restrict__ Jd,
+                                                                int N, float* __restrict__ joints, int nj,
+                                                                float* __restrict__ A, float* __restrict__ feat_hi,
+                                                                float* __restrict__ feat_lo) {
+  __shared__ float sW[kFkWarps][kJ][12];   // world transforms [R | t] row-major 3x4
+  __shared__ float sJ[kFkWarps][kJ][3];    // rest joints
+  __shared__ int sDone[kFkWarps][kJ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kFkWarps + warp;
+  if (n >= N) return;  // whole warp
   float be[kBetas];
 #pragma unroll
   for (int l = 0; l < kBetas; ++l) be[l] = betas[static_cast<int64_t>(n) * kBetas + l];
   const V3 tr = {transl[n * 3], transl[n * 3 + 1], transl[n * 3 + 2]};
-  // world transforms of the joints processed so far (55 x (R, t)) live in local memory; parents precede children
-  M3 Wr[kJ];
-  V3 Wt[kJ];
-  V3 Jrest[kJ];
-  for (int j = 0; j < kJ; ++j) {
+  M3 Rl[2];
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    if (j >= kJ) break;
     V3 J = {Jt[j * 3], Jt[j * 3 + 1], Jt[j * 3 + 2]};
 #pragma unroll
     for (int l = 0; l < kBetas; ++l) {
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(128) fk_full_kernel(const float* __restrict__ 
       J.y = fmaf(Jd[j * 30 + 10 + l], be[l], J.y);
       J.z = fmaf(Jd[j * 30 + 20 + l], be[l], J.z);
     }
-    Jrest[j] = J;
+    sJ[warp][j][0] = J.x, sJ[warp][j][1] = J.y, sJ[warp][j][2] = J.z;
     M3 R = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
     if (j < kBodyJ) {
       const float* r = (j == 0) ? go + static_cast<int64_t>(n) * 3 : bp + static_cast<int64_t>(n) * 63 + (j - 1) * 3;
@@ -232,72 +241,125 @@ __global__ void __launch_bounds__(128) fk_full_kernel(const float* __restrict__ 
         const float pf[9] = {R.c0.x - 1.f, R.c1.x, R.c2.x, R.c0.y, R.c1.y - 1.f, R.c2.y, R.c0.z, R.c1.z, R.c2.z - 1.f};
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
-          const float h = ptx::to_tf32(pf[e]);
-          feat_hi[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = h;
-          feat_lo[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = pf[e] - h;
+          const float hh = ptx::to_tf32(pf[e]);
+          feat_hi[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = hh;
+          feat_lo[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = pf[e] - hh;
         }
       }
     }
-    const int p = c_parents[j];
-    if (p < 0) {
-      Wr[j] = R, Wt[j] = J;
-    } else {
-      Wr[j] = mul(Wr[p], R);
-      Wt[j] = Wt[p] + mul(Wr[p], J - Jrest[p]);
-    }
-    if (joints != nullptr && j < nj) {
-      float* o = joints + (static_cast<int64_t>(n) * nj + j) * 3;
-      o[0] = Wt[j].x + tr.x, o[1] = Wt[j].y + tr.y, o[2] = Wt[j].z + tr.z;
-    }
-    if (A != nullptr) {  // A_j = [W_r | W_t - W_r J_rest], translation folded in
-      const V3 t = Wt[j] - mul(Wr[j], J) + tr;
-      float* o = A + (static_cast<int64_t>(n) * kJ + j) * 12;
-      o[0] = Wr[j].c0.x, o[1] = Wr[j].c1.x, o[2] = Wr[j].c2.x, o[3] = t.x;
-      o[4] = Wr[j].c0.y, o[5] = Wr[j].c1.y, o[6] = Wr[j].c2.y, o[7] = t.y;
-      o[8] = Wr[j].c0.z, o[9] = Wr[j].c1.z, o[10] = Wr[j].c2.z, o[11] = t.z;
+    Rl[h] = R;
+    sDone[warp][j] = 0;
+  }
+  if (feat_hi != nullptr && lane < kBlendK - kPoseFeat) {
+    const int c = kPoseFeat + lane;  // betas | 1 | zero padding
+    const float v = lane < kBetas ? be[lane] : (lane == kBetas ? 1.0f : 0.0f);
+    const float hh = ptx::to_tf32(v);
+    feat_hi[static_cast<int64_t>(n) * kBlendK + c] = hh;
+    feat_lo[static_cast<int64_t>(n) * kBlendK + c] = v - hh;
+    if (lane + 32 < kBlendK - kPoseFeat) {
+      feat_hi[static_cast<int64_t>(n) * kBlendK + c + 32] = 0.0f;
+      feat_lo[static_cast<int64_t>(n) * kBlendK + c + 32] = 0.0f;
     }
   }
-  if (feat_hi != nullptr) {
-    float* fh = feat_hi + static_cast<int64_t>(n) * kBlendK;
-    float* fl = feat_lo + static_cast<int64_t>(n) * kBlendK;
-#pragma unroll
-    for (int l = 0; l < kBetas; ++l) {
-      const float h = ptx::to_tf32(be[l]);
-      fh[kPoseFeat + l] = h, fl[kPoseFeat + l] = be[l] - h;
+  __syncwarp();
+  // level-synchronous walk of the kinematic tree (parents precede children in index order)
+  bool mine_done[2] = {false, false};
+  for (int level = 0; level < kJ; ++level) {
+    bool progressed = false;
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      if (j >= kJ || mine_done[h]) continue;
+      const int p = c_parents[j];
+      if (p >= 0 && sDone[warp][p] == 0) continue;
+      const V3 J = {sJ[warp][j][0], sJ[warp][j][1], sJ[warp][j][2]};
+      M3 Wr;
+      V3 Wt;
+      if (p < 0) {
+        Wr = Rl[h], Wt = J;
+      } else {
+        const float* w = sW[warp][p];
+        const M3 Pr = {{w[0], w[4], w[8]}, {w[1], w[5], w[9]}, {w[2], w[6], w[10]}};
+        const V3 Pt = {w[3], w[7], w[11]};
+        const V3 Jp = {sJ[warp][p][0], sJ[warp][p][1], sJ[warp][p][2]};
+        Wr = mul(Pr, Rl[h]);
+        Wt = Pt + mul(Pr, J - Jp);
+      }
+      float* w = sW[warp][j];
+      w[0] = Wr.c0.x, w[1] = Wr.c1.x, w[2] = Wr.c2.x, w[3] = Wt.x;
+      w[4] = Wr.c0.y, w[5] = Wr.c1.y, w[6] = Wr.c2.y, w[7] = Wt.y;
+      w[8] = Wr.c0.z, w[9] = Wr.c1.z, w[10] = Wr.c2.z, w[11] = Wt.z;
+      mine_done[h] = true;
+      progressed = true;
+      if (joints != nullptr && j < nj) {
+        float* o = joints + (static_cast<int64_t>(n) * nj + j) * 3;
+        o[0] = Wt.x + tr.x, o[1] = Wt.y + tr.y, o[2] = Wt.z + tr.z;
+      }
+      if (A != nullptr) {  // A_j = [W_r | W_t - W_r J_rest + transl]
+        const V3 t = Wt - mul(Wr, J) + tr;
+        float* o = A + (static_cast<int64_t>(n) * kJ + j) * 12;
+        o[0] = Wr.c0.x, o[1] = Wr.c1.x, o[2] = Wr.c2.x, o[3] = t.x;
+        o[4] = Wr.c0.y, o[5] = Wr.c1.y, o[6] = Wr.c2.y, o[7] = t.y;
+        o[8] = Wr.c0.z, o[9] = Wr.c1.z, o[10] = Wr.c2.z, o[11] = t.z;
+      }
     }
-    fh[kPoseFeat + kBetas] = 1.0f, fl[kPoseFeat + kBetas] = 0.0f;
-    for (int c = kPoseFeat + kBetas + 1; c < kBlendK; ++c) fh[c] = 0.0f, fl[c] = 0.0f;
+    __syncwarp();
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      if (j < kJ && mine_done[h]) sDone[warp][j] = 1;
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, progressed)) break;
   }
 }
 
 // verts[n][v] = sum_k w_k A[n][j_k] [v_posed[n][v]; 1]   (translation already folded into A)
+// One CTA = 256 vertices x kSkinFrames frames: the 8 (bone, weight) pairs of a vertex are read once and kept in
+// registers for all frames (re-reading them per frame was 5x the algorithmic traffic), the frames' 55 x 12 transform
+// tables are staged in shared memory.  HBM-bound: 12 B in + 12 B out per vertex and frame.
+constexpr int kSkinFrames = 16;
 __global__ void __launch_bounds__(256) skin_kernel(const float* __restrict__ vposed, int64_t vp_pitch,
                                                    const float* __restrict__ A, const int* __restrict__ idx,
-                                                   const float* __restrict__ wt, int V, float* __restrict__ verts) {
-  __shared__ float sA[kJ * 12];
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < kJ * 12; i += blockDim.x) sA[i] = A[static_cast<int64_t>(n) * kJ * 12 + i];
-  __syncthreads();
+                                                   const float* __restrict__ wt, int V, int64_t N,
+                                                   float* __restrict__ verts) {
+  __shared__ __align__(16) float sA[kSkinFrames][kJ * 12];
+  const int64_t n0 = static_cast<int64_t>(blockIdx.y) * kSkinFrames;
+  const int nf = static_cast<int>(min(static_cast<int64_t>(kSkinFrames), N - n0));
+  for (int i = threadIdx.x; i < nf * kJ * 12; i += blockDim.x) sA[i / (kJ * 12)][i % (kJ * 12)] = A[n0 * kJ * 12 + i];
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  const float* p = vposed + static_cast<int64_t>(n) * vp_pitch + static_cast<int64_t>(v) * 3;
-  const float x = p[0], y = p[1], z = p[2];
-  float T[12];
-#pragma unroll
-  for (int e = 0; e < 12; ++e) T[e] = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kMaxBones; ++k) {
-    const float w = wt[v * kMaxBones + k];
-    if (w != 0.0f) {
-      const float* a = sA + idx[v * kMaxBones + k] * 12;
-#pragma unroll
-      for (int e = 0; e < 12; ++e) T[e] = fmaf(w, a[e], T[e]);
-    }
+  int bi[kMaxBones];
+  float bw[kMaxBones];
+  if (v < V) {
+    const int4 i0 = *reinterpret_cast<const int4*>(idx + v * kMaxBones);
+    const int4 i1 = *reinterpret_cast<const int4*>(idx + v * kMaxBones + 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(wt + v * kMaxBones);
+    const float4 w1 = *reinterpret_cast<const float4*>(wt + v * kMaxBones + 4);
+    bi[0] = i0.x, bi[1] = i0.y, bi[2] = i0.z, bi[3] = i0.w, bi[4] = i1.x, bi[5] = i1.y, bi[6] = i1.z, bi[7] = i1.w;
+    bw[0] = w0.x, bw[1] = w0.y, bw[2] = w0.z, bw[3] = w0.w, bw[4] = w1.x, bw[5] = w1.y, bw[6] = w1.z, bw[7] = w1.w;
   }
-  float* o = verts + (static_cast<int64_t>(n) * V + v) * 3;
-  o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
-  o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
-  o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+  __syncthreads();
+  if (v >= V) return;
+  for (int f = 0; f < nf; ++f) {
+    const float* p = vposed + (n0 + f) * vp_pitch + static_cast<int64_t>(v) * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    float T[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxBones; ++k) {
+      if (bw[k] != 0.0f) {
+        const float4* a = reinterpret_cast<const float4*>(sA[f] + bi[k] * 12);  // 3 x 128-bit smem loads per bone
+        const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+        const float w = bw[k];
+        T[0] = fmaf(w, r0.x, T[0]), T[1] = fmaf(w, r0.y, T[1]), T[2] = fmaf(w, r0.z, T[2]), T[3] = fmaf(w, r0.w, T[3]);
+        T[4] = fmaf(w, r1.x, T[4]), T[5] = fmaf(w, r1.y, T[5]), T[6] = fmaf(w, r1.z, T[6]), T[7] = fmaf(w, r1.w, T[7]);
+        T[8] = fmaf(w, r2.x, T[8]), T[9] = fmaf(w, r2.y, T[9]), T[10] = fmaf(w, r2.z, T[10]), T[11] = fmaf(w, r2.w, T[11]);
+      }
+    }
+    float* o = verts + ((n0 + f) * V + v) * 3;
+    o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+    o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+    o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+  }
 }
 
 // dense fallback when a vertex has more than kMaxBones non-zero weights
@@ -756,7 +818,7 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
     return fail(ctx, ROHM_ERR_STATE, "rohm_body_forward: handle was created without vertex support");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool verts = vertices != nullptr;
-  fk_full_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(
+  fk_full_kernel<<<static_cast<unsigned>((N + kFkWarps - 1) / kFkWarps), 32 * kFkWarps, 0, st>>>(
       global_orient, body_pose, betas, transl, bd->Jt, bd->Jd, static_cast<int>(N), joints, num_joints,
       verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr);
   ROHM_CUDA(ctx, cudaGetLastError());
@@ -766,7 +828,8 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
     ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 128, bd->passes, st));
     dim3 grid((bd->V + 255) / 256, static_cast<unsigned>(N));
     if (bd->sparse_ok)
-      skin_kernel<<<grid, 256, 0, st>>>(bd->vposed, bd->blend.Np, bd->A, bd->bone_idx, bd->bone_w, bd->V, vertices);
+      skin_kernel<<<dim3((bd->V + 255) / 256, static_cast<unsigned>((N + kSkinFrames - 1) / kSkinFrames)), 256, 0, st>>>(
+          bd->vposed, bd->blend.Np, bd->A, bd->bone_idx, bd->bone_w, bd->V, N, vertices);
     else
       skin_dense_kernel<<<grid, 256, 0, st>>>(bd->vposed, bd->blend.Np, bd->A, bd->lbs_w_copy, bd->V, vertices);
     ROHM_CUDA(ctx, cudaGetLastError());

@@ -12,7 +12,7 @@ namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kSmemBudget = 192 * 1024;  // operand ring budget (3 stages of 64 KB at BLOCK_N = 128, PASSES = 3)
+constexpr int kSmemBudget = 192 * 1024;  // operand ring budget (BLOCK_N = 128, PASSES = 3: 6 x 32 KB or 3 x 64 KB)
 constexpr int kEpiTileFloats = 32 * 32;   // per-epilogue-warp staging tile (32 x 32, XOR-swizzled columns): coalesced stores
 
 template <int BLOCK_N, int PASSES>
@@ -22,7 +22,7 @@ struct TileCfg {
   static constexpr int kSplit = (PASSES == 3) ? 2 : 1;
   static constexpr int kStageBytes = kSplit * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kEpiWarps * kEpiTileFloats * 4;
   // PASSES == 3 keeps two accumulators per stage: columns [0, BLOCK_N) take the leading hi*hi products, columns
   // [BLOCK_N, 2*BLOCK_N) the two small cross terms.  The tensor core truncates when it adds into the
@@ -72,11 +72,12 @@ struct EpiParams {
 
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
 // (N-tile index fastest, so CTAs running concurrently share the same A rows in L2).
-// LEAN epilogue: bias + residual + fp32 / hi-lo stores only (the PoseNet linears); the full epilogue adds activations,
-// padded-clip row masks and GroupNorm partial sums.  Two instantiations keep the hot variant's code small (the full
+// Epilogue variants: 0 = bias + residual + fp32 / hi-lo stores (the PoseNet linears), 1 = the same + exact GELU (FFN1),
+// 2 = everything (other activations, padded-clip row masks, GroupNorm partial sums: TrajNet).  Separate instantiations keep the hot variants' code small (the full
 // epilogue is ~7000 SASS instructions, most of them predicated-off activation code when unused).
-template <int BLOCK_N, int PASSES, bool LEAN>
+template <int BLOCK_N, int PASSES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool LEAN = EPI != 2;  // EPI: 0 = bias/residual/stores, 1 = the same + exact GELU, 2 = everything
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[Cfg::kStages];
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int it = 0;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * kGemmBlockM;
         const int n0 = (tile % tiles_n) * BLOCK_N;
@@ -151,8 +153,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
           const int nkb = p.seg_kblocks[s];
           for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kGemmBlockK) {
-            const int stage = it % Cfg::kStages;
-            const uint32_t phase = (it / Cfg::kStages) & 1;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (it == 0) stamp(p, 2);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
               ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kGemmBlockK, row);
               ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], kcol, n0);
             }
+            if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
           }
         }
       }
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc(/*TF32*/ 2, kGemmBlockM, BLOCK_N);
-      int it = 0, tcount = 0;
+      int it = 0, tcount = 0, stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         const int acc_stage = tcount % Cfg::kAccStages;
         const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
@@ -179,19 +181,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         ptx::tc_fence_after_sync();
         const uint32_t acc = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols);
         for (int ki = 0; ki < total_iters; ++ki, ++it) {
-          const int stage = it % Cfg::kStages;
-          const uint32_t phase = (it / Cfg::kStages) & 1;
           ptx::mbar_wait(&full_bar[stage], phase);
           if (it == 0) stamp(p, 3);
           ptx::tc_fence_after_sync();
           const uint32_t st = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t a_hi = ptx::make_desc_sw128_kmajor(st);
-          const uint64_t b_hi = ptx::make_desc_sw128_kmajor(st + Cfg::kSplit * Cfg::kABytes);
-          const uint64_t a_lo = ptx::make_desc_sw128_kmajor(st + Cfg::kABytes);
-          const uint64_t b_lo = ptx::make_desc_sw128_kmajor(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+          const uint64_t a_hi = ptx::make_desc_kmajor<kGemmBlockK * 4>(st);
+          const uint64_t b_hi = ptx::make_desc_kmajor<kGemmBlockK * 4>(st + Cfg::kSplit * Cfg::kABytes);
+          const uint64_t a_lo = ptx::make_desc_kmajor<kGemmBlockK * 4>(st + Cfg::kABytes);
+          const uint64_t b_lo = ptx::make_desc_kmajor<kGemmBlockK * 4>(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kGemmBlockK / 8; ++k) {
-            // advancing K by 8 fp32 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
+            // advancing K by 8 fp32 = 32 bytes inside the swizzle span: +2 in the (>>4) address field
             const uint64_t koff = static_cast<uint64_t>(k * 2);
             const uint32_t first = (ki > 0 || k > 0) ? 1u : 0u;
             if (PASSES == 3) {
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             }
           }
           ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
         }
         ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
         if (tcount == 0) stamp(p, 4);
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           }
           // one warp-uniform branch per activation: a per-element switch compiles to ~3000 predicated-off
           // instructions per chunk that are still issued when act == none (measured: 0.6 us per chunk)
-          if (LEAN) {
-          } else if (e.act == kActGelu) {
+          if (EPI == 0) {
+          } else if (EPI == 1 || e.act == kActGelu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
           } else if (e.act == kActSilu) {
@@ -450,18 +451,23 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 template <int BLOCK_N, int PASSES>
 static cudaError_t set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        TileCfg<BLOCK_N, PASSES>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               TileCfg<BLOCK_N, PASSES>::kSmemBytes);
 }
 
 template <int BLOCK_N, int PASSES>
 cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t stream, bool pdl) {
   using Cfg = TileCfg<BLOCK_N, PASSES>;
-  const bool lean = p.act == kActNone && p.clip_rows == 0 && p.gn_stats == nullptr;
-  auto kern = lean ? gemm_tile_kernel<BLOCK_N, PASSES, true> : gemm_tile_kernel<BLOCK_N, PASSES, false>;
+  const bool plain = p.clip_rows == 0 && p.gn_stats == nullptr;
+  auto kern = (plain && p.act == kActNone)   ? gemm_tile_kernel<BLOCK_N, PASSES, 0>
+              : (plain && p.act == kActGelu) ? gemm_tile_kernel<BLOCK_N, PASSES, 1>
+                                             : gemm_tile_kernel<BLOCK_N, PASSES, 2>;
   static bool attr_set = false;
   if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
     cudaError_t e = set_attr<BLOCK_N, PASSES>();
@@ -504,7 +510,8 @@ int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), static_cast<cuuint32_t>(box_rows * row_elem_stride)};
   cuuint32_t estride[2] = {1u, static_cast<cuuint32_t>(row_elem_stride)};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kGemmBlockK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return static_cast<int>(r);
 }

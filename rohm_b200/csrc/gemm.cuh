@@ -25,7 +25,16 @@
 namespace rohm {
 
 constexpr int kGemmBlockM = 128;
-constexpr int kGemmBlockK = 32;  // fp32 elements: 128 bytes = one SWIZZLE_128B span
+// K extent of one pipeline stage in fp32 elements: 32 = 128-byte rows (SWIZZLE_128B), 64 KB stages, 3 in flight;
+// 16 = 64-byte rows (SWIZZLE_64B), 32 KB stages, 6 in flight.  Both are implemented and pass the self-test; measured on
+// B200 (N=512, 148 tiles): 0.51 us per 32 K-columns with BLOCK_K = 32 against 0.73 us with BLOCK_K = 16 (MMA-bound would
+// be 0.39 us) -- the per-stage handshake (full-barrier wait, descriptor setup, commit) costs ~250-350 cycles of tensor-
+// pipe bubble, so fewer, larger stages win even though fewer bytes are in flight.
+#ifndef ROHM_GEMM_BLOCK_K
+#define ROHM_GEMM_BLOCK_K 32
+#endif
+constexpr int kGemmBlockK = ROHM_GEMM_BLOCK_K;
+static_assert(kGemmBlockK == 16 || kGemmBlockK == 32, "one 64- or 128-byte swizzle span");
 constexpr int kMaxSegs = 10;
 
 enum GemmAct : int { kActNone = 0, kActGelu = 1, kActSilu = 2, kActMish = 3 };
@@ -70,7 +79,7 @@ struct alignas(64) GemmParams {
 
 // Host side ------------------------------------------------------------------------------------
 // Fills a 2-D fp32 tensor map: inner dim `cols` (contiguous), outer dim `rows`, row pitch `ld` elements,
-// box = {32, box_rows}, SWIZZLE_128B, zero OOB fill, optional row traversal stride.
+// box = {kGemmBlockK, box_rows}, SWIZZLE_64B/128B to match, zero OOB fill, optional row traversal stride.
 // Returns 0 on success, a CUresult otherwise.
 int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int row_elem_stride = 1);

@@ -156,17 +156,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------------------------
 // Descriptors
 // ----------------------------------------------------------------------------------------------
-// Shared-memory matrix descriptor for a K-major tile whose rows are exactly one 128-byte swizzle span
-// (SWIZZLE_128B): 8-row core groups are 1024 B apart.  Field layout follows the sm_100 descriptor:
-// start_address[0,14) (>>4), LBO[16,30) (ignored for swizzled K-major, set to 1), SBO[32,46) (>>4),
-// version[46,48)=1, layout_type[61,64)=2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc_sw128_kmajor(uint32_t smem_addr) {
+// Shared-memory matrix descriptor for a K-major tile whose rows are exactly one swizzle span of kRowBytes (128 ->
+// SWIZZLE_128B, 64 -> SWIZZLE_64B): 8-row core groups are 8 * kRowBytes apart.  Field layout of the sm_100 descriptor:
+// start_address[0,14) (>>4), LBO[16,30) (ignored for swizzled K-major, set to 1), SBO[32,46) (>>4), version[46,48)=1,
+// layout_type[61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) {
+  static_assert(kRowBytes == 128 || kRowBytes == 64, "row = one swizzle span");
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>((8 * kRowBytes) >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(kRowBytes == 128 ? 2 : 4) << 61;
   return d;
 }
 // Instruction descriptor (32-bit): c_format[4,6), a_format[7,10), b_format[10,13), a_major[15], b_major[16],

@@ -94,7 +94,7 @@ static void case_linear(int M, int N, int K, int block_n, int act, bool with_res
       exit(2);
     }
     p.num_segs = 1;
-    p.seg_kblocks[0] = Kp / 32;
+    p.seg_kblocks[0] = Kp / kGemmBlockK;
     p.seg_row_shift[0] = 0;
     p.seg_row_mul[0] = 1;
     p.bias = db;
@@ -194,7 +194,7 @@ static void case_conv(int B, int T_in, int Tp_in, int Cin, int Cout, int ks, int
       printf("tensor map encode failed (conv A)\n");
       exit(2);
     }
-    p.seg_kblocks[j] = Cin_p / 32;
+    p.seg_kblocks[j] = Cin_p / kGemmBlockK;
     p.seg_row_shift[j] = j - pad;
     p.seg_row_mul[j] = stride;
   }
@@ -266,7 +266,7 @@ static void bench_fixed(int M, int N, int K, int outputs /*0 none, 1 fp32, 2 hi/
   make_tmap_2d(&p.a_lo[0], sA.lo, M, Kp, Kp, kGemmBlockM);
   make_tmap_2d(&p.b_hi, sW.hi, N, Kp, Kp, 128);
   make_tmap_2d(&p.b_lo, sW.lo, N, Kp, Kp, 128);
-  p.num_segs = 1, p.seg_kblocks[0] = Kp / 32, p.seg_row_mul[0] = 1;
+  p.num_segs = 1, p.seg_kblocks[0] = Kp / kGemmBlockK, p.seg_row_mul[0] = 1;
   p.bias = db;
   p.residual = with_res ? dR : nullptr, p.ldr = N;
   if (outputs & 1) p.out = dC, p.ldo = N;
