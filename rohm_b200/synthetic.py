@@ -146,5 +146,10 @@ def smplx_like_model(seed=0, num_verts=10475, dtype=torch.float32):
         Jreg[j, pick] = w / w.sum()
     shapedirs = 0.01 * torch.randn(V, 3, 20, generator=g)
     posedirs = 0.002 * torch.randn((J - 1) * 9, V * 3, generator=g)
+    # real meshes index neighbouring vertices (same dominant bone) next to each other; reproduce that locality by
+    # ordering the vertices by their primary bone (a pure relabelling applied consistently to every per-vertex array)
+    perm = torch.sort(owner, stable=True).indices
+    v_template, lbs, Jreg, shapedirs = v_template[perm], lbs[perm], Jreg[:, perm], shapedirs[perm]
+    posedirs = posedirs.view(-1, V, 3)[:, perm].reshape(-1, V * 3)
     return {"v_template": v_template.to(dtype), "shapedirs": shapedirs.to(dtype), "posedirs": posedirs.to(dtype),
             "J_regressor": Jreg.to(dtype), "lbs_weights": lbs.to(dtype), "parents": list(SMPLX_PARENTS)}

@@ -180,7 +180,7 @@ def test_sampling_posenet_guided():
     for k, i in enumerate(range(first, -1, -1)):
         x = ref_xt[k]
         x0 = posenet_oracle.posenet_forward(sd, x, cond, torch.full((B,), tmap[i], dtype=torch.long))
-        assert float((x0 - ref_x0[k]).abs().max()) < 2e-5
+        assert float((x0 - ref_x0[k]).abs().max()) < 2e-5 * max(1.0, float(ref_xt[k].abs().max()))  # |x_t| reaches ~1e2 here
         noise = tape.randn_like(x)
         gr = ko.guide_skating(ref_x0[k], mean, std, body)
         n_guided += int(gr.dim() > 0)
