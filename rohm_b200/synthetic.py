@@ -129,9 +129,16 @@ def smplx_like_model(seed=0, num_verts=10475, dtype=torch.float32):
     owner = torch.randint(0, J, (V,), generator=g)
     owner[:J] = torch.arange(J)
     v_template = rest[owner] + 0.05 * torch.randn(V, 3, generator=g)
+    # skinning weights are spatially local in SMPL-X: a vertex is driven by its primary bone and that bone's
+    # neighbours in the kinematic tree (parent, grand-parent, a child) -- not by arbitrary bones
+    parent = torch.tensor([max(p, 0) for p in SMPLX_PARENTS])
+    first_child = torch.arange(J)
+    for j in range(J - 1, 0, -1):
+        first_child[SMPLX_PARENTS[j]] = j
+    neighbours = [None, parent, parent[parent], first_child]
     lbs = torch.zeros(V, J)
     for k in range(4):
-        idx = owner if k == 0 else torch.randint(0, J, (V,), generator=g)
+        idx = owner if k == 0 else neighbours[k][owner]
         w = torch.rand(V, generator=g) * (1.0 if k == 0 else 0.3)
         lbs[torch.arange(V), idx] += w
     lbs = lbs / lbs.sum(dim=1, keepdim=True)
