@@ -166,7 +166,7 @@ def workload_config(n_gpus, device_kind):
                         "tokens, 294 channels), 1000 DDPM steps, p_sample (no guidance)",
             "clips_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "frames": T_FRAMES,
             "diffusion_steps": DIFFUSION_STEPS, "parallelism": f"clip-sharded x{n_gpus} (no intra-step collective)",
-            "precision_mode": os.environ.get("ROHM_B200_PRECISION", "tf32x3"),
+            "precision_mode": os.environ.get("ROHM_B200_PRECISION", "f16x2"),
             "l2": "flushed (256 MiB write) between timed iterations", "device": device_kind}
 
 
@@ -287,14 +287,26 @@ def main():
     flops = gemm_flops_per_forward(B, T + 1)
     gemm_s = cat_ms["gemm"] / 1000.0
     achieved = flops / gemm_s / 1e12 if gemm_s > 0 else None
-    passes = engine.precision
+    prec = engine.precision  # 3 = TF32 hi/lo x 3 products, 2 = fp16 hi/lo x 3 products, 1 = single-pass TF32
+    passes = 1 if prec == 1 else 3
+    kernel_kind = {3: "tcgen05 kind::tf32 on TF32 hi/lo pairs, 3 products", 2: "tcgen05 kind::f16 on fp16 hi/lo pairs, 3 products",
+                   1: "tcgen05 kind::tf32, single pass"}[prec]
+    # tensor-pipe work per algorithmic flop: 3 products; fp16 products run at the bf16 rate, TF32 ones at half of it
+    pipe_peak = peaks["bf16_tflops"] if prec == 2 else peaks["bf16_tflops"] / 2.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], f"profiles/r1_gemm_traffic.json ({tj['source']}, cold-cache ncu capture)"
     roofline = {
-        "kernel": f"gemm_tile_kernel<BLOCK_N,{passes}> (tcgen05 TF32 x{passes}), {cat_n['gemm']} launches per PoseNet forward",
+        "kernel": f"gemm_tile_kernel ({kernel_kind}), {cat_n['gemm']} launches per PoseNet forward",
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": (achieved / peaks["bf16_tflops"]) if achieved else None, "traffic": None,
+        "frac": (achieved / peaks["bf16_tflops"]) if achieved else None, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peaks["source"],
         "algorithmic_flops_per_forward": flops, "avg_launch_us": 1000.0 * cat_ms["gemm"] / max(cat_n["gemm"], 1),
-        "tensor_work_frac_of_tf32_peak": (achieved * passes / (peaks["bf16_tflops"] / 2.0)) if achieved else None,
+        "tensor_pipe_frac": (achieved * passes / pipe_peak) if achieved else None,
+        "tensor_pipe_frac_note": "issued tensor work (3 products per algorithmic flop) / peak of that operand type",
         "share_of_forward": {k: cat_ms[k] / max(sum(cat_ms.values()), 1e-9) for k in cat_ms},
         "forward_ms_by_kernel_class": cat_ms,
     }
@@ -311,7 +323,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (TF32x3 error-compensated tensor-core GEMMs)" if passes == 3 else "tf32",
+            "vs_baseline": None, "dtype": {3: "f32 (TF32 hi/lo error-compensated tensor-core GEMMs)", 2: "f32 (fp16 hi/lo error-compensated tensor-core GEMMs)",
+                                                   1: "tf32"}[prec],
             "data": "synthetic", "config": workload_config(world, "B200"),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": cond_host.numel() * 4,

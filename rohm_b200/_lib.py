@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "librohm_b200.so")
 
 ROHM_OK = 0
 PRECISION_TF32X3 = 3
+PRECISION_F16X2 = 2
 PRECISION_TF32 = 1
 DDPM_COEFS = 8
 

@@ -66,11 +66,14 @@ class DevicePool {
   int64_t total_ = 0;
 };
 
-// A weight matrix [N, K] repacked for the GEMM: zero-padded to [Np, Kp] and split into TF32 hi / lo.
+// A weight matrix [N, K] repacked for the GEMM: zero-padded to [Np, Kp] and split into a hi / lo pair: TF32 values in
+// fp32 containers (kind 0) or fp16 values of w * scale (kind 1, scale a power of two; see gemm.cuh GemmKind).
 struct PackedWeight {
   float* hi = nullptr;
   float* lo = nullptr;
   int N = 0, K = 0, Np = 0, Kp = 0, block_n = 0;
+  int kind = 0;
+  float scale = 1.0f;
 };
 
 }  // namespace rohm

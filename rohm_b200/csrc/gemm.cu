@@ -64,9 +64,10 @@ struct EpiParams {
   const float* bias;
   const float* residual;
   float* out;
-  float* out_hi;
-  float* out_lo;
+  void* out_hi;
+  void* out_lo;
   double* gn_stats;
+  float acc_scale;
   int ldr, ldo, lds, act, M, N, out_row_mul, out_row_add, clip_rows, clip_valid, gn_groups, gn_group_size;
 };
 
@@ -75,9 +76,10 @@ struct EpiParams {
 // Epilogue variants: 0 = bias + residual + fp32 / hi-lo stores (the PoseNet linears), 1 = the same + exact GELU (FFN1),
 // 2 = everything (other activations, padded-clip row masks, GroupNorm partial sums: TrajNet).  Separate instantiations keep the hot variants' code small (the full
 // epilogue is ~7000 SASS instructions, most of them predicated-off activation code when unused).
-template <int BLOCK_N, int PASSES, int EPI>
+template <int BLOCK_N, int PASSES, int EPI, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
-  constexpr bool LEAN = EPI != 2;  // EPI: 0 = bias/residual/stores, 1 = the same + exact GELU, 2 = everything
+  constexpr bool LEAN = EPI != 2;
+  constexpr int kElemK = gemm_block_k(KIND);  // K elements per pipeline stage (TMA coordinates are in elements)  // EPI: 0 = bias/residual/stores, 1 = the same + exact GELU, 2 = everything
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[Cfg::kStages];
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     epi_s.out_row_mul = p.out_row_mul, epi_s.out_row_add = p.out_row_add, epi_s.clip_rows = p.clip_rows;
     epi_s.clip_valid = p.clip_valid, epi_s.gn_stats = p.gn_stats, epi_s.gn_groups = p.gn_groups;
     epi_s.gn_group_size = p.gn_group_size;
+    epi_s.acc_scale = p.acc_scale == 0.0f ? 1.0f : p.acc_scale;
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -152,15 +155,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         for (int s = 0; s < p.num_segs; ++s) {
           const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
           const int nkb = p.seg_kblocks[s];
-          for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kGemmBlockK) {
+          for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kElemK) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (it == 0) stamp(p, 2);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kGemmBlockK, row);
+            ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kElemK, row);
             ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], kcol, n0);
             if (PASSES == 3) {
-              ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kGemmBlockK, row);
+              ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kElemK, row);
               ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], kcol, n0);
             }
             if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
@@ -171,7 +174,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(/*TF32*/ 2, kGemmBlockM, BLOCK_N);
+      constexpr uint32_t idesc = ptx::make_idesc(KIND == kKindF16 ? /*F16*/ 0 : /*TF32*/ 2, kGemmBlockM, BLOCK_N);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
+        if (KIND == kKindF16) ptx::mma_f16_ss(d, a, b, id, accumulate);
+        else ptx::mma_tf32_ss(d, a, b, id, accumulate);
+      };
       int it = 0, tcount = 0, stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -191,15 +198,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           const uint64_t b_lo = ptx::make_desc_kmajor<kGemmBlockK * 4>(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kGemmBlockK / 8; ++k) {
-            // advancing K by 8 fp32 = 32 bytes inside the swizzle span: +2 in the (>>4) address field
+            // advancing K by one instruction (8 fp32 / 16 fp16 = 32 bytes) inside the swizzle span: +2 in the (>>4)
+            // address field
             const uint64_t koff = static_cast<uint64_t>(k * 2);
             const uint32_t first = (ki > 0 || k > 0) ? 1u : 0u;
             if (PASSES == 3) {
-              ptx::mma_tf32_ss(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, first);
-              ptx::mma_tf32_ss(acc + BLOCK_N, a_hi + koff, b_lo + koff, idesc, 1u);
-              ptx::mma_tf32_ss(acc, a_hi + koff, b_hi + koff, idesc, first);
+              mma(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, first);
+              mma(acc + BLOCK_N, a_hi + koff, b_lo + koff, idesc, 1u);
+              mma(acc, a_hi + koff, b_hi + koff, idesc, first);
             } else {
-              ptx::mma_tf32_ss(acc, a_hi + koff, b_hi + koff, idesc, first);
+              mma(acc, a_hi + koff, b_hi + koff, idesc, first);
             }
           }
           ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -283,6 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (PASSES == 3) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
+        }
+        if (KIND == kKindF16) {  // undo the power-of-two weight scale (exact)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= e.acc_scale;
         }
         if (nb >= e.N) continue;  // warp-uniform
 
@@ -377,11 +389,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
               const int64_t orr = static_cast<int64_t>(mr) * e.out_row_mul + e.out_row_add;
               if (e.out != nullptr) *reinterpret_cast<float4*>(e.out + orr * e.ldo + nb + tc) = w;
               if (e.out_hi != nullptr) {
-                float4 h, l;
-                h.x = ptx::to_tf32(w.x), h.y = ptx::to_tf32(w.y), h.z = ptx::to_tf32(w.z), h.w = ptx::to_tf32(w.w);
-                l.x = w.x - h.x, l.y = w.y - h.y, l.z = w.z - h.z, l.w = w.w - h.w;
-                *reinterpret_cast<float4*>(e.out_hi + orr * e.lds + nb + tc) = h;
-                *reinterpret_cast<float4*>(e.out_lo + orr * e.lds + nb + tc) = l;
+                if (KIND == kKindF16) {
+                  uint2 h, l;
+                  ptx::split_f16x4(w, h, l);
+                  *reinterpret_cast<uint2*>(static_cast<__half*>(e.out_hi) + orr * e.lds + nb + tc) = h;
+                  *reinterpret_cast<uint2*>(static_cast<__half*>(e.out_lo) + orr * e.lds + nb + tc) = l;
+                } else {
+                  float4 h, l;
+                  h.x = ptx::to_tf32(w.x), h.y = ptx::to_tf32(w.y), h.z = ptx::to_tf32(w.z), h.w = ptx::to_tf32(w.w);
+                  l.x = w.x - h.x, l.y = w.y - h.y, l.z = w.z - h.z, l.w = w.w - h.w;
+                  *reinterpret_cast<float4*>(static_cast<float*>(e.out_hi) + orr * e.lds + nb + tc) = h;
+                  *reinterpret_cast<float4*>(static_cast<float*>(e.out_lo) + orr * e.lds + nb + tc) = l;
+                }
               }
             }
           }
@@ -395,9 +414,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             for (int j = 0; j < 32; ++j)
               if (nb + j < e.N) o[j] = v[j];
           }
-          if (e.out_hi != nullptr) {
-            float* oh = e.out_hi + orow * e.lds + nb;
-            float* ol = e.out_lo + orow * e.lds + nb;
+          if (e.out_hi != nullptr && KIND == kKindF16) {
+            __half* oh = static_cast<__half*>(e.out_hi) + orow * e.lds + nb;
+            __half* ol = static_cast<__half*>(e.out_lo) + orow * e.lds + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) ptx::split_f16(v[j], oh[j], ol[j]);
+          } else if (e.out_hi != nullptr) {
+            float* oh = static_cast<float*>(e.out_hi) + orow * e.lds + nb;
+            float* ol = static_cast<float*>(e.out_lo) + orow * e.lds + nb;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (nb + j < e.N) {
@@ -437,6 +462,13 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n,
+                                 float scale) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) ptx::split_f16(x[i] * scale, hi[i], lo[i]);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -449,28 +481,28 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-template <int BLOCK_N, int PASSES>
+template <int BLOCK_N, int PASSES, int KIND>
 static cudaError_t set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 0, KIND>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BLOCK_N, PASSES>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            TileCfg<BLOCK_N, PASSES>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 2, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               TileCfg<BLOCK_N, PASSES>::kSmemBytes);
 }
 
-template <int BLOCK_N, int PASSES>
+template <int BLOCK_N, int PASSES, int KIND>
 cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t stream, bool pdl) {
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   const bool plain = p.clip_rows == 0 && p.gn_stats == nullptr;
-  auto kern = (plain && p.act == kActNone)   ? gemm_tile_kernel<BLOCK_N, PASSES, 0>
-              : (plain && p.act == kActGelu) ? gemm_tile_kernel<BLOCK_N, PASSES, 1>
-                                             : gemm_tile_kernel<BLOCK_N, PASSES, 2>;
+  auto kern = (plain && p.act == kActNone)   ? gemm_tile_kernel<BLOCK_N, PASSES, 0, KIND>
+              : (plain && p.act == kActGelu) ? gemm_tile_kernel<BLOCK_N, PASSES, 1, KIND>
+                                             : gemm_tile_kernel<BLOCK_N, PASSES, 2, KIND>;
   static bool attr_set = false;
   if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
-    cudaError_t e = set_attr<BLOCK_N, PASSES>();
+    cudaError_t e = set_attr<BLOCK_N, PASSES, KIND>();
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -499,17 +531,18 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
 
 }  // namespace
 
-int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                 int row_elem_stride) {
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                 int row_elem_stride, int kind) {
   auto fn = get_encode_fn();
   if (fn == nullptr) return -1;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * gemm_elem_bytes(kind)};
   // With a traversal stride s the box spans box_rows * s tensor rows and TMA delivers every s-th of them
   // (ceil(boxDim / elementStride) elements), so smem still receives exactly box_rows rows.
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), static_cast<cuuint32_t>(box_rows * row_elem_stride)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(gemm_block_k(kind)), static_cast<cuuint32_t>(box_rows * row_elem_stride)};
   cuuint32_t estride[2] = {1u, static_cast<cuuint32_t>(row_elem_stride)};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+  CUresult r = fn(map, kind == kKindF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, kGemmBlockK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -517,11 +550,13 @@ int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n, int passes, cudaStream_t stream,
-                        bool pdl) {
-#define ROHM_GEMM_CASE(BN)                                                             \
-  case BN:                                                                             \
-    return passes == 3 ? launch_cfg<BN, 3>(p, m_rows, n_cols, stream, pdl)             \
-                       : launch_cfg<BN, 1>(p, m_rows, n_cols, stream, pdl);
+                        bool pdl, int kind) {
+  if (kind == kKindF16 && passes != 3) return cudaErrorInvalidValue;
+#define ROHM_GEMM_CASE(BN)                                                                       \
+  case BN:                                                                                       \
+    if (kind == kKindF16) return launch_cfg<BN, 3, kKindF16>(p, m_rows, n_cols, stream, pdl);    \
+    return passes == 3 ? launch_cfg<BN, 3, kKindTf32>(p, m_rows, n_cols, stream, pdl)            \
+                       : launch_cfg<BN, 1, kKindTf32>(p, m_rows, n_cols, stream, pdl);
   switch (block_n) {
     ROHM_GEMM_CASE(32)
     ROHM_GEMM_CASE(64)
@@ -535,15 +570,29 @@ cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n
 
 cudaError_t gemm_init_attributes() {
   cudaError_t e;
-  if ((e = set_attr<32, 1>()) != cudaSuccess) return e;
-  if ((e = set_attr<32, 3>()) != cudaSuccess) return e;
-  if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
-  if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
-  if ((e = set_attr<96, 1>()) != cudaSuccess) return e;
-  if ((e = set_attr<96, 3>()) != cudaSuccess) return e;
-  if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
-  if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
+  if ((e = set_attr<32, 1, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<32, 3, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 1, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 3, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<96, 1, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<96, 3, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 1, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 3, kKindTf32>()) != cudaSuccess) return e;
+  if ((e = set_attr<32, 3, kKindF16>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 3, kKindF16>()) != cudaSuccess) return e;
+  if ((e = set_attr<96, 3, kKindF16>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 3, kKindF16>()) != cudaSuccess) return e;
   return cudaSuccess;
+}
+
+cudaError_t launch_split_f16(const float* x, void* hi, void* lo, int64_t n, float scale, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_f16_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                                          n, scale);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {

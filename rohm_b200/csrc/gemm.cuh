@@ -37,6 +37,16 @@ constexpr int kGemmBlockK = ROHM_GEMM_BLOCK_K;
 static_assert(kGemmBlockK == 16 || kGemmBlockK == 32, "one 64- or 128-byte swizzle span");
 constexpr int kMaxSegs = 10;
 
+// Operand element type of a GEMM.  kKindTf32: fp32 containers holding TF32 hi/lo pairs (tcgen05 kind::tf32, 8 K-columns
+// per instruction).  kKindF16: fp16 hi/lo pairs (kind::f16, 16 K-columns per instruction): the same 2 x 11 significant
+// bits per value in half the bytes, so one 128-byte swizzle row -- one pipeline stage -- covers twice the K extent at the
+// same tensor-pipe and shared-memory-fill cost.  Weights are pre-scaled by a power of two into the middle of the fp16
+// range (GemmParams::acc_scale undoes it exactly in the epilogue); activations must stay below 1.3e5 in magnitude.
+enum GemmKind : int { kKindTf32 = 0, kKindF16 = 1 };
+// K extent of one pipeline stage in elements
+__host__ __device__ constexpr int gemm_block_k(int kind) { return kind == kKindF16 ? 2 * kGemmBlockK : kGemmBlockK; }
+__host__ __device__ constexpr int gemm_elem_bytes(int kind) { return kind == kKindF16 ? 2 : 4; }
+
 enum GemmAct : int { kActNone = 0, kActGelu = 1, kActSilu = 2, kActMish = 3 };
 
 struct alignas(64) GemmParams {
@@ -44,7 +54,7 @@ struct alignas(64) GemmParams {
   CUtensorMap a_lo[kMaxSegs];
   CUtensorMap b_hi;
   CUtensorMap b_lo;
-  int seg_kblocks[kMaxSegs];    // number of 32-wide K blocks of this segment
+  int seg_kblocks[kMaxSegs];    // number of gemm_block_k(kind)-wide K blocks of this segment
   int seg_row_shift[kMaxSegs];  // A row coordinate = m0 * seg_row_mul + seg_row_shift
   int seg_row_mul[kMaxSegs];
   int num_segs;
@@ -54,9 +64,10 @@ struct alignas(64) GemmParams {
   int ldr;
   float* out;  // fp32 [*, ldo] or nullptr
   int ldo;
-  float* out_hi;  // TF32 split of the result for a following GEMM, or nullptr
-  float* out_lo;
-  int lds;
+  void* out_hi;  // hi/lo split of the result for a following GEMM (fp32 TF32 pairs or fp16 pairs, as the kind), or nullptr
+  void* out_lo;
+  int lds;        // pitch of out_hi / out_lo in elements
+  float acc_scale;  // the accumulator is multiplied by this before the bias (0 = 1.0); kKindF16: 2^-s of the weight scale
   int act;
   int M;  // rows to store (rows >= M are never written)
   int N;  // columns to store
@@ -81,13 +92,13 @@ struct alignas(64) GemmParams {
 // Fills a 2-D fp32 tensor map: inner dim `cols` (contiguous), outer dim `rows`, row pitch `ld` elements,
 // box = {kGemmBlockK, box_rows}, SWIZZLE_64B/128B to match, zero OOB fill, optional row traversal stride.
 // Returns 0 on success, a CUresult otherwise.
-int make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                 int row_elem_stride = 1);
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                 int row_elem_stride = 1, int kind = kKindTf32);
 
-// Launches the tile kernel.  block_n in {32, 64, 96, 128}; passes in {1, 3}.
+// Launches the tile kernel.  block_n in {32, 64, 96, 128}; passes in {1, 3} (kKindF16: 3 only).
 // grid = ceil(M_tiles) x ceil(N_tiles) where M_tiles covers `m_rows` GEMM rows.
 cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n, int passes, cudaStream_t stream,
-                        bool pdl = false);
+                        bool pdl = false, int kind = kKindTf32);
 
 // Raises the dynamic shared-memory limit of every kernel instantiation (call once per process, outside any stream
 // capture).
@@ -95,5 +106,7 @@ cudaError_t gemm_init_attributes();
 
 // fp32 -> (hi, lo) TF32 split, elementwise; n elements.
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
+// fp32 -> (hi, lo) fp16 split of x * scale, elementwise; n elements.
+cudaError_t launch_split_f16(const float* x, void* hi, void* lo, int64_t n, float scale, cudaStream_t stream);
 
 }  // namespace rohm

@@ -25,7 +25,7 @@ namespace {
 
 // [B, C, T] (frames contiguous) -> token rows (b*S + 1 + t) of a [B*S, ld] hi/lo pair.  32x32 smem transpose.
 __global__ void pack_tokens_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int C,
-                                   int T, int S, int ld) {
+                                   int T, int S, int ld, int f16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -39,10 +39,14 @@ __global__ void pack_tokens_kernel(const float* __restrict__ x, float* __restric
     const int t = t0 + j, c = c0 + tx;
     if (t < T && c < C) {
       const float v = tile[tx][j];
-      const float h = ptx::to_tf32(v);
       const int64_t o = (static_cast<int64_t>(b) * S + 1 + t) * ld + c;
-      hi[o] = h;
-      lo[o] = v - h;
+      if (f16) {
+        ptx::split_f16(v, reinterpret_cast<__half*>(hi)[o], reinterpret_cast<__half*>(lo)[o]);
+      } else {
+        const float h = ptx::to_tf32(v);
+        hi[o] = h;
+        lo[o] = v - h;
+      }
     }
   }
 }
@@ -87,7 +91,7 @@ __global__ void pe_rows_kernel(const float* __restrict__ pe, float* __restrict__
 // over all pe_len timesteps); per step the token row (b, 0) is a gather.
 __global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, const float* __restrict__ table,
                                          int table_rows, float* __restrict__ X, float* __restrict__ Xh,
-                                         float* __restrict__ Xl, int S, int D) {
+                                         float* __restrict__ Xl, int S, int D, int f16) {
   const int b = blockIdx.x;
   int64_t t = timesteps[b];
   t = t < 0 ? 0 : (t >= table_rows ? table_rows - 1 : t);
@@ -95,12 +99,19 @@ __global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, 
   const int64_t o = static_cast<int64_t>(b) * S * D;
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
     const float4 v = src[i];
-    float4 h, l;
-    h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
-    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
     reinterpret_cast<float4*>(X + o)[i] = v;
-    reinterpret_cast<float4*>(Xh + o)[i] = h;
-    reinterpret_cast<float4*>(Xl + o)[i] = l;
+    if (f16) {
+      uint2 h, l;
+      ptx::split_f16x4(v, h, l);
+      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Xh) + o)[i] = h;
+      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Xl) + o)[i] = l;
+    } else {
+      float4 h, l;
+      h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
+      l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+      reinterpret_cast<float4*>(Xh + o)[i] = h;
+      reinterpret_cast<float4*>(Xl + o)[i] = l;
+    }
   }
 }
 
@@ -114,7 +125,7 @@ template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ out,
                                                         float* __restrict__ out_hi, float* __restrict__ out_lo,
-                                                        int rows) {
+                                                        int rows, int f16) {
   static_assert(D % 128 == 0, "row must be a multiple of 32 lanes x float4");
   constexpr int V = D / 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -145,19 +156,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float4* o = reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * D);
   float4* oh = reinterpret_cast<float4*>(out_hi + static_cast<int64_t>(row) * D);
   float4* ol = reinterpret_cast<float4*>(out_lo + static_cast<int64_t>(row) * D);
+  uint2* oh16 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_hi) + static_cast<int64_t>(row) * D);
+  uint2* ol16 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_lo) + static_cast<int64_t>(row) * D);
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
-    float4 y, h, l;
+    float4 y;
     y.x = (x[i].x - mean) * rstd * g.x + bb.x;
     y.y = (x[i].y - mean) * rstd * g.y + bb.y;
     y.z = (x[i].z - mean) * rstd * g.z + bb.z;
     y.w = (x[i].w - mean) * rstd * g.w + bb.w;
-    h.x = ptx::to_tf32(y.x), h.y = ptx::to_tf32(y.y), h.z = ptx::to_tf32(y.z), h.w = ptx::to_tf32(y.w);
-    l.x = y.x - h.x, l.y = y.y - h.y, l.z = y.z - h.z, l.w = y.w - h.w;
     o[lane + 32 * i] = y;
-    oh[lane + 32 * i] = h;
-    ol[lane + 32 * i] = l;
+    if (f16) {
+      uint2 h, l;
+      ptx::split_f16x4(y, h, l);
+      oh16[lane + 32 * i] = h;
+      ol16[lane + 32 * i] = l;
+    } else {
+      float4 h, l;
+      h.x = ptx::to_tf32(y.x), h.y = ptx::to_tf32(y.y), h.z = ptx::to_tf32(y.z), h.w = ptx::to_tf32(y.w);
+      l.x = y.x - h.x, l.y = y.y - h.y, l.z = y.z - h.z, l.w = y.w - h.w;
+      oh[lane + 32 * i] = h;
+      ol[lane + 32 * i] = l;
+    }
   }
 }
 
@@ -166,7 +187,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // qkv: [B*S, 3*D] fp32 (Q | K | V, head h at columns h*DH).  ctx hi/lo: [B*S, D].
 template <int DH>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx_hi,
-                                                        float* __restrict__ ctx_lo, int S, int D, int H, float scale) {
+                                                        float* __restrict__ ctx_lo, int S, int D, int H, float scale,
+                                                        int f16) {
   constexpr int KP = DH + 4;  // padded K row: conflict-free float4 reads with one key per lane
   constexpr int NW = 8;
   extern __shared__ float sm[];
@@ -262,6 +284,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
       }
     }
     const int64_t o = (base + i) * D + h * DH + lane * CPL;
+    if (f16) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+        ptx::split_f16(acc[c], reinterpret_cast<__half*>(ctx_hi)[o + c], reinterpret_cast<__half*>(ctx_lo)[o + c]);
+      __syncwarp();
+      continue;
+    }
     float hh[CPL], ll[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
@@ -313,7 +342,7 @@ template <int DH, int NT>  // NT = number of 8-key tiles (keys padded to 8*NT), 
 __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(const float* __restrict__ qkv,
                                                                           float* __restrict__ ctx_hi,
                                                                           float* __restrict__ ctx_lo, int S, int D,
-                                                                          int H, float scale) {
+                                                                          int H, float scale, int f16) {
   extern __shared__ float sm[];
   float* Ks = sm;                          // [8*NT][kAttnPitch]
   float* Vs = Ks + 8 * NT * kAttnPitch;    // [8*NT][kAttnPitch]
@@ -471,6 +500,20 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(c
       const int n = n0 + u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[u][i] += os[u][i];
+      if (f16) {
+        __half2 hA, lA, hB, lB;
+        ptx::split_f16(o[u][0], hA.x, lA.x), ptx::split_f16(o[u][1], hA.y, lA.y);
+        ptx::split_f16(o[u][2], hB.x, lB.x), ptx::split_f16(o[u][3], hB.y, lB.y);
+        if (okA) {
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(ctx_hi) + oA + 8 * n) = hA;
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(ctx_lo) + oA + 8 * n) = lA;
+        }
+        if (okB) {
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(ctx_hi) + oB + 8 * n) = hB;
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(ctx_lo) + oB + 8 * n) = lB;
+        }
+        continue;
+      }
       if (okA) {
         const float h0 = ptx::to_tf32(o[u][0]), h1 = ptx::to_tf32(o[u][1]);
         *reinterpret_cast<float2*>(ctx_hi + oA + 8 * n) = make_float2(h0, h1);
@@ -510,6 +553,7 @@ struct rohm_posenet {
   rohm_ctx* ctx = nullptr;
   DevicePool pool;
   int D = 0, F = 0, L = 0, H = 0, C = 0, Cout = 0, traj = 0, pe_len = 0, passes = 3;
+  int kind = kKindTf32;  // operand element type of every per-step GEMM (kKindF16 in ROHM_PRECISION_F16X2)
   int max_batch = 0, max_frames = 0;
   int64_t max_rows = 0;
   int Kin_p = 0;
@@ -587,27 +631,68 @@ static int pick_block_n(int N) {
 
 // device [N,K] fp32 -> padded hi/lo pair
 static __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int N,
-                                   int K, int Kp) {
+                                   int K, int Kp, int f16, float scale) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(N) * K) return;
   const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
   const float v = w[i];
-  const float h = ptx::to_tf32(v);
-  hi[static_cast<int64_t>(n) * Kp + k] = h;
-  lo[static_cast<int64_t>(n) * Kp + k] = v - h;
+  const int64_t o = static_cast<int64_t>(n) * Kp + k;
+  if (f16) {
+    ptx::split_f16(v * scale, reinterpret_cast<__half*>(hi)[o], reinterpret_cast<__half*>(lo)[o]);
+  } else {
+    const float h = ptx::to_tf32(v);
+    hi[o] = h;
+    lo[o] = v - h;
+  }
 }
 
-static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out) {
+// max |w| over n elements (bit pattern of a non-negative float is monotonic in its value)
+static __global__ void absmax_kernel(const float* __restrict__ w, int64_t n, unsigned int* __restrict__ out) {
+  float m = 0.0f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float a = fabsf(w[i]);
+    m = (a <= 3.0e38f && a > m) ? a : m;  // ignores NaN / inf
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// kind == kKindF16: the matrix is stored as fp16 hi/lo of w * 2^s, s chosen per matrix so that max |w| 2^s lies in
+// [2^13, 2^14): every weight within 2^-13 of the largest keeps a normal-range lo half, and nothing overflows.
+static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out, int kind = kKindTf32) {
   out->N = N, out->K = K;
   out->block_n = pick_block_n(N);
   out->Np = static_cast<int>(round_up(N, out->block_n));
-  out->Kp = static_cast<int>(round_up(K, kGemmBlockK));
-  out->hi = pn->pool.floats(static_cast<int64_t>(out->Np) * out->Kp);
-  out->lo = pn->pool.floats(static_cast<int64_t>(out->Np) * out->Kp);
+  out->Kp = static_cast<int>(round_up(K, gemm_block_k(kind)));
+  out->kind = kind;
+  out->scale = 1.0f;
+  const int64_t bytes = static_cast<int64_t>(out->Np) * out->Kp * gemm_elem_bytes(kind);
+  out->hi = static_cast<float*>(pn->pool.bytes(bytes));
+  out->lo = static_cast<float*>(pn->pool.bytes(bytes));
   if (out->hi == nullptr || out->lo == nullptr)
     return fail(pn->ctx, ROHM_ERR_CUDA, "weight alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
   const int64_t n = static_cast<int64_t>(N) * K;
-  pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w, out->hi, out->lo, N, K, out->Kp);
+  if (kind == kKindF16) {
+    unsigned int* d_max = static_cast<unsigned int*>(pn->pool.bytes(16));
+    if (d_max == nullptr) return fail(pn->ctx, ROHM_ERR_CUDA, "weight alloc failed");
+    absmax_kernel<<<148, 256>>>(w, n, d_max);
+    ROHM_CUDA(pn->ctx, cudaGetLastError());
+    unsigned int bits = 0;
+    ROHM_CUDA(pn->ctx, cudaMemcpy(&bits, d_max, sizeof bits, cudaMemcpyDeviceToHost));
+    float wmax;
+    memcpy(&wmax, &bits, sizeof wmax);
+    if (wmax > 0.0f) {
+      int e2 = 0;
+      frexpf(wmax, &e2);  // wmax = f * 2^e2, f in [0.5, 1)
+      int s = 14 - e2;
+      s = s > 100 ? 100 : (s < -100 ? -100 : s);
+      out->scale = ldexpf(1.0f, s);
+    }
+  }
+  pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w, out->hi, out->lo, N, K, out->Kp,
+                                                                     kind == kKindF16 ? 1 : 0, out->scale);
   ROHM_CUDA(pn->ctx, cudaGetLastError());
   return ROHM_OK;
 }
@@ -623,13 +708,14 @@ static int copy_vec(rohm_posenet* pn, const float* src, int64_t n, float** dst) 
 static int setup_linear(rohm_posenet* pn, GemmParams* g, const float* a_hi, const float* a_lo, int64_t rows, int K, int lda,
                  const PackedWeight& w, const float* bias) {
   *g = GemmParams{};
-  int rc = make_tmap_2d(&g->a_hi[0], a_hi, rows, K, lda, kGemmBlockM);
-  rc |= make_tmap_2d(&g->a_lo[0], a_lo, rows, K, lda, kGemmBlockM);
-  rc |= make_tmap_2d(&g->b_hi, w.hi, w.Np, w.Kp, w.Kp, w.block_n);
-  rc |= make_tmap_2d(&g->b_lo, w.lo, w.Np, w.Kp, w.Kp, w.block_n);
+  int rc = make_tmap_2d(&g->a_hi[0], a_hi, rows, K, lda, kGemmBlockM, 1, w.kind);
+  rc |= make_tmap_2d(&g->a_lo[0], a_lo, rows, K, lda, kGemmBlockM, 1, w.kind);
+  rc |= make_tmap_2d(&g->b_hi, w.hi, w.Np, w.Kp, w.Kp, w.block_n, 1, w.kind);
+  rc |= make_tmap_2d(&g->b_lo, w.lo, w.Np, w.Kp, w.Kp, w.block_n, 1, w.kind);
   if (rc != 0) return fail(pn->ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
   g->num_segs = 1;
-  g->seg_kblocks[0] = w.Kp / kGemmBlockK;
+  g->seg_kblocks[0] = w.Kp / gemm_block_k(w.kind);
+  g->acc_scale = 1.0f / w.scale;
   g->seg_row_shift[0] = 0;
   g->seg_row_mul[0] = 1;
   g->bias = bias;
@@ -644,7 +730,7 @@ static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int 
   prof_begin(pn, kCatGemm, st);
   // programmatic dependent launch: this GEMM's prologue (barrier init, TMEM alloc, tensor-map prefetch) overlaps the
   // tail of the previous kernel; its griddepcontrol.wait orders all global reads/writes after that kernel
-  ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st, pn->use_pdl && !pn->profiling));
+  ROHM_CUDA(pn->ctx, launch_gemm(g, rows, w.N, w.block_n, pn->passes, st, pn->use_pdl && !pn->profiling, w.kind));
   prof_end(pn, st);
   pn->launches++;
   return ROHM_OK;
@@ -652,18 +738,19 @@ static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int 
 
 template <int D>
 static void launch_ln(const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
-               cudaStream_t st) {
-  layernorm_kernel<D><<<(rows + 7) / 8, 256, 0, st>>>(in, g, b, out, oh, ol, rows);
+               cudaStream_t st, int f16) {
+  layernorm_kernel<D><<<(rows + 7) / 8, 256, 0, st>>>(in, g, b, out, oh, ol, rows, f16);
 }
 
 static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
            cudaStream_t st) {
   prof_begin(pn, kCatLayerNorm, st);
+  const int f16 = pn->kind == kKindF16 ? 1 : 0;
   switch (pn->D) {
-    case 128: launch_ln<128>(in, g, b, out, oh, ol, rows, st); break;
-    case 256: launch_ln<256>(in, g, b, out, oh, ol, rows, st); break;
-    case 512: launch_ln<512>(in, g, b, out, oh, ol, rows, st); break;
-    case 1024: launch_ln<1024>(in, g, b, out, oh, ol, rows, st); break;
+    case 128: launch_ln<128>(in, g, b, out, oh, ol, rows, st, f16); break;
+    case 256: launch_ln<256>(in, g, b, out, oh, ol, rows, st, f16); break;
+    case 512: launch_ln<512>(in, g, b, out, oh, ol, rows, st, f16); break;
+    case 1024: launch_ln<1024>(in, g, b, out, oh, ol, rows, st, f16); break;
     default: return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported d_model %d for LayerNorm", pn->D);
   }
   prof_end(pn, st);
@@ -683,7 +770,8 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
     attr_set = true;
   }
   const int warps = (S + 15) / 16;
-  kern<<<B * pn->H, 32 * warps, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+  kern<<<B * pn->H, 32 * warps, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
+                                            pn->kind == kKindF16 ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -706,9 +794,11 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   if (!done) {
     const size_t smem = attention_smem_bytes(S, dh);
     if (dh == 128) {
-      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
+                                                          pn->kind == kKindF16 ? 1 : 0);
     } else if (dh == 64) {
-      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale);
+      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
+                                                         pn->kind == kKindF16 ? 1 : 0);
     } else {
       return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
     }
@@ -759,10 +849,10 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   if (ctx == nullptr) return ROHM_ERR_INVALID;
   if (w == nullptr || out == nullptr || max_batch <= 0 || max_frames <= 0)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: bad arguments");
-  if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32)
-    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: precision must be 3 (TF32x3) or 1 (TF32)");
-  if (w->d_model % 128 != 0 || w->d_model % w->num_heads != 0 || w->ff_size % 32 != 0)
-    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: d_model must be a multiple of 128, ff_size of 32");
+  if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32 && precision != ROHM_PRECISION_F16X2)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: precision must be 3 (TF32x3), 2 (F16x2) or 1 (TF32)");
+  if (w->d_model % 128 != 0 || w->d_model % w->num_heads != 0 || w->ff_size % 64 != 0)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: d_model must be a multiple of 128, ff_size of 64");
   const int dh = w->d_model / w->num_heads;
   if (dh != 64 && dh != 128) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: head dim must be 64 or 128");
   if (max_frames + 1 > 256) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: at most 255 frames per clip");
@@ -774,10 +864,11 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   pn->ctx = ctx;
   pn->D = w->d_model, pn->F = w->ff_size, pn->L = w->num_layers, pn->H = w->num_heads;
   pn->C = w->in_feats, pn->Cout = w->out_feats, pn->traj = w->traj_feats, pn->pe_len = w->pe_len;
-  pn->passes = precision;
+  pn->kind = precision == ROHM_PRECISION_F16X2 ? kKindF16 : kKindTf32;
+  pn->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
   pn->max_batch = max_batch, pn->max_frames = max_frames;
   pn->max_rows = static_cast<int64_t>(max_batch) * (max_frames + 1);
-  pn->Kin_p = static_cast<int>(round_up(pn->C, kGemmBlockK));
+  pn->Kin_p = static_cast<int>(round_up(pn->C, gemm_block_k(pn->kind)));
   const int D = pn->D, F = pn->F;
   const int64_t R = pn->max_rows;
 
@@ -790,9 +881,9 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     }                        \
   } while (0)
 
-  TRY(pack_weight(pn, w->in_w, D, pn->C, &pn->w_in));
-  TRY(pack_weight(pn, w->cond_w, D, pn->C, &pn->w_cond));
-  TRY(pack_weight(pn, w->out_w, pn->Cout, D, &pn->w_out));
+  TRY(pack_weight(pn, w->in_w, D, pn->C, &pn->w_in, pn->kind));
+  TRY(pack_weight(pn, w->cond_w, D, pn->C, &pn->w_cond, pn->kind));
+  TRY(pack_weight(pn, w->out_w, pn->Cout, D, &pn->w_out, pn->kind));
   TRY(copy_vec(pn, w->in_b, D, &pn->in_b));
   TRY(copy_vec(pn, w->cond_b, D, &pn->cond_b));
   TRY(copy_vec(pn, w->out_b, pn->Cout, &pn->out_b));
@@ -802,10 +893,10 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   for (int l = 0; l < pn->L; ++l) {
     const rohm_posenet_layer& s = w->layers[l];
     PoseNetLayerDev& d = pn->layers[l];
-    TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv));
-    TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj));
-    TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1));
-    TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2));
+    TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv, pn->kind));
+    TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj, pn->kind));
+    TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1, pn->kind));
+    TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2, pn->kind));
     TRY(copy_vec(pn, s.in_proj_b, 3 * D, &d.qkv_b));
     TRY(copy_vec(pn, s.out_proj_b, D, &d.proj_b));
     TRY(copy_vec(pn, s.lin1_b, F, &d.ff1_b));
@@ -919,7 +1010,8 @@ extern "C" int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B,
   const int rows = B * S;
   // A_in <- tokens of cond (row (b,0) stays zero: the buffer was zero-initialised and is never written there)
   dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
-  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(cond, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p);
+  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(cond, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p,
+                                                   pn->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(ctx, cudaGetLastError());
   const int64_t total4 = static_cast<int64_t>(rows) * D / 4;
   pe_rows_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(pn->pe, pn->condpe, S, D, total4);
@@ -950,13 +1042,15 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
 
   dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
   prof_begin(pn, kCatOther, st);
-  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p);
+  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p,
+                                                   pn->kind == kKindF16 ? 1 : 0);
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
   if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
   prof_begin(pn, kCatOther, st);
-  time_token_gather_kernel<<<B, 128, 0, st>>>(timesteps, pn->time_table, pn->pe_len, pn->X, pn->Xh, pn->Xl, S, D);
+  time_token_gather_kernel<<<B, 128, 0, st>>>(timesteps, pn->time_table, pn->pe_len, pn->X, pn->Xh, pn->Xl, S, D,
+                                              pn->kind == kKindF16 ? 1 : 0);
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
@@ -1091,14 +1185,14 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   void* a_o = out;
   {
     cudaKernelNodeParams kp = fg->p_pack;
-    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 7);
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 8);
     args[0] = &a_x;
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_pack, &kp));
   }
   {
     cudaKernelNodeParams kp = fg->p_time;
-    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 8);
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 9);
     args[0] = &a_t;
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_time, &kp));

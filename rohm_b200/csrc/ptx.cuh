@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace rohm {
@@ -120,8 +121,8 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// BF16 inputs, FP32 accumulate.
-__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// F16 / BF16 inputs (the instruction descriptor says which), FP32 accumulate.
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -182,6 +183,27 @@ __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// Two-term fp16 split x ~= hi + lo (2 x 11 significant bits, the same 22 bits a TF32 hi/lo pair carries).  hi is
+// clamped to the fp16 range so values up to 2 x 65504 still split into finite halves; below 2^-14 the halves go
+// subnormal and the split degrades gracefully to an absolute error of 2^-25 per element.
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(x, -65504.0f), 65504.0f);
+  hi = __float2half_rn(c);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+// (x, y, z, w) -> four hi halves and four lo halves packed for 8-byte stores
+__device__ __forceinline__ void split_f16x4(const float4& v, uint2& hi, uint2& lo) {
+  __half h[4], l[4];
+  split_f16(v.x, h[0], l[0]);
+  split_f16(v.y, h[1], l[1]);
+  split_f16(v.z, h[2], l[2]);
+  split_f16(v.w, h[3], l[3]);
+  hi.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  hi.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  lo.x = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+  lo.y = static_cast<uint32_t>(__half_as_ushort(l[2])) | (static_cast<uint32_t>(__half_as_ushort(l[3])) << 16);
 }
 
 // Programmatic dependent launch hooks (no-ops unless the launch carries the PDL attribute).

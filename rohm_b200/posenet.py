@@ -17,13 +17,20 @@ from ._lib import RohmB200Error
 from .heads import InputProcess, OutputProcess, PositionalEncoding, TimestepEmbedder
 
 
-def _precision_from_env():
-    v = os.environ.get("ROHM_B200_PRECISION", "tf32x3").lower()
-    if v in ("tf32x3", "3xtf32", "fp32", "parity"):
+DEFAULT_PRECISION = "f16x2"
+
+
+def _precision_from_env(supports_f16=True):
+    """ROHM_B200_PRECISION: 'f16x2' (default: fp16 hi/lo pairs, fp32-grade), 'tf32x3' (TF32 hi/lo pairs, fp32-grade),
+    'tf32' (single pass, fast, ~1e-3).  Engines without an fp16 path (TrajNet) run 'f16x2' as 'tf32x3'."""
+    v = os.environ.get("ROHM_B200_PRECISION", DEFAULT_PRECISION).lower()
+    if v in ("f16x2", "fp16x2", "parity"):
+        return _lib.PRECISION_F16X2 if supports_f16 else _lib.PRECISION_TF32X3
+    if v in ("tf32x3", "3xtf32", "fp32"):
         return _lib.PRECISION_TF32X3
     if v in ("tf32", "fast"):
         return _lib.PRECISION_TF32
-    raise RohmB200Error(f"ROHM_B200_PRECISION={v!r}: expected 'tf32x3' (default, parity) or 'tf32' (fast)")
+    raise RohmB200Error(f"ROHM_B200_PRECISION={v!r}: expected 'f16x2' (default), 'tf32x3' or 'tf32' (fast)")
 
 
 class PoseNetEngine:
@@ -186,7 +193,7 @@ class PoseNet(nn.Module):
         self.embed_timestep = TimestepEmbedder(self.latent_dim, self.sequence_pos_encoder)
         self.output_process = OutputProcess(self.dataset.pose_feat_dim, self.latent_dim, self.nfeats)
 
-        self.precision = None  # None -> ROHM_B200_PRECISION env (default tf32x3)
+        self.precision = None  # None -> ROHM_B200_PRECISION env (default f16x2)
         self._engine = None
         self._engine_fingerprint = None
 

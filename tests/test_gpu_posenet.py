@@ -67,6 +67,27 @@ def test_forward_matches_oracle(posenet, cuda_device, B, T):
     assert torch.equal(y[:, :22], cond[:, :22])  # trajectory channels are a verbatim copy of the condition
 
 
+@pytest.mark.parametrize("prec,tol", [(_lib.PRECISION_F16X2, TOL), (_lib.PRECISION_TF32X3, TOL), (_lib.PRECISION_TF32, 5e-2)])
+def test_every_precision_mode_against_oracle(posenet, cuda_device, prec, tol):
+    """fp16 hi/lo (default) and TF32 hi/lo are both fp32-grade; single-pass TF32 is the documented fast mode.
+    Includes large-magnitude inputs (|x| ~ 500, the range guided sampling reaches) for the fp16 range."""
+    m, sd = posenet
+    B, T = 3, 60
+    gen = torch.Generator().manual_seed(4242)
+    x = torch.randn(B, 294, 1, T, generator=gen)
+    x[1] *= 500.0
+    cond = synthetic.posenet_batch(B, T, 9)['cond']
+    ts = torch.tensor([0, 500, 999])
+    ref = posenet_oracle.posenet_forward(sd, x.double(), cond.double(), ts).float()
+    m.precision = prec
+    try:
+        y = m({'x_t': x.to(cuda_device), 'cond': cond.to(cuda_device)}, ts.to(cuda_device)).cpu()
+    finally:
+        m.precision = None
+    assert m._engine.precision == prec
+    assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()) / 10.0)
+
+
 def test_forward_noncontiguous_inputs_and_cond_updates(posenet, cuda_device):
     """The driver builds cond by permute(0,2,1).unsqueeze(-2) (non-contiguous) and edits it in place between rounds."""
     m, sd = posenet

@@ -19,14 +19,14 @@ for (B, T) in [(2, 16), (3, 143), (2, 144)]:
     ts = torch.randint(0, 1000, (B,), generator=g)
     ref = posenet_oracle.posenet_forward(sd, x, cond, ts)
     ref64 = posenet_oracle.posenet_forward(sd, x.double(), cond.double(), ts)
-    for prec, name in ((3, 'tf32x3'), (1, 'tf32')):
+    for prec, name in ((3, 'tf32x3'), (2, 'f16x2'), (1, 'tf32')):
         m.precision = prec
         out = m({'x_t': x.to(dev), 'cond': cond.to(dev)}, ts.to(dev)).cpu()
         print(f"B{B} T{T} {name}: max|gpu-oracle32| {float((out-ref).abs().max()):.3e}  max|gpu-oracle64| {float((out-ref64).abs().max()):.3e}  "
               f"max|oracle32-oracle64| {float((ref-ref64).abs().max()):.3e}  max|ref| {float(ref.abs().max()):.2f}", flush=True)
 
 # timing of the forward at the bench shape
-for prec, name in ((3, 'tf32x3'), (1, 'tf32')):
+for prec, name in ((3, 'tf32x3'), (2, 'f16x2'), (1, 'tf32')):
     m.precision = prec
     B, T = 32, 144
     x = torch.randn(B, 294, 1, T, device=dev)
@@ -43,7 +43,7 @@ for prec, name in ((3, 'tf32x3'), (1, 'tf32')):
 
 # a short sampling loop through the public API
 args = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
-m.precision = 3
+m.precision = None
 d = diffusion.create_gaussian_diffusion(args, diffusion, diffusion.SpacedDiffusionPoseNet, 1000, '', dev)
 B, T = 32, 144
 batch = {'cond': synthetic.posenet_batch(B, T, 7, device=dev)['cond']}

@@ -155,6 +155,102 @@ static void case_linear(int M, int N, int K, int block_n, int act, bool with_res
   cudaFree(sA.hi), cudaFree(sA.lo), cudaFree(sW.hi), cudaFree(sW.lo);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Case 1b: the same linear layer on fp16 hi/lo pairs (kKindF16): A split as is, W scaled by a power of two into the
+// middle of the fp16 range, accumulator scaled back in the epilogue.  a_scale stresses the fp16 range of the activations.
+// ------------------------------------------------------------------------------------------------
+#include <cuda_fp16.h>
+static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with_res, bool timing, float a_scale) {
+  const int BK = gemm_block_k(kKindF16);
+  const int ldk = (K + 7) / 8 * 8;  // 16-byte row pitch in halves
+  const int Kp = (K + BK - 1) / BK * BK;
+  const int Np = (N + block_n - 1) / block_n * block_n;
+  std::vector<float> A((size_t)M * ldk, 0.f), W((size_t)Np * Kp, 0.f), b(N), R((size_t)M * N);
+  float wmax = 0.f;
+  {
+    std::normal_distribution<float> d(0.f, 1.f);
+    for (int m = 0; m < M; ++m)
+      for (int k = 0; k < K; ++k) A[(size_t)m * ldk + k] = d(rng) * a_scale;
+    const float ws = 1.0f / std::sqrt((float)K);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) wmax = std::fmax(wmax, std::fabs(W[(size_t)n * Kp + k] = d(rng) * ws));
+  }
+  fill(b);
+  fill(R);
+  int e2;
+  std::frexp(wmax, &e2);                       // wmax = f * 2^e2, f in [0.5, 1)
+  const float w_scale = std::ldexp(1.0f, 14 - e2);  // scaled max in [2^13, 2^14)
+  float *dA = dev(A), *dW = dev(W), *db = dev(b), *dR = dev(R);
+  __half *Ah, *Al, *Wh, *Wl, *dCh, *dCl;
+  CK(cudaMalloc(&Ah, A.size() * 2));
+  CK(cudaMalloc(&Al, A.size() * 2));
+  CK(cudaMalloc(&Wh, W.size() * 2));
+  CK(cudaMalloc(&Wl, W.size() * 2));
+  CK(cudaMalloc(&dCh, (size_t)M * N * 2));
+  CK(cudaMalloc(&dCl, (size_t)M * N * 2));
+  CK(launch_split_f16(dA, Ah, Al, (int64_t)A.size(), 1.0f, 0));
+  CK(launch_split_f16(dW, Wh, Wl, (int64_t)W.size(), w_scale, 0));
+  float* dC = dev_zero((size_t)M * N);
+  GemmParams p{};
+  if (make_tmap_2d(&p.a_hi[0], Ah, M, K, ldk, kGemmBlockM, 1, kKindF16) || make_tmap_2d(&p.a_lo[0], Al, M, K, ldk, kGemmBlockM, 1, kKindF16) ||
+      make_tmap_2d(&p.b_hi, Wh, Np, Kp, Kp, block_n, 1, kKindF16) || make_tmap_2d(&p.b_lo, Wl, Np, Kp, Kp, block_n, 1, kKindF16)) {
+    printf("tensor map encode failed (f16)\n");
+    exit(2);
+  }
+  p.num_segs = 1, p.seg_kblocks[0] = Kp / BK, p.seg_row_mul[0] = 1;
+  p.bias = db, p.residual = with_res ? dR : nullptr, p.ldr = N;
+  p.out = dC, p.ldo = N;
+  const bool split_out = (N % 4) == 0;
+  if (split_out) p.out_hi = dCh, p.out_lo = dCl, p.lds = N;
+  p.act = act, p.M = M, p.N = N, p.out_row_mul = 1;
+  p.acc_scale = 1.0f / w_scale;
+  CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+  CK(cudaDeviceSynchronize());
+  auto C = host(dC, (size_t)M * N);
+  std::vector<__half> Ch((size_t)M * N), Cl((size_t)M * N);
+  CK(cudaMemcpy(Ch.data(), dCh, Ch.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(Cl.data(), dCl, Cl.size() * 2, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0, maxsplit = 0;
+  const int step = M > 600 ? 7 : 1;
+  for (int m = 0; m < M; m += step)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * ldk + k] * (double)W[(size_t)n * Kp + k];
+      acc += b[n];
+      if (act == kActGelu) acc = 0.5 * acc * (1.0 + std::erf(acc / std::sqrt(2.0)));
+      if (act == kActSilu) acc = acc / (1.0 + std::exp(-acc));
+      if (with_res) acc += R[(size_t)m * N + n];
+      const double got = C[(size_t)m * N + n];
+      maxerr = std::fmax(maxerr, std::fabs(got - acc));
+      maxref = std::fmax(maxref, std::fabs(acc));
+      if (split_out)
+        maxsplit = std::fmax(maxsplit, std::fabs((double)__half2float(Ch[(size_t)m * N + n]) +
+                                                 (double)__half2float(Cl[(size_t)m * N + n]) - got));
+    }
+  char name[160];
+  snprintf(name, sizeof name, "f16x2 linear M%d N%d K%d bn%d act%d a_scale %g", M, N, K, block_n, act, a_scale);
+  report(name, maxerr, maxref, 2e-5 * std::fmax(1.0f, a_scale));
+  report("  hi+lo == out (fp16 split epilogue)", maxsplit, maxref, 4e-6 * std::fmax(1.0, maxref));
+  if (timing) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 5; ++i) CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+    CK(cudaEventRecord(e0));
+    const int iters = 50;
+    for (int i = 0; i < iters; ++i) CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1000.0 / iters;
+    printf("    timing: %.2f us/launch  -> %.1f TFLOP/s algorithmic (fp16 hi/lo, 3 tensor passes)\n", us, 2.0 * M * N * K / us * 1e-6);
+  }
+  cudaFree(dA), cudaFree(dW), cudaFree(db), cudaFree(dR), cudaFree(dC), cudaFree(dCh), cudaFree(dCl);
+  cudaFree(Ah), cudaFree(Al), cudaFree(Wh), cudaFree(Wl);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Case 2: Conv1d over a padded-clip channels-last layout, as TrajNet uses it.
 //   x: [B, Tp_in, Cin] with the first T_in rows of each clip real, others zero.
@@ -346,6 +442,17 @@ int main() {
   case_linear(4640, 512, 1024, 128, kActNone, true, true);   // FFN2 + residual
   case_linear(4640, 512, 294, 128, kActNone, true, false);   // input embedding (K tail via TMA OOB)
   case_linear(4640, 272, 512, 96, kActNone, false, true);    // output head (N tail)
+  // the same shapes on fp16 hi/lo operands
+  case_linear_f16(4640, 512, 512, 128, kActNone, true, true, 1.0f);
+  case_linear_f16(4640, 1536, 512, 128, kActNone, false, true, 1.0f);
+  case_linear_f16(4640, 1024, 512, 128, kActGelu, false, true, 1.0f);
+  case_linear_f16(4640, 512, 1024, 128, kActNone, true, true, 1.0f);
+  case_linear_f16(4640, 512, 294, 128, kActNone, true, false, 1.0f);
+  case_linear_f16(4640, 272, 512, 96, kActNone, false, true, 1.0f);
+  case_linear_f16(300, 512, 512, 128, kActNone, false, false, 300.0f);   // large activations
+  case_linear_f16(300, 512, 512, 128, kActNone, false, false, 1e-3f);    // lo halves all subnormal
+  case_linear_f16(77, 64, 40, 64, kActSilu, false, false, 1.0f);
+  case_linear_f16(33, 13, 32, 32, kActNone, false, false, 1.0f);
   // small / ragged
   case_linear(300, 272, 294, 96, kActNone, false, false);
   case_linear(77, 64, 40, 64, kActSilu, false, false);
