@@ -185,10 +185,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // Multi-head self-attention, fp32 on CUDA cores (v1): one CTA per (clip, head); K and V of the head live in shared
 // memory, each warp owns query rows round-robin.  softmax(Q K^T / sqrt(dh)) V with no mask (posenet.py:63-69).
 // qkv: [B*S, 3*D] fp32 (Q | K | V, head h at columns h*DH).  ctx hi/lo: [B*S, D].
+// f16 != 0: Q/K/V arrive as fp16 hi/lo pairs (qkv = hi plane, qkv_lo = lo plane; value = hi + lo) and ctx is written as
+// fp16 pairs.
+__device__ __forceinline__ float4 load_qkv4(const float* qkv, const float* qkv_lo, int f16, int64_t idx) {
+  if (!f16) return *reinterpret_cast<const float4*>(qkv + idx);
+  const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(qkv) + idx);
+  const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(qkv_lo) + idx);
+  const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
+  const __half2 l0 = *reinterpret_cast<const __half2*>(&l.x), l1 = *reinterpret_cast<const __half2*>(&l.y);
+  return make_float4(__low2float(h0) + __low2float(l0), __high2float(h0) + __high2float(l0),
+                     __low2float(h1) + __low2float(l1), __high2float(h1) + __high2float(l1));
+}
 template <int DH>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx_hi,
-                                                        float* __restrict__ ctx_lo, int S, int D, int H, float scale,
-                                                        int f16) {
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_lo,
+                                                        float* __restrict__ ctx_hi, float* __restrict__ ctx_lo, int S,
+                                                        int D, int H, float scale, int f16) {
   constexpr int KP = DH + 4;  // padded K row: conflict-free float4 reads with one key per lane
   constexpr int NW = 8;
   extern __shared__ float sm[];
@@ -204,9 +215,9 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 
   for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
     const int s = i / (DH / 4), c = i % (DH / 4);
-    const float* row = qkv + (base + s) * ld + h * DH + c * 4;
-    const float4 k = *reinterpret_cast<const float4*>(row + D);
-    const float4 v = *reinterpret_cast<const float4*>(row + 2 * D);
+    const int64_t row = (base + s) * ld + h * DH + c * 4;
+    const float4 k = load_qkv4(qkv, qkv_lo, f16, row + D);
+    const float4 v = load_qkv4(qkv, qkv_lo, f16, row + 2 * D);
     *reinterpret_cast<float4*>(Ks + s * KP + c * 4) = k;
     *reinterpret_cast<float4*>(Vs + s * DH + c * 4) = v;
   }
@@ -217,8 +228,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   float* q = Qs + warp * DH;
   float* p = Ps + warp * Sp;
   for (int i = warp; i < S; i += NW) {
-    const float* qrow = qkv + (base + i) * ld + h * DH;
-    for (int c = lane; c < DH / 4; c += 32) *reinterpret_cast<float4*>(q + c * 4) = *reinterpret_cast<const float4*>(qrow + c * 4);
+    const int64_t qrow = (base + i) * ld + h * DH;
+    for (int c = lane; c < DH / 4; c += 32) *reinterpret_cast<float4*>(q + c * 4) = load_qkv4(qkv, qkv_lo, f16, qrow + c * 4);
     __syncwarp();
     float sc[MAXJ];
 #pragma unroll
@@ -528,6 +539,214 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(c
   }
 }
 
+// ---- tensor-core attention on fp16 hi/lo pairs (ROHM_PRECISION_F16X2) ------------------------------------------------
+// Same decomposition (one CTA per (clip, head), warp w owns query rows [16w, 16w+16), logits / softmax / P in
+// registers), but Q, K and V arrive already split into fp16 hi/lo halves by the QKV GEMM's epilogue, so the kernel does
+// no operand conversion at all: K and V fragments come out of shared memory with ldmatrix (.trans for V), Q fragments
+// straight from global/L2, and every product is an mma.sync m16n8k16 -- half the instruction count of the m16n8k8 TF32
+// kernel for the same 3-product error compensation.  The S accumulator pair of two adjacent 8-key tiles is exactly the A
+// fragment of one 16-key P V step (the usual register reuse), so P is split into hi/lo halves once, in registers.
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(smem_row)));
+}
+// (x, y) -> packed half2 hi and lo words (x in the low half)
+__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __half hx, lx, hy, ly;
+  ptx::split_f16(x, hx, lx);
+  ptx::split_f16(y, hy, ly);
+  hi = static_cast<uint32_t>(__half_as_ushort(hx)) | (static_cast<uint32_t>(__half_as_ushort(hy)) << 16);
+  lo = static_cast<uint32_t>(__half_as_ushort(lx)) | (static_cast<uint32_t>(__half_as_ushort(ly)) << 16);
+}
+
+template <int DH>
+__host__ __device__ constexpr int attn_f16_pitch() { return DH + 8; }  // halves; 16-byte row chunks land on distinct bank groups
+
+// qkv_hi / qkv_lo: [B*S, 3*D] fp16 (Q | K | V, head h at columns h*DH); ctx_hi / ctx_lo: [B*S, D] fp16.
+template <int DH, int NK>  // NK = number of 16-key tiles (keys padded to 16*NK); one warp per 16 query rows, <= NK warps
+__global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half* __restrict__ qkv_hi,
+                                                                   const __half* __restrict__ qkv_lo,
+                                                                   __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo,
+                                                                   int S, int D, int H, float scale) {
+  static_assert(NK % 2 == 0, "key tiles are processed in groups of four 8-key tiles");
+  constexpr int P = attn_f16_pitch<DH>();
+  constexpr int NT = 2 * NK;  // 8-key tiles
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __half* Kh = reinterpret_cast<__half*>(sm_raw);  // [16*NK][P]
+  __half* Kl = Kh + 16 * NK * P;
+  __half* Vh = Kl + 16 * NK * P;
+  __half* Vl = Vh + 16 * NK * P;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t base = static_cast<int64_t>(b) * S;
+  const int ld = 3 * D;
+
+  for (int i = threadIdx.x; i < 16 * NK * (DH / 8); i += blockDim.x) {
+    const int s = i / (DH / 8), c = i % (DH / 8);
+    uint4 kh = make_uint4(0u, 0u, 0u, 0u), kl = kh, vh = kh, vl = kh;
+    if (s < S) {
+      const int64_t o = (base + s) * ld + h * DH + c * 8;
+      kh = *reinterpret_cast<const uint4*>(qkv_hi + o + D);
+      kl = *reinterpret_cast<const uint4*>(qkv_lo + o + D);
+      vh = *reinterpret_cast<const uint4*>(qkv_hi + o + 2 * D);
+      vl = *reinterpret_cast<const uint4*>(qkv_lo + o + 2 * D);
+    }
+    *reinterpret_cast<uint4*>(Kh + s * P + c * 8) = kh;
+    *reinterpret_cast<uint4*>(Kl + s * P + c * 8) = kl;
+    *reinterpret_cast<uint4*>(Vh + s * P + c * 8) = vh;
+    *reinterpret_cast<uint4*>(Vl + s * P + c * 8) = vl;
+  }
+
+  const int r0 = warp * 16;
+  const int rowA = min(r0 + g, S - 1), rowB = min(r0 + g + 8, S - 1);
+  const __half* qAh = qkv_hi + (base + rowA) * ld + h * DH + 2 * t;
+  const __half* qBh = qkv_hi + (base + rowB) * ld + h * DH + 2 * t;
+  const __half* qAl = qkv_lo + (base + rowA) * ld + h * DH + 2 * t;
+  const __half* qBl = qkv_lo + (base + rowB) * ld + h * DH + 2 * t;
+  auto ldq = [](const __half* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); };
+  __syncthreads();
+
+  // ---- S = Q K^T ----
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+  // ldmatrix row address of this lane: matrices 0/1 = K_hi columns +0 / +8, matrices 2/3 = K_lo columns +0 / +8
+  const int lm = lane >> 3, lr = lane & 7;
+  const __half* kbase = (lm < 2 ? Kh : Kl) + lr * P + (lm & 1) * 8;
+  uint32_t qh[4] = {ldq(qAh), ldq(qBh), ldq(qAh + 8), ldq(qBh + 8)};
+  uint32_t ql[4] = {ldq(qAl), ldq(qBl), ldq(qAl + 8), ldq(qBl + 8)};
+#pragma unroll 1
+  for (int k = 0; k < DH / 16; ++k) {
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ah[i] = qh[i], al[i] = ql[i];
+    if (k + 1 < DH / 16) {  // prefetch the next Q fragment (each value is used once, straight from L2)
+      const int o = 16 * (k + 1);
+      qh[0] = ldq(qAh + o), qh[1] = ldq(qBh + o), qh[2] = ldq(qAh + o + 8), qh[3] = ldq(qBh + o + 8);
+      ql[0] = ldq(qAl + o), ql[1] = ldq(qBl + o), ql[2] = ldq(qAl + o + 8), ql[3] = ldq(qBl + o + 8);
+    }
+    const __half* kp = kbase + 16 * k;
+    // groups of 4 key tiles, products issued pass-major so that consecutive MMAs hit different accumulators
+#pragma unroll
+    for (int j0 = 0; j0 < NT; j0 += 4) {
+      uint32_t bf[4][4];  // {b0_hi, b1_hi, b0_lo, b1_lo}
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ldmatrix_x4(bf[u], kp + (j0 + u) * 8 * P);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mma_f16_16x8x16(acc[j0 + u], al, bf[u][0], bf[u][1]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mma_f16_16x8x16(acc[j0 + u], ah, bf[u][2], bf[u][3]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mma_f16_16x8x16(acc[j0 + u], ah, bf[u][0], bf[u][1]);
+    }
+  }
+
+  // ---- softmax over keys (rows rowA: elements [0],[1]; rowB: [2],[3]; columns 8j + 2t + {0,1}) ----
+  float mxA = -INFINITY, mxB = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = (8 * j + 2 * t + e) < S;
+      acc[j][e] = ok ? acc[j][e] * scale : -INFINITY;
+      acc[j][2 + e] = ok ? acc[j][2 + e] * scale : -INFINITY;
+      mxA = fmaxf(mxA, acc[j][e]);
+      mxB = fmaxf(mxB, acc[j][2 + e]);
+    }
+  }
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+  float sumA = 0.0f, sumB = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      acc[j][e] = expf(acc[j][e] - mxA);  // exp(-inf) = 0 for padded keys
+      acc[j][2 + e] = expf(acc[j][2 + e] - mxB);
+      sumA += acc[j][e];
+      sumB += acc[j][2 + e];
+    }
+  }
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
+  const float invA = 1.0f / sumA, invB = 1.0f / sumB;
+
+  // ---- P as A fragments of the 16-key steps: {rowA keys 2t..+1, rowB keys 2t..+1, rowA keys 8+2t.., rowB keys 8+2t..} ----
+  uint32_t ph[NK][4], pl[NK][4];
+#pragma unroll
+  for (int jj = 0; jj < NK; ++jj) {
+    split_f16x2(acc[2 * jj][0] * invA, acc[2 * jj][1] * invA, ph[jj][0], pl[jj][0]);
+    split_f16x2(acc[2 * jj][2] * invB, acc[2 * jj][3] * invB, ph[jj][1], pl[jj][1]);
+    split_f16x2(acc[2 * jj + 1][0] * invA, acc[2 * jj + 1][1] * invA, ph[jj][2], pl[jj][2]);
+    split_f16x2(acc[2 * jj + 1][2] * invB, acc[2 * jj + 1][3] * invB, ph[jj][3], pl[jj][3]);
+  }
+
+  // ---- O = P V ----  four 8-wide output tiles per (rolled) iteration
+  const bool okA = (r0 + g) < S, okB = (r0 + g + 8) < S;
+  const int64_t oA = (base + r0 + g) * D + h * DH + 2 * t;
+  const int64_t oB = oA + static_cast<int64_t>(8) * D;
+  // ldmatrix.trans row address: matrices 0/1 = V_hi keys +0 / +8, matrices 2/3 = V_lo keys +0 / +8
+  const __half* vbase = (lm < 2 ? Vh : Vl) + ((lm & 1) * 8 + lr) * P;
+  constexpr int NU = 4;
+#pragma unroll 1
+  for (int n0 = 0; n0 < DH / 8; n0 += NU) {
+    float o[NU][4], os[NU][4];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.0f;
+      os[u][0] = os[u][1] = os[u][2] = os[u][3] = 0.0f;
+    }
+    const __half* vp = vbase + 8 * n0;
+#pragma unroll
+    for (int jj = 0; jj < NK; ++jj) {
+      uint32_t bf[NU][4];  // {b0_hi, b1_hi, b0_lo, b1_lo}
+#pragma unroll
+      for (int u = 0; u < NU; ++u) ldmatrix_x4_trans(bf[u], vp + 16 * jj * P + 8 * u);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(os[u], pl[jj], bf[u][0], bf[u][1]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(o[u], ph[jj], bf[u][0], bf[u][1]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(os[u], ph[jj], bf[u][2], bf[u][3]);
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int n = n0 + u;
+      uint32_t hA, lA, hB, lB;
+      split_f16x2(o[u][0] + os[u][0], o[u][1] + os[u][1], hA, lA);
+      split_f16x2(o[u][2] + os[u][2], o[u][3] + os[u][3], hB, lB);
+      if (okA) {
+        *reinterpret_cast<uint32_t*>(ctx_hi + oA + 8 * n) = hA;
+        *reinterpret_cast<uint32_t*>(ctx_lo + oA + 8 * n) = lA;
+      }
+      if (okB) {
+        *reinterpret_cast<uint32_t*>(ctx_hi + oB + 8 * n) = hB;
+        *reinterpret_cast<uint32_t*>(ctx_lo + oB + 8 * n) = lB;
+      }
+    }
+  }
+}
+
+template <int DH>
+size_t attention_f16_smem_bytes(int NK) { return sizeof(__half) * 4 * 16 * NK * attn_f16_pitch<DH>(); }
+
 size_t attention_mma_smem_bytes(int NT) { return sizeof(float) * 2 * 8 * NT * kAttnPitch; }
 
 size_t attention_smem_bytes(int S, int DH) {
@@ -775,6 +994,16 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
   return cudaGetLastError();
 }
 
+template <int DH, int NK>
+static cudaError_t launch_attention_f16(rohm_posenet* pn, int B, int S, float scale, cudaStream_t st) {
+  const int warps = (S + 15) / 16;
+  const __half* qh = reinterpret_cast<const __half*>(pn->QKV);
+  const __half* ql = qh + pn->max_rows * 3 * pn->D;
+  attention_f16_kernel<DH, NK><<<B * pn->H, 32 * warps, attention_f16_smem_bytes<DH>(NK), st>>>(
+      qh, ql, reinterpret_cast<__half*>(pn->CTXh), reinterpret_cast<__half*>(pn->CTXl), S, pn->D, pn->H, scale);
+  return cudaGetLastError();
+}
+
 static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   const int dh = pn->D / pn->H;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
@@ -782,8 +1011,21 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   const int nt = (S + 7) / 8;
   cudaError_t e = cudaSuccess;
   bool done = true;
+  const bool f16 = pn->kind == kKindF16;
+  const float* qkv_lo = reinterpret_cast<const float*>(reinterpret_cast<const __half*>(pn->QKV) + pn->max_rows * 3 * pn->D);
+  if (f16) {
+    const int nk = (S + 15) / 16;
+    if (dh == 128 && nk <= 2) e = launch_attention_f16<128, 2>(pn, B, S, scale, st);
+    else if (dh == 128 && nk <= 4) e = launch_attention_f16<128, 4>(pn, B, S, scale, st);
+    else if (dh == 128 && nk <= 6) e = launch_attention_f16<128, 6>(pn, B, S, scale, st);
+    else if (dh == 128 && nk <= 8) e = launch_attention_f16<128, 8>(pn, B, S, scale, st);
+    else if (dh == 128 && nk <= 10) e = launch_attention_f16<128, 10>(pn, B, S, scale, st);
+    else if (dh == 64 && nk <= 4) e = launch_attention_f16<64, 4>(pn, B, S, scale, st);
+    else if (dh == 64 && nk <= 10) e = launch_attention_f16<64, 10>(pn, B, S, scale, st);
+    else done = false;
+  }
   // tensor-core path: S <= 160 tokens (register budget of the S/P fragment); wider clips use the SIMT kernel
-  if (dh == 128 && nt <= 4) e = launch_attention_mma<128, 4>(pn, B, S, scale, st);
+  else if (dh == 128 && nt <= 4) e = launch_attention_mma<128, 4>(pn, B, S, scale, st);
   else if (dh == 128 && nt <= 8) e = launch_attention_mma<128, 8>(pn, B, S, scale, st);
   else if (dh == 128 && nt <= 12) e = launch_attention_mma<128, 12>(pn, B, S, scale, st);
   else if (dh == 128 && nt <= 16) e = launch_attention_mma<128, 16>(pn, B, S, scale, st);
@@ -794,11 +1036,11 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   if (!done) {
     const size_t smem = attention_smem_bytes(S, dh);
     if (dh == 128) {
-      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
-                                                          pn->kind == kKindF16 ? 1 : 0);
+      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
+                                                          f16 ? 1 : 0);
     } else if (dh == 64) {
-      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
-                                                         pn->kind == kKindF16 ? 1 : 0);
+      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
+                                                         f16 ? 1 : 0);
     } else {
       return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
     }
@@ -940,7 +1182,13 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
     TRY(setup_linear(pn, &pn->g_qkv[l], pn->Xh, pn->Xl, R, D, D, d.qkv, d.qkv_b));
-    pn->g_qkv[l].out = pn->QKV, pn->g_qkv[l].ldo = 3 * D;
+    if (pn->kind == kKindF16) {  // Q | K | V as fp16 hi/lo planes sharing the fp32 buffer's footprint
+      pn->g_qkv[l].out_hi = pn->QKV;
+      pn->g_qkv[l].out_lo = reinterpret_cast<__half*>(pn->QKV) + R * 3 * D;
+      pn->g_qkv[l].lds = 3 * D;
+    } else {
+      pn->g_qkv[l].out = pn->QKV, pn->g_qkv[l].ldo = 3 * D;
+    }
     TRY(setup_linear(pn, &pn->g_proj[l], pn->CTXh, pn->CTXl, R, D, D, d.proj, d.proj_b));
     pn->g_proj[l].residual = pn->X, pn->g_proj[l].ldr = D;
     pn->g_proj[l].out = pn->Y, pn->g_proj[l].ldo = D;
@@ -967,6 +1215,16 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     set_mma(attention_mma_kernel<128, 20>, 20);
     set_mma(attention_mma_kernel<64, 8>, 8);
     set_mma(attention_mma_kernel<64, 20>, 20);
+    auto set_f16 = [&](auto kern, size_t bytes) {
+      if (ea == cudaSuccess) ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    };
+    set_f16(attention_f16_kernel<128, 2>, attention_f16_smem_bytes<128>(2));
+    set_f16(attention_f16_kernel<128, 4>, attention_f16_smem_bytes<128>(4));
+    set_f16(attention_f16_kernel<128, 6>, attention_f16_smem_bytes<128>(6));
+    set_f16(attention_f16_kernel<128, 8>, attention_f16_smem_bytes<128>(8));
+    set_f16(attention_f16_kernel<128, 10>, attention_f16_smem_bytes<128>(10));
+    set_f16(attention_f16_kernel<64, 4>, attention_f16_smem_bytes<64>(4));
+    set_f16(attention_f16_kernel<64, 10>, attention_f16_smem_bytes<64>(10));
     if (ea != cudaSuccess) {
       delete pn;
       return fail(ctx, ROHM_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ea));
