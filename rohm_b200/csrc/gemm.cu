@@ -68,6 +68,7 @@ struct EpiParams {
   void* out_lo;
   double* gn_stats;
   float acc_scale;
+  int tma_store;
   int ldr, ldo, lds, act, M, N, out_row_mul, out_row_add, clip_rows, clip_valid, gn_groups, gn_group_size;
 };
 
@@ -133,6 +134,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     epi_s.clip_valid = p.clip_valid, epi_s.gn_stats = p.gn_stats, epi_s.gn_groups = p.gn_groups;
     epi_s.gn_group_size = p.gn_group_size;
     epi_s.acc_scale = p.acc_scale == 0.0f ? 1.0f : p.acc_scale;
+    epi_s.tma_store = p.tma_store;
+    if (p.tma_store) {
+      ptx::prefetch_tmap(&p.st_out);
+      ptx::prefetch_tmap(&p.st_hi);
+      ptx::prefetch_tmap(&p.st_lo);
+    }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -140,7 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
 
   if (threadIdx.x == 0) stamp(p, 1);
-  // Everything above overlaps the tail of the previous kernel under programmatic dependent launch.
+  // Programmatic dependent launch: let the next kernel of the chain become resident as soon as SMs free up (its
+  // prologue then overlaps this kernel's tail; it blocks in its own griddepcontrol.wait until this grid has completed
+  // and flushed), then order everything below after the previous kernel.
+  ptx::pdl_launch_dependents();
   ptx::pdl_wait_prior_grid();
 
   if (warp_idx == 0) {
@@ -270,6 +280,66 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (PASSES == 3) ptx::tmem_ld_32x32(taddr + BLOCK_N, raw2);
         const int nb = n0 + c0;
         const bool full = vec_ok && (nb + 32 <= e.N);
+        if (LEAN && e.tma_store && full && (m0 + q * 32 + 32 <= e.M)) {
+          // ---- TMA-store path: row-per-thread registers -> swizzled staging tile -> bulk tensor store ----
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (PASSES == 3) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
+          }
+          if (KIND == kKindF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= e.acc_scale;
+          }
+          if (e.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[acc_stage][c0 + j]);
+              v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+            }
+          }
+          if (EPI == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+          }
+          // the previous chunk's bulk store must have finished reading the staging tile
+          if (lane == 0) ptx::bulk_wait_read_all();
+          __syncwarp();
+          uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+          if (e.out != nullptr) {
+            // 32 rows x 128 B, SWIZZLE_128B: 16-byte chunk c of row r lives at slot c ^ (r & 7)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(tb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          } else {
+            // two planes of 32 rows x 64 B (hi at +0, lo at +2048), SWIZZLE_64B: chunk c of row r at slot c ^ ((r >> 1) & 3)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint2 h0, l0, h1, l1;
+              ptx::split_f16x4(make_float4(v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3]), h0, l0);
+              ptx::split_f16x4(make_float4(v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]), h1, l1);
+              const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(tb + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+              *reinterpret_cast<uint4*>(tb + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (e.out != nullptr) {
+              ptx::tma_store_2d(&p.st_out, tb, nb, m0 + q * 32);
+            } else {
+              ptx::tma_store_2d(&p.st_hi, tb, nb, m0 + q * 32);
+              ptx::tma_store_2d(&p.st_lo, tb + 2048, nb, m0 + q * 32);
+            }
+            ptx::bulk_commit();
+          }
+          continue;
+        }
         // residual in the transposed (coalesced) layout: loads are issued before waiting on TMEM
         float4 res[8];
         const bool use_res = e.residual != nullptr && full;
@@ -369,6 +439,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 9);
         if (full) {
           // ---- coalesced path through the staging tile ----
+          if (LEAN && e.tma_store) {  // an earlier chunk's bulk store may still be reading the tile
+            if (lane == 0) ptx::bulk_wait_read_all();
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = v[j];  // column ^ row: conflict-free both ways
           __syncwarp();
@@ -439,10 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 6);
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
     }
+    if (lane == 0) ptx::bulk_wait_all();  // outstanding TMA stores of this warp (no-op without the TMA-store path)
   }
 
   __syncthreads();
-  ptx::pdl_launch_dependents();
   if (warp_idx == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -547,6 +621,45 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return static_cast<int>(r);
+}
+
+static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half) {
+  auto fn = get_encode_fn();
+  if (fn == nullptr) return -1;
+  const int eb = half ? 2 : 4;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * eb};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estride[2] = {1u, 1u};
+  return static_cast<int>(fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                             const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+}
+
+int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind) {
+  p->tma_store = 0;
+  const bool plain = p->residual == nullptr && p->out_row_mul == 1 && p->out_row_add == 0 && p->clip_rows == 0 &&
+                     p->gn_stats == nullptr && (p->act == kActNone || p->act == kActGelu);
+  const bool only_out = p->out != nullptr && p->out_hi == nullptr;
+  const bool only_pair = p->out == nullptr && p->out_hi != nullptr && kind == kKindF16;
+  if (!plain || !(only_out || only_pair)) return 0;
+  int rc = 0;
+  if (only_out) {
+    if ((p->ldo * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15) != 0) return 0;
+    rc = encode_store_map(&p->st_out, p->out, rows_total, p->N, p->ldo, false);
+    p->st_hi = p->st_out, p->st_lo = p->st_out;
+  } else {
+    if ((p->lds * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out_hi) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(p->out_lo) & 15) != 0)
+      return 0;
+    rc = encode_store_map(&p->st_hi, p->out_hi, rows_total, p->N, p->lds, true);
+    if (rc == 0) rc = encode_store_map(&p->st_lo, p->out_lo, rows_total, p->N, p->lds, true);
+    p->st_out = p->st_hi;
+  }
+  if (rc != 0) return rc;
+  p->tma_store = 1;
+  return 0;
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int m_rows, int n_cols, int block_n, int passes, cudaStream_t stream,

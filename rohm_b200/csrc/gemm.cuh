@@ -81,6 +81,14 @@ struct alignas(64) GemmParams {
   double* gn_stats;  // [num_clips, gn_groups, 2] or nullptr
   int gn_groups;
   int gn_group_size;  // channels per group
+  // TMA-store epilogue (gemm_enable_tma_store): 32 x 32 output chunks go registers -> swizzled shared-memory tile ->
+  // cp.async.bulk.tensor store.  Eligible launches: no residual, identity output row map, no clip mask / GroupNorm
+  // statistics, and either only `out` (fp32) or only an fp16 out_hi/out_lo pair.  Chunks on a ragged M or N edge still
+  // take the per-thread path.
+  CUtensorMap st_out;
+  CUtensorMap st_hi;
+  CUtensorMap st_lo;
+  int tma_store;
   // optional: CTA 0 records %globaltimer at 8 milestones (developer instrumentation, see tools/gemm_selftest)
   unsigned long long* debug_ts;
   // filled in by launch_gemm: extent of the tile grid
@@ -94,6 +102,11 @@ struct alignas(64) GemmParams {
 // Returns 0 on success, a CUresult otherwise.
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int row_elem_stride = 1, int kind = kKindTf32);
+
+// Builds the store tensor maps of p for its current out / out_hi / out_lo pointers (rows_total = row capacity of those
+// buffers) and sets p.tma_store when the launch is eligible (see GemmParams); otherwise clears it.  Returns 0 or a
+// CUresult.
+int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind);
 
 // Launches the tile kernel.  block_n in {32, 64, 96, 128}; passes in {1, 3} (kKindF16: 3 only).
 // grid = ceil(M_tiles) x ceil(N_tiles) where M_tiles covers `m_rows` GEMM rows.

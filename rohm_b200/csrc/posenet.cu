@@ -10,6 +10,8 @@
 //         X --GEMM(+bias,GELU)--> H --GEMM(+bias+X)--> Y --LN--> X }
 //   X --GEMM--> OUT_tok --unpack(+copy cond[:, :traj])--> out [B,C,1,T]
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "common.h"
@@ -120,25 +122,36 @@ __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restr
   if (i < n) out[i] = a[i] + b[i];
 }
 
-// LayerNorm over the last dim (eps 1e-5), one warp per row; writes fp32 and the TF32 hi/lo pair.
+// LayerNorm over the last dim (eps 1e-5) of in + res (res = the residual stream, may be null), one warp per row; writes
+// fp32 and the hi/lo pair.  `out` may alias `res` (each row is read completely before it is written).
 template <int D>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float* __restrict__ out,
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* res,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* out,
                                                         float* __restrict__ out_hi, float* __restrict__ out_lo,
                                                         int rows, int f16) {
   static_assert(D % 128 == 0, "row must be a multiple of 32 lanes x float4");
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
   constexpr int V = D / 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* src = reinterpret_cast<const float4*>(in + static_cast<int64_t>(row) * D);
   float4 x[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) x[i] = src[lane + 32 * i];
+  if (res != nullptr) {  // x = sublayer output + residual stream (torch: x + sa_block(x) / x + ff_block(x))
+    const float4* rs = reinterpret_cast<const float4*>(res + static_cast<int64_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 r = rs[lane + 32 * i];
+      x[i].x += r.x, x[i].y += r.y, x[i].z += r.z, x[i].w += r.w;
+    }
+  }
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    x[i] = src[lane + 32 * i];
-    sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-  }
+  for (int i = 0; i < V; ++i) sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
   const float mean = sum * (1.0f / D);
@@ -202,6 +215,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
                                                         int D, int H, float scale, int f16) {
   constexpr int KP = DH + 4;  // padded K row: conflict-free float4 reads with one key per lane
   constexpr int NW = 8;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
   extern __shared__ float sm[];
   float* Ks = sm;                      // [S][KP]
   float* Vs = Ks + S * KP;             // [S][DH]
@@ -355,6 +370,8 @@ __global__ void __launch_bounds__(32 * ((NT + 1) / 2), 1) attention_mma_kernel(c
                                                                           float* __restrict__ ctx_lo, int S, int D,
                                                                           int H, float scale, int f16) {
   extern __shared__ float sm[];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
   float* Ks = sm;                          // [8*NT][kAttnPitch]
   float* Vs = Ks + 8 * NT * kAttnPitch;    // [8*NT][kAttnPitch]
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -594,29 +611,35 @@ __global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half*
   const int64_t base = static_cast<int64_t>(b) * S;
   const int ld = 3 * D;
 
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+  // K and V of the head -> shared memory with 16-byte cp.async (all copies of a thread in flight at once; key rows past
+  // the clip are zero-filled through the src-size operand)
+  const int64_t lo_off = qkv_lo - qkv_hi;  // element distance between the hi and lo planes
   for (int i = threadIdx.x; i < 16 * NK * (DH / 8); i += blockDim.x) {
     const int s = i / (DH / 8), c = i % (DH / 8);
-    uint4 kh = make_uint4(0u, 0u, 0u, 0u), kl = kh, vh = kh, vl = kh;
-    if (s < S) {
-      const int64_t o = (base + s) * ld + h * DH + c * 8;
-      kh = *reinterpret_cast<const uint4*>(qkv_hi + o + D);
-      kl = *reinterpret_cast<const uint4*>(qkv_lo + o + D);
-      vh = *reinterpret_cast<const uint4*>(qkv_hi + o + 2 * D);
-      vl = *reinterpret_cast<const uint4*>(qkv_lo + o + 2 * D);
-    }
-    *reinterpret_cast<uint4*>(Kh + s * P + c * 8) = kh;
-    *reinterpret_cast<uint4*>(Kl + s * P + c * 8) = kl;
-    *reinterpret_cast<uint4*>(Vh + s * P + c * 8) = vh;
-    *reinterpret_cast<uint4*>(Vl + s * P + c * 8) = vl;
+    const int sc = s < S ? s : S - 1;
+    const uint32_t nbytes = s < S ? 16u : 0u;
+    const __half* src = qkv_hi + (base + sc) * ld + h * DH + c * 8 + D;
+    const uint32_t dst = ptx::smem_u32(Kh + s * P + c * 8);
+    constexpr uint32_t plane = 16 * NK * P * 2;  // bytes between Kh, Kl, Vh, Vl
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + plane), "l"(src + lo_off), "r"(nbytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 2 * plane), "l"(src + D), "r"(nbytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 3 * plane), "l"(src + D + lo_off), "r"(nbytes)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   const int r0 = warp * 16;
   const int rowA = min(r0 + g, S - 1), rowB = min(r0 + g + 8, S - 1);
-  const __half* qAh = qkv_hi + (base + rowA) * ld + h * DH + 2 * t;
-  const __half* qBh = qkv_hi + (base + rowB) * ld + h * DH + 2 * t;
-  const __half* qAl = qkv_lo + (base + rowA) * ld + h * DH + 2 * t;
-  const __half* qBl = qkv_lo + (base + rowB) * ld + h * DH + 2 * t;
+  // Q fragments come straight from global/L2: one base pointer, the other three addresses are fixed element offsets
+  const __half* qA = qkv_hi + (base + rowA) * ld + h * DH + 2 * t;
+  const int dB = (rowB - rowA) * ld;
   auto ldq = [](const __half* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); };
+  uint32_t qh[4] = {ldq(qA), ldq(qA + dB), ldq(qA + 8), ldq(qA + dB + 8)};
+  uint32_t ql[4] = {ldq(qA + lo_off), ldq(qA + lo_off + dB), ldq(qA + lo_off + 8), ldq(qA + lo_off + dB + 8)};
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- S = Q K^T ----
@@ -626,17 +649,16 @@ __global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half*
   // ldmatrix row address of this lane: matrices 0/1 = K_hi columns +0 / +8, matrices 2/3 = K_lo columns +0 / +8
   const int lm = lane >> 3, lr = lane & 7;
   const __half* kbase = (lm < 2 ? Kh : Kl) + lr * P + (lm & 1) * 8;
-  uint32_t qh[4] = {ldq(qAh), ldq(qBh), ldq(qAh + 8), ldq(qBh + 8)};
-  uint32_t ql[4] = {ldq(qAl), ldq(qBl), ldq(qAl + 8), ldq(qBl + 8)};
 #pragma unroll 1
   for (int k = 0; k < DH / 16; ++k) {
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) ah[i] = qh[i], al[i] = ql[i];
     if (k + 1 < DH / 16) {  // prefetch the next Q fragment (each value is used once, straight from L2)
-      const int o = 16 * (k + 1);
-      qh[0] = ldq(qAh + o), qh[1] = ldq(qBh + o), qh[2] = ldq(qAh + o + 8), qh[3] = ldq(qBh + o + 8);
-      ql[0] = ldq(qAl + o), ql[1] = ldq(qBl + o), ql[2] = ldq(qAl + o + 8), ql[3] = ldq(qBl + o + 8);
+      const __half* q = qA + 16 * (k + 1);
+      qh[0] = ldq(q), qh[1] = ldq(q + dB), qh[2] = ldq(q + 8), qh[3] = ldq(q + dB + 8);
+      q += lo_off;
+      ql[0] = ldq(q), ql[1] = ldq(q + dB), ql[2] = ldq(q + 8), ql[3] = ldq(q + dB + 8);
     }
     const __half* kp = kbase + 16 * k;
     // groups of 4 key tiles, products issued pass-major so that consecutive MMAs hit different accumulators
@@ -707,12 +729,9 @@ __global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half*
   constexpr int NU = 4;
 #pragma unroll 1
   for (int n0 = 0; n0 < DH / 8; n0 += NU) {
-    float o[NU][4], os[NU][4];
+    float o[NU][4];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.0f;
-      os[u][0] = os[u][1] = os[u][2] = os[u][3] = 0.0f;
-    }
+    for (int u = 0; u < NU; ++u) o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.0f;
     const __half* vp = vbase + 8 * n0;
 #pragma unroll
     for (int jj = 0; jj < NK; ++jj) {
@@ -720,18 +739,18 @@ __global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half*
 #pragma unroll
       for (int u = 0; u < NU; ++u) ldmatrix_x4_trans(bf[u], vp + 16 * jj * P + 8 * u);
 #pragma unroll
-      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(os[u], pl[jj], bf[u][0], bf[u][1]);
+      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(o[u], pl[jj], bf[u][0], bf[u][1]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(o[u], ph[jj], bf[u][2], bf[u][3]);
 #pragma unroll
       for (int u = 0; u < NU; ++u) mma_f16_16x8x16(o[u], ph[jj], bf[u][0], bf[u][1]);
-#pragma unroll
-      for (int u = 0; u < NU; ++u) mma_f16_16x8x16(os[u], ph[jj], bf[u][2], bf[u][3]);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int n = n0 + u;
       uint32_t hA, lA, hB, lB;
-      split_f16x2(o[u][0] + os[u][0], o[u][1] + os[u][1], hA, lA);
-      split_f16x2(o[u][2] + os[u][2], o[u][3] + os[u][3], hB, lB);
+      split_f16x2(o[u][0], o[u][1], hA, lA);
+      split_f16x2(o[u][2], o[u][3], hB, lB);
       if (okA) {
         *reinterpret_cast<uint32_t*>(ctx_hi + oA + 8 * n) = hA;
         *reinterpret_cast<uint32_t*>(ctx_lo + oA + 8 * n) = lA;
@@ -800,6 +819,7 @@ struct rohm_posenet {
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
   bool use_pdl = true;
+  bool use_tma_store = true;  // ROHM_B200_TMA_STORE=0 falls back to the per-thread store epilogue (developer switch)
   cudaStream_t capture_stream = nullptr;
   ~rohm_posenet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -955,21 +975,40 @@ static int run_gemm(rohm_posenet* pn, GemmParams& g, const PackedWeight& w, int 
   return ROHM_OK;
 }
 
-template <int D>
-static void launch_ln(const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
-               cudaStream_t st, int f16) {
-  layernorm_kernel<D><<<(rows + 7) / 8, 256, 0, st>>>(in, g, b, out, oh, ol, rows, f16);
+// Kernel launch with the programmatic-dependent-launch attribute (the kernel must call griddepcontrol.wait before it
+// touches memory, which every kernel launched through here does).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-static int run_ln(rohm_posenet* pn, const float* in, const float* g, const float* b, float* out, float* oh, float* ol, int rows,
-           cudaStream_t st) {
+template <int D>
+static void launch_ln(const float* in, const float* res, const float* g, const float* b, float* out, float* oh, float* ol,
+               int rows, cudaStream_t st, int f16, bool pdl) {
+  launch_chain(layernorm_kernel<D>, dim3((rows + 7) / 8), dim3(256), 0, st, pdl, in, res, g, b, out, oh, ol, rows, f16);
+}
+
+static int run_ln(rohm_posenet* pn, const float* in, const float* res, const float* g, const float* b, float* out, float* oh,
+           float* ol, int rows, cudaStream_t st) {
   prof_begin(pn, kCatLayerNorm, st);
   const int f16 = pn->kind == kKindF16 ? 1 : 0;
+  const bool pdl = pn->use_pdl && !pn->profiling;
   switch (pn->D) {
-    case 128: launch_ln<128>(in, g, b, out, oh, ol, rows, st, f16); break;
-    case 256: launch_ln<256>(in, g, b, out, oh, ol, rows, st, f16); break;
-    case 512: launch_ln<512>(in, g, b, out, oh, ol, rows, st, f16); break;
-    case 1024: launch_ln<1024>(in, g, b, out, oh, ol, rows, st, f16); break;
+    case 128: launch_ln<128>(in, res, g, b, out, oh, ol, rows, st, f16, pdl); break;
+    case 256: launch_ln<256>(in, res, g, b, out, oh, ol, rows, st, f16, pdl); break;
+    case 512: launch_ln<512>(in, res, g, b, out, oh, ol, rows, st, f16, pdl); break;
+    case 1024: launch_ln<1024>(in, res, g, b, out, oh, ol, rows, st, f16, pdl); break;
     default: return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported d_model %d for LayerNorm", pn->D);
   }
   prof_end(pn, st);
@@ -989,9 +1028,8 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
     attr_set = true;
   }
   const int warps = (S + 15) / 16;
-  kern<<<B * pn->H, 32 * warps, smem, st>>>(pn->QKV, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
-                                            pn->kind == kKindF16 ? 1 : 0);
-  return cudaGetLastError();
+  return launch_chain(kern, dim3(B * pn->H), dim3(32 * warps), smem, st, pn->use_pdl && !pn->profiling, pn->QKV, pn->CTXh,
+                      pn->CTXl, S, pn->D, pn->H, scale, pn->kind == kKindF16 ? 1 : 0);
 }
 
 template <int DH, int NK>
@@ -999,9 +1037,9 @@ static cudaError_t launch_attention_f16(rohm_posenet* pn, int B, int S, float sc
   const int warps = (S + 15) / 16;
   const __half* qh = reinterpret_cast<const __half*>(pn->QKV);
   const __half* ql = qh + pn->max_rows * 3 * pn->D;
-  attention_f16_kernel<DH, NK><<<B * pn->H, 32 * warps, attention_f16_smem_bytes<DH>(NK), st>>>(
-      qh, ql, reinterpret_cast<__half*>(pn->CTXh), reinterpret_cast<__half*>(pn->CTXl), S, pn->D, pn->H, scale);
-  return cudaGetLastError();
+  return launch_chain(attention_f16_kernel<DH, NK>, dim3(B * pn->H), dim3(32 * warps), attention_f16_smem_bytes<DH>(NK), st,
+                      pn->use_pdl && !pn->profiling, qh, ql, reinterpret_cast<__half*>(pn->CTXh),
+                      reinterpret_cast<__half*>(pn->CTXl), S, pn->D, pn->H, scale);
 }
 
 static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
@@ -1036,15 +1074,14 @@ static int run_attention(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   if (!done) {
     const size_t smem = attention_smem_bytes(S, dh);
     if (dh == 128) {
-      attention_kernel<128><<<B * pn->H, 256, smem, st>>>(pn->QKV, qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
-                                                          f16 ? 1 : 0);
+      e = launch_chain(attention_kernel<128>, dim3(B * pn->H), dim3(256), smem, st, pn->use_pdl && !pn->profiling, pn->QKV,
+                       qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale, f16 ? 1 : 0);
     } else if (dh == 64) {
-      attention_kernel<64><<<B * pn->H, 256, smem, st>>>(pn->QKV, qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale,
-                                                         f16 ? 1 : 0);
+      e = launch_chain(attention_kernel<64>, dim3(B * pn->H), dim3(256), smem, st, pn->use_pdl && !pn->profiling, pn->QKV,
+                       qkv_lo, pn->CTXh, pn->CTXl, S, pn->D, pn->H, scale, f16 ? 1 : 0);
     } else {
       return fail(pn->ctx, ROHM_ERR_INVALID, "unsupported head dim %d", dh);
     }
-    e = cudaGetLastError();
   }
   prof_end(pn, st);
   ROHM_CUDA(pn->ctx, e);
@@ -1107,6 +1144,7 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   pn->D = w->d_model, pn->F = w->ff_size, pn->L = w->num_layers, pn->H = w->num_heads;
   pn->C = w->in_feats, pn->Cout = w->out_feats, pn->traj = w->traj_feats, pn->pe_len = w->pe_len;
   pn->kind = precision == ROHM_PRECISION_F16X2 ? kKindF16 : kKindTf32;
+  if (const char* env = getenv("ROHM_B200_TMA_STORE")) pn->use_tma_store = env[0] != '0';
   pn->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
   pn->max_batch = max_batch, pn->max_frames = max_frames;
   pn->max_rows = static_cast<int64_t>(max_batch) * (max_frames + 1);
@@ -1189,15 +1227,27 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     } else {
       pn->g_qkv[l].out = pn->QKV, pn->g_qkv[l].ldo = 3 * D;
     }
+    // the residual adds (x + sa_block(x), x + ff_block(x)) happen in the LayerNorm kernel that follows, which leaves
+    // the GEMM epilogues free of global reads
     TRY(setup_linear(pn, &pn->g_proj[l], pn->CTXh, pn->CTXl, R, D, D, d.proj, d.proj_b));
-    pn->g_proj[l].residual = pn->X, pn->g_proj[l].ldr = D;
     pn->g_proj[l].out = pn->Y, pn->g_proj[l].ldo = D;
     TRY(setup_linear(pn, &pn->g_ff1[l], pn->Xh, pn->Xl, R, D, D, d.ff1, d.ff1_b));
     pn->g_ff1[l].act = kActGelu;
     pn->g_ff1[l].out_hi = pn->Hh, pn->g_ff1[l].out_lo = pn->Hl, pn->g_ff1[l].lds = F;
     TRY(setup_linear(pn, &pn->g_ff2[l], pn->Hh, pn->Hl, R, F, F, d.ff2, d.ff2_b));
-    pn->g_ff2[l].residual = pn->X, pn->g_ff2[l].ldr = D;
     pn->g_ff2[l].out = pn->Y, pn->g_ff2[l].ldo = D;
+    for (GemmParams* g : {&pn->g_qkv[l], &pn->g_proj[l], &pn->g_ff1[l], &pn->g_ff2[l]}) {
+      if (pn->use_tma_store && gemm_enable_tma_store(g, R, pn->kind) != 0) {
+        const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
+        delete pn;
+        return rc__;
+      }
+    }
+  }
+  if (pn->use_tma_store && gemm_enable_tma_store(&pn->g_out, R, pn->kind) != 0) {
+    const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
+    delete pn;
+    return rc__;
   }
 #undef TRY
 
@@ -1318,10 +1368,10 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
     if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_proj[l], d.proj, rows, st)) != ROHM_OK) return rc;
-    if ((rc = run_ln(pn, pn->Y, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_ln(pn, pn->Y, pn->X, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_ff1[l], d.ff1, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_ff2[l], d.ff2, rows, st)) != ROHM_OK) return rc;
-    if ((rc = run_ln(pn, pn->Y, d.n2_w, d.n2_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+    if ((rc = run_ln(pn, pn->Y, pn->X, d.n2_w, d.n2_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
   }
   if ((rc = run_gemm(pn, pn->g_out, pn->w_out, rows, st)) != ROHM_OK) return rc;
   dim3 grid_o((T + 31) / 32, (pn->Cout + 31) / 32, B);

@@ -161,7 +161,8 @@ static void case_linear(int M, int N, int K, int block_n, int act, bool with_res
 // middle of the fp16 range, accumulator scaled back in the epilogue.  a_scale stresses the fp16 range of the activations.
 // ------------------------------------------------------------------------------------------------
 #include <cuda_fp16.h>
-static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with_res, bool timing, float a_scale) {
+static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with_res, bool timing, float a_scale,
+                            int tma_mode = 0) {
   const int BK = gemm_block_k(kKindF16);
   const int ldk = (K + 7) / 8 * 8;  // 16-byte row pitch in halves
   const int Kp = (K + BK - 1) / BK * BK;
@@ -205,6 +206,16 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
   if (split_out) p.out_hi = dCh, p.out_lo = dCl, p.lds = N;
   p.act = act, p.M = M, p.N = N, p.out_row_mul = 1;
   p.acc_scale = 1.0f / w_scale;
+  if (tma_mode == 1) p.out_hi = nullptr, p.out_lo = nullptr;  // fp32 out through the TMA-store epilogue
+  if (tma_mode == 2) p.out = nullptr;                           // fp16 pair through the TMA-store epilogue
+  if (tma_mode != 0) {
+    if (gemm_enable_tma_store(&p, M, kKindF16) != 0 || !p.tma_store) {
+      printf("gemm_enable_tma_store refused an eligible launch\n");
+      exit(2);
+    }
+  }
+  CK(cudaMemset(dCh, 0, (size_t)M * N * 2));
+  CK(cudaMemset(dCl, 0, (size_t)M * N * 2));
   CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
   CK(cudaDeviceSynchronize());
   auto C = host(dC, (size_t)M * N);
@@ -221,17 +232,17 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
       if (act == kActGelu) acc = 0.5 * acc * (1.0 + std::erf(acc / std::sqrt(2.0)));
       if (act == kActSilu) acc = acc / (1.0 + std::exp(-acc));
       if (with_res) acc += R[(size_t)m * N + n];
-      const double got = C[(size_t)m * N + n];
+      const double pair = (double)__half2float(Ch[(size_t)m * N + n]) + (double)__half2float(Cl[(size_t)m * N + n]);
+      const double got = tma_mode == 2 ? pair : C[(size_t)m * N + n];
       maxerr = std::fmax(maxerr, std::fabs(got - acc));
       maxref = std::fmax(maxref, std::fabs(acc));
-      if (split_out)
-        maxsplit = std::fmax(maxsplit, std::fabs((double)__half2float(Ch[(size_t)m * N + n]) +
-                                                 (double)__half2float(Cl[(size_t)m * N + n]) - got));
+      if (split_out && tma_mode == 0) maxsplit = std::fmax(maxsplit, std::fabs(pair - got));
     }
   char name[160];
-  snprintf(name, sizeof name, "f16x2 linear M%d N%d K%d bn%d act%d a_scale %g", M, N, K, block_n, act, a_scale);
-  report(name, maxerr, maxref, 2e-5 * std::fmax(1.0f, a_scale));
-  report("  hi+lo == out (fp16 split epilogue)", maxsplit, maxref, 4e-6 * std::fmax(1.0, maxref));
+  snprintf(name, sizeof name, "f16x2 linear M%d N%d K%d bn%d act%d a_scale %g%s", M, N, K, block_n, act, a_scale,
+           tma_mode == 1 ? " [TMA store fp32]" : tma_mode == 2 ? " [TMA store fp16 pair]" : "");
+  report(name, maxerr, maxref, (tma_mode == 2 ? 2.5e-5 : 2e-5) * std::fmax(1.0f, a_scale));
+  if (tma_mode == 0) report("  hi+lo == out (fp16 split epilogue)", maxsplit, maxref, 4e-6 * std::fmax(1.0, maxref));
   if (timing) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -449,6 +460,14 @@ int main() {
   case_linear_f16(4640, 512, 1024, 128, kActNone, true, true, 1.0f);
   case_linear_f16(4640, 512, 294, 128, kActNone, true, false, 1.0f);
   case_linear_f16(4640, 272, 512, 96, kActNone, false, true, 1.0f);
+  // TMA-store epilogue (PoseNet QKV / out-proj / FFN shapes, plus ragged M and N edges that mix both store paths)
+  case_linear_f16(4640, 1536, 512, 128, kActNone, false, true, 1.0f, 2);
+  case_linear_f16(4640, 512, 512, 128, kActNone, false, true, 1.0f, 1);
+  case_linear_f16(4640, 1024, 512, 128, kActGelu, false, true, 1.0f, 2);
+  case_linear_f16(4640, 512, 1024, 128, kActNone, false, true, 1.0f, 1);
+  case_linear_f16(4640, 272, 512, 96, kActNone, false, true, 1.0f, 1);
+  case_linear_f16(145, 512, 512, 128, kActNone, false, false, 1.0f, 1);
+  case_linear_f16(333, 1536, 512, 128, kActNone, false, false, 1.0f, 2);
   case_linear_f16(300, 512, 512, 128, kActNone, false, false, 300.0f);   // large activations
   case_linear_f16(300, 512, 512, 128, kActNone, false, false, 1e-3f);    // lo halves all subnormal
   case_linear_f16(77, 64, 40, 64, kActSilu, false, false, 1.0f);
