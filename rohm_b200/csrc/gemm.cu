@@ -60,6 +60,36 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Exact (erf) GELU, nn.GELU's default, without erff's data-dependent branches: both erf branches are evaluated for every
+// element (|z| < 1: z + z P(z^2); otherwise sign(z) (1 - exp(Q(min(|z|, 4))))) and selected, so the 32 independent
+// elements of an epilogue chunk interleave freely.  Coefficients: tools/fit_gelu_erf.py (least squares on Chebyshev
+// nodes); max |error| of the whole GELU against float64 3.0e-7, the same as the fp32 erff formulation (4.5e-7).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float s = z * z;
+  float r = 7.680843555e-05f;
+  r = fmaf(r, s, -7.953780587e-04f);
+  r = fmaf(r, s, 5.181253888e-03f);
+  r = fmaf(r, s, -2.684955671e-02f);
+  r = fmaf(r, s, 1.128346100e-01f);
+  r = fmaf(r, s, -3.761261106e-01f);
+  r = fmaf(r, s, 1.283791661e-01f);
+  const float e_small = fmaf(r, z, z);
+  const float t = fminf(fabsf(z), 4.0f);
+  float q = -2.117903023e-05f;
+  q = fmaf(q, t, 4.352589312e-04f);
+  q = fmaf(q, t, -4.174096975e-03f);
+  q = fmaf(q, t, 2.512531355e-02f);
+  q = fmaf(q, t, -1.082860529e-01f);
+  q = fmaf(q, t, -6.333442330e-01f);
+  q = fmaf(q, t, -1.129514933e+00f);
+  q = fmaf(q, t, 1.744384354e-04f);
+  const float e_large = copysignf(1.0f - __expf(q), z);
+  const float e = fabsf(z) < 1.0f ? e_small : e_large;
+  const float h = 0.5f * x;
+  return fmaf(h, e, h);
+}
+
 struct EpiParams {
   const float* bias;
   const float* residual;
@@ -225,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         }
         ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
         if (tcount == 0) stamp(p, 4);
+        stamp(p, 12);  // last write wins: all MMAs of this CTA issued
       }
     }
   } else {
@@ -303,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           }
           if (EPI == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
           // the previous chunk's bulk store must have finished reading the staging tile
           if (lane == 0) ptx::bulk_wait_read_all();
@@ -378,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           if (EPI == 0) {
           } else if (EPI == 1 || e.act == kActGelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           } else if (e.act == kActSilu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + expf(-v[j]));
@@ -513,7 +544,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 6);
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
     }
+    if (warp_idx == 2 && lane == 0) stamp(p, 13);  // this warp's last tile drained
     if (lane == 0) ptx::bulk_wait_all();  // outstanding TMA stores of this warp (no-op without the TMA-store path)
+    if (warp_idx == 2 && lane == 0) stamp(p, 14);
   }
 
   __syncthreads();

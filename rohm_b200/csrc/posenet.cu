@@ -579,14 +579,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(ptx::smem_u32(smem_row)));
 }
-// (x, y) -> packed half2 hi and lo words (x in the low half)
-__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __half hx, lx, hy, ly;
-  ptx::split_f16(x, hx, lx);
-  ptx::split_f16(y, hy, ly);
-  hi = static_cast<uint32_t>(__half_as_ushort(hx)) | (static_cast<uint32_t>(__half_as_ushort(hy)) << 16);
-  lo = static_cast<uint32_t>(__half_as_ushort(lx)) | (static_cast<uint32_t>(__half_as_ushort(ly)) << 16);
-}
+using ptx::split_f16x2;
 
 template <int DH>
 __host__ __device__ constexpr int attn_f16_pitch() { return DH + 8; }  // halves; 16-byte row chunks land on distinct bank groups

@@ -257,6 +257,20 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double us = ms * 1000.0 / iters;
     printf("    timing: %.2f us/launch  -> %.1f TFLOP/s algorithmic (fp16 hi/lo, 3 tensor passes)\n", us, 2.0 * M * N * K / us * 1e-6);
+    unsigned long long* dts;
+    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
+    p.debug_ts = dts;
+    CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+    CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[16];
+    CK(cudaMemcpy(h, dts, sizeof h, cudaMemcpyDeviceToHost));
+    printf("    CTA0 timeline (ns): setup %llu | first_tma %llu | first_full %llu | tile0 mma issued %llu | tile0 epi start %llu | "
+           "tile0 epi done %llu | all mma issued %llu | last epi done %llu | stores done %llu | end %llu\n",
+           h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0],
+           h[7] - h[0]);
+    p.debug_ts = nullptr;
+    cudaFree(dts);
   }
   cudaFree(dA), cudaFree(dW), cudaFree(db), cudaFree(dR), cudaFree(dC), cudaFree(dCh), cudaFree(dCl);
   cudaFree(Ah), cudaFree(Al), cudaFree(Wh), cudaFree(Wl);
