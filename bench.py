@@ -136,7 +136,7 @@ def run_reference_arm(args):
         return
     cores = host_threads()
     _, sd = build_posenet(None)
-    n_clips, n_steps = B_PER_GPU, 4
+    n_clips, n_steps = B_PER_GPU, 16
     vals = []
     for _ in range(args.warmup):
         cpu_port_clips_per_s(sd, n_clips, 1, cores)
@@ -314,9 +314,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_threads()
-        v, dt = cpu_port_clips_per_s(sd, B, 8, cores)
+        v, dt = cpu_port_clips_per_s(sd, B, 64, cores)
         cpu_baseline = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                        "sample": f"{B} clips x 8 consecutive DDPM steps of the oracle port ({dt:.1f} s, {cores} of "
+                        "sample": f"{B} clips x 64 consecutive DDPM steps of the oracle port ({dt:.1f} s, {cores} of "
                                   f"{os.cpu_count()} host threads), extrapolated linearly to 1000 steps"}
 
     if rank == 0:

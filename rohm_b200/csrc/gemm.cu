@@ -99,6 +99,7 @@ struct EpiParams {
   double* gn_stats;
   float acc_scale;
   int tma_store;
+  int bias_per_row;
   int ldr, ldo, lds, act, M, N, out_row_mul, out_row_add, clip_rows, clip_valid, gn_groups, gn_group_size;
 };
 
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   // Epilogue parameters are copied from the (3 KB, tensor-map dominated) kernel parameter block into shared memory
   // once: reading them late from the constant bank cost ~0.7 us per first touch (measured with %globaltimer stamps).
   __shared__ EpiParams epi_s;
-  __shared__ float bias_s[Cfg::kAccStages][BLOCK_N];
+  __shared__ __align__(16) float bias_s[Cfg::kAccStages][BLOCK_N];
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     epi_s.gn_group_size = p.gn_group_size;
     epi_s.acc_scale = p.acc_scale == 0.0f ? 1.0f : p.acc_scale;
     epi_s.tma_store = p.tma_store;
+    epi_s.bias_per_row = p.bias_per_row;
     if (p.tma_store) {
       ptx::prefetch_tmap(&p.st_out);
       ptx::prefetch_tmap(&p.st_hi);
@@ -286,11 +288,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         row_real = (m - clip * e.clip_rows) < e.clip_valid;
       }
       const int64_t orow = static_cast<int64_t>(m) * e.out_row_mul + e.out_row_add;
+      const float bias_row = (e.bias != nullptr && e.bias_per_row && row_ok) ? __ldg(e.bias + m) : 0.0f;
 
       // stage this tile's bias slice (and warm the residual lines) while the MMA warp is still accumulating
       {
         const int i = (warp_idx - 2) * 32 + lane;
-        if (e.bias != nullptr && i < BLOCK_N) bias_s[acc_stage][i] = (n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.0f;
+        if (e.bias != nullptr && i < BLOCK_N)
+          bias_s[acc_stage][i] = (!e.bias_per_row && n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.0f;
         if (e.residual != nullptr && row_ok) {
           const float* r = e.residual + orow * e.ldr + n0 + half * 32;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
@@ -330,6 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[acc_stage][c0 + j]);
               v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+            }
+            if (e.bias_per_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += bias_row;
             }
           }
           if (EPI == 1) {
@@ -403,6 +411,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           if (e.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bias_s[acc_stage][c0 + j];  // smem broadcast; zero beyond N
+            if (e.bias_per_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += bias_row;
+            }
           }
           // one warp-uniform branch per activation: a per-element switch compiles to ~3000 predicated-off
           // instructions per chunk that are still issued when act == none (measured: 0.6 us per chunk)

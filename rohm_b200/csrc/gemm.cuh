@@ -59,7 +59,8 @@ struct alignas(64) GemmParams {
   int seg_row_mul[kMaxSegs];
   int num_segs;
   // ---- epilogue ----
-  const float* bias;      // [N] or nullptr
+  const float* bias;      // [N] (per output column) or, with bias_per_row, [M] (per output row); nullptr = none
+  int bias_per_row;       // transposed products (C^T = W A^T): the bias follows the rows
   const float* residual;  // fp32 [*, ldr] added after the activation, or nullptr
   int ldr;
   float* out;  // fp32 [*, ldo] or nullptr

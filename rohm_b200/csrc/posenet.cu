@@ -759,6 +759,238 @@ __global__ void __launch_bounds__(32 * NK, 1) attention_f16_kernel(const __half*
 template <int DH>
 size_t attention_f16_smem_bytes(int NK) { return sizeof(__half) * 4 * 16 * NK * attn_f16_pitch<DH>(); }
 
+// ---- tcgen05 attention (ROHM_PRECISION_F16X2, head dim 128, clips of at most 160 tokens) ----------------------------
+// One CTA per (clip, head).  Q and K of the head are TMA-loaded as K-major SWIZZLE_128B tiles straight from the Q|K GEMM's
+// fp16 hi/lo output; S = Q K^T runs as UMMA 128 x 160 x 16 (two 128-row query tiles, 160 padded keys) into TMEM; one
+// thread per query row reads its logits back (tcgen05.ld), does the softmax in registers (two passes over TMEM: max,
+// then exp / sum) and writes the unnormalised P row as fp16 hi/lo into a K-major shared-memory tile; O = P V^T^T runs as
+// UMMA 128 x 128 x 16 against V^T, which the projection GEMM produced directly in [feature][token] order (a transposed
+// product, see g_vt), so both operands of both products are K-major and no transposition happens in this kernel.
+// Every product is the 3-term hi/lo expansion; all three terms accumulate into one TMEM accumulator.
+// TMA needs a 16-byte aligned global start, but a clip's first token column in V^T (clip * S) is arbitrary: the V^T box
+// starts at the aligned-down column and the d = (clip * S) % 8 extra leading keys are compensated by writing P shifted by
+// d columns (its first d columns zero), which costs nothing because the shift is applied to the TMEM column address the
+// logits are re-read from.
+//   TMEM columns: [32,192) S tile 0 (reused by O tile 1), [192,352) S tile 1, [352,480) O tile 0.
+//   smem: phase 1  Q {hi,lo} x {dh 0-63, 64-127} 4 x 20 KB | K likewise 4 x 20 KB
+//         phase 2  V^T {hi,lo} x 3 key chunks 6 x 16 KB (over Q/K once S is complete) | P likewise 6 x 16 KB
+struct AttnTcParams {
+  CUtensorMap qk_hi, qk_lo;  // [rows, 2D] fp16, box {64, 160}
+  CUtensorMap vt_hi, vt_lo;  // [D, ldv] fp16, box {64, 128}
+  __half* ctx_hi;
+  __half* ctx_lo;
+  int S, D, H;
+  float scale;
+  int stages;  // developer bisection aid (ROHM_B200_ATTN_STAGES): 1 = loads only, 2 = + S MMAs, 3 = + softmax, 4 = everything
+};
+constexpr int kAtKeys = 160;                  // padded key count = UMMA N of the S product
+constexpr int kAtMaxTokens = kAtKeys - 7;     // room for the alignment shift of the P / V^T key axis
+constexpr uint32_t kAtColS = 32, kAtColO0 = 32 + 2 * kAtKeys;  // TMEM column map (see above)
+constexpr int kAtQKBuf = kAtKeys * 128;       // bytes of one {plane, dh-chunk} Q or K buffer (160 rows x 128 B)
+constexpr int kAtTile = 128 * 128;            // bytes of one {plane, key-chunk} V^T or P buffer (128 rows x 128 B)
+constexpr int kAtSmemBytes = 12 * kAtTile + 1024;
+constexpr int kAtThreads = 320;
+
+__global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t at_smem_raw[];
+  __shared__ uint64_t qk_full, v_full, s_full[2], p_ready[2], o_full[2];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t raw_addr = ptx::smem_u32(at_smem_raw);
+  uint8_t* smem = at_smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int S = p.S;
+  const int ntiles = S > 128 ? 2 : 1;
+  const int row0 = b * S;  // first token row of this clip
+  const bool full = p.stages == 4;
+  const bool run_v = p.stages == 3 || p.stages == 4 || p.stages == 6;
+  const bool run_p2 = p.stages == 3 || p.stages == 4 || p.stages == 5;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.qk_hi), ptx::prefetch_tmap(&p.qk_lo), ptx::prefetch_tmap(&p.vt_hi), ptx::prefetch_tmap(&p.vt_lo);
+    ptx::mbar_init(&qk_full, 1), ptx::mbar_init(&v_full, 1);
+    for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 4), ptx::mbar_init(&o_full[t], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc<512>(&tmem_base_smem);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+
+  uint8_t* const Qb = smem;                  // + (plane * 2 + kc) * kAtQKBuf
+  uint8_t* const Kb = smem + 4 * kAtQKBuf;
+  uint8_t* const Vb = smem;                  // + (plane * 3 + c) * kAtTile
+  uint8_t* const Pb = smem + 6 * kAtTile;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&qk_full, 8 * kAtQKBuf);
+      for (int pl = 0; pl < 2; ++pl) {
+        const CUtensorMap* m = pl == 0 ? &p.qk_hi : &p.qk_lo;
+        for (int kc = 0; kc < 2; ++kc) {
+          ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h * 128 + kc * 64, row0);
+        }
+      }
+      if (!run_v) goto done;
+      // V^T lands on top of Q / K: wait until every S MMA has read them
+      ptx::mbar_wait(&s_full[ntiles - 1], 0);
+      ptx::mbar_expect_tx(&v_full, 6 * kAtTile);
+      for (int pl = 0; pl < 2; ++pl) {
+        const CUtensorMap* m = pl == 0 ? &p.vt_hi : &p.vt_lo;
+        for (int c = 0; c < 3; ++c)
+          ptx::tma_load_2d(Vb + (pl * 3 + c) * kAtTile, m, &v_full, (row0 & ~7) + c * 64, h * 128);
+      }
+      if (!full) ptx::mbar_wait(&v_full, 0);
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::make_idesc(/*F16*/ 0, 128, kAtKeys);
+      constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128);
+      ptx::mbar_wait(&qk_full, 0);
+      ptx::tc_fence_after_sync();
+      if (p.stages < 2) goto done;
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t acc = tmem_base + kAtColS + static_cast<uint32_t>(t * kAtKeys);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 16 head-dim columns per instruction
+          const int kc = ks >> 2;
+          const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
+          const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Qb + (0 * 2 + kc) * kAtQKBuf + t * kAtTile)) + ko;
+          const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Qb + (1 * 2 + kc) * kAtQKBuf + t * kAtTile)) + ko;
+          const uint64_t b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Kb + (0 * 2 + kc) * kAtQKBuf)) + ko;
+          const uint64_t b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Kb + (1 * 2 + kc) * kAtQKBuf)) + ko;
+          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc_s, ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc_s, 1u);
+          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc_s, 1u);
+        }
+        ptx::mma_commit(&s_full[t]);
+      }
+      if (!full) goto done;
+      ptx::mbar_wait(&v_full, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        ptx::mbar_wait(&p_ready[t], 0);
+        ptx::tc_fence_after_sync();
+        const uint32_t acc = tmem_base + (t == 0 ? kAtColO0 : kAtColS);
+#pragma unroll
+        for (int ks = 0; ks < kAtKeys / 16; ++ks) {  // 16 keys per instruction
+          const int c = ks >> 2;
+          const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
+          const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (0 * 3 + c) * kAtTile)) + ko;
+          const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (1 * 3 + c) * kAtTile)) + ko;
+          const uint64_t b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (0 * 3 + c) * kAtTile)) + ko;
+          const uint64_t b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (1 * 3 + c) * kAtTile)) + ko;
+          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc_o, ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc_o, 1u);
+          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc_o, 1u);
+        }
+        ptx::mma_commit(&o_full[t]);
+      }
+    }
+  } else {
+    // ===================== softmax + output warps: tile t = (warp_idx - 2) / 4, one thread per query row =====================
+    const int t = (warp_idx - 2) >> 2;
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int grow = t * 128 + row;  // token index inside the clip
+    const bool valid = grow < S;
+    if (t < ntiles && p.stages >= 2) {
+      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
+      const int d = row0 & 7;  // key-axis shift of P and V^T
+      ptx::mbar_wait(&s_full[t], 0);
+      ptx::tc_fence_after_sync();
+      // pass 1: row maximum over the real keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kAtKeys / 32; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(s_addr + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < S) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      }
+      if (!run_p2) goto done;
+      if (!full && t == 1) goto done;
+      // the P tile overlaps K (tile 0: every S MMA must be done) / is still being read by the O MMAs of tile 0 (tile 1)
+      if (t == 0) ptx::mbar_wait(&s_full[ntiles - 1], 0);
+      else ptx::mbar_wait(&o_full[0], 0);
+      // pass 2: p = exp(scale (s - max)), row sum, fp16 hi/lo -> K-major SWIZZLE_128B tile (16-byte unit u of row r at
+      // slot u ^ (r & 7)).  P column k holds key k - d: the logits are re-read from TMEM column k - d.
+      float sum = 0.0f;
+      const float ms = mx * p.scale;
+#pragma unroll 1
+      for (int c = 0; c < kAtKeys / 32; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(s_addr + c * 32 - d, raw);
+        ptx::tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c * 32 + j - d;
+          const float e = __expf(fmaf(__uint_as_float(raw[j]), p.scale, -ms));
+          pv[j] = (key >= 0 && key < S) ? e : 0.0f;
+          sum += pv[j];
+        }
+        if (valid) {
+          uint8_t* ph = Pb + (0 * 3 + (c >> 1)) * kAtTile + row * 128;
+          uint8_t* pl = Pb + (1 * 3 + (c >> 1)) * kAtTile + row * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ptx::split_f16x2(pv[8 * u + 2 * i], pv[8 * u + 2 * i + 1], hw[i], lw[i]);
+            const int slot = (((c & 1) * 4 + u) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(ph + slot) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(pl + slot) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
+      if (!full) goto done;
+
+      // output: O / sum -> fp16 hi/lo rows of ctx
+      ptx::mbar_wait(&o_full[t], 0);
+      ptx::tc_fence_after_sync();
+      const float inv = 1.0f / sum;
+      const uint32_t o_addr = tmem_base + lane_addr + (t == 0 ? kAtColO0 : kAtColS);
+      const int64_t o = (static_cast<int64_t>(row0) + grow) * p.D + h * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(o_addr + c * 32, raw);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              ptx::split_f16x2(__uint_as_float(raw[8 * u + 2 * i]) * inv, __uint_as_float(raw[8 * u + 2 * i + 1]) * inv, hw[i],
+                               lw[i]);
+            *reinterpret_cast<uint4*>(p.ctx_hi + o + c * 32 + u * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(p.ctx_lo + o + c * 32 + u * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+    }
+  }
+done:
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 size_t attention_mma_smem_bytes(int NT) { return sizeof(float) * 2 * 8 * NT * kAttnPitch; }
 
 size_t attention_smem_bytes(int S, int DH) {
@@ -773,6 +1005,7 @@ size_t attention_smem_bytes(int S, int DH) {
 // ------------------------------------------------------------------------------------------------------------
 struct PoseNetLayerDev {
   PackedWeight qkv, proj, ff1, ff2;
+  PackedWeight qk, v;  // tcgen05-attention path: Q|K projection and the V projection used as the A operand of V^T = W_v X^T
   float *qkv_b, *proj_b, *ff1_b, *ff2_b, *n1_w, *n1_b, *n2_w, *n2_b;
 };
 
@@ -813,6 +1046,13 @@ struct rohm_posenet {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_tma_store = true;  // ROHM_B200_TMA_STORE=0 falls back to the per-thread store epilogue (developer switch)
+  // tcgen05 attention (F16X2, head dim 128, <= 160 tokens per clip; ROHM_B200_TC_ATTENTION=0 disables): Q|K as fp16 planes
+  // [rows, 2D] inside the QKV buffer, V^T as fp16 planes [D, ldv]
+  bool tc_attention = false;
+  int ldv = 0;
+  __half *Vth = nullptr, *Vtl = nullptr;
+  AttnTcParams attn_tc{};
+  std::vector<GemmParams> g_qk, g_vt;
   cudaStream_t capture_stream = nullptr;
   ~rohm_posenet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -1025,6 +1265,31 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
                       pn->CTXl, S, pn->D, pn->H, scale, pn->kind == kKindF16 ? 1 : 0);
 }
 
+// V^T = W_v X^T: M = d_model output features, N = token rows of this call.
+static int run_gemm_vt(rohm_posenet* pn, GemmParams& g, int rows, cudaStream_t st) {
+  g.M = pn->D;
+  g.N = rows;
+  prof_begin(pn, kCatGemm, st);
+  ROHM_CUDA(pn->ctx, launch_gemm(g, pn->D, rows, 128, 3, st, pn->use_pdl && !pn->profiling, kKindF16));
+  prof_end(pn, st);
+  pn->launches++;
+  return ROHM_OK;
+}
+
+static int run_attention_tc(rohm_posenet* pn, int B, int S, cudaStream_t st) {
+  AttnTcParams prm = pn->attn_tc;
+  prm.S = S;
+  prm.stages = 4;
+  if (const char* env = getenv("ROHM_B200_ATTN_STAGES")) prm.stages = atoi(env);
+  prof_begin(pn, kCatAttention, st);
+  cudaError_t e = launch_chain(attention_tc_kernel, dim3(B * pn->H), dim3(kAtThreads), kAtSmemBytes, st,
+                               pn->use_pdl && !pn->profiling, prm);
+  prof_end(pn, st);
+  ROHM_CUDA(pn->ctx, e);
+  pn->launches++;
+  return ROHM_OK;
+}
+
 template <int DH, int NK>
 static cudaError_t launch_attention_f16(rohm_posenet* pn, int B, int S, float scale, cudaStream_t st) {
   const int warps = (S + 15) / 16;
@@ -1142,6 +1407,10 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   pn->max_batch = max_batch, pn->max_frames = max_frames;
   pn->max_rows = static_cast<int64_t>(max_batch) * (max_frames + 1);
   pn->Kin_p = static_cast<int>(round_up(pn->C, gemm_block_k(pn->kind)));
+  {
+    const char* env = getenv("ROHM_B200_TC_ATTENTION");
+    pn->tc_attention = pn->kind == kKindF16 && dh == 128 && (env == nullptr || env[0] != '0');
+  }
   const int D = pn->D, F = pn->F;
   const int64_t R = pn->max_rows;
 
@@ -1167,6 +1436,10 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     const rohm_posenet_layer& s = w->layers[l];
     PoseNetLayerDev& d = pn->layers[l];
     TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv, pn->kind));
+    if (pn->tc_attention) {
+      TRY(pack_weight(pn, s.in_proj_w, 2 * D, D, &d.qk, pn->kind));
+      TRY(pack_weight(pn, s.in_proj_w + static_cast<int64_t>(2) * D * D, D, D, &d.v, pn->kind));
+    }
     TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj, pn->kind));
     TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1, pn->kind));
     TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2, pn->kind));
@@ -1197,6 +1470,17 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     }
   }
 
+  if (pn->tc_attention) {
+    pn->ldv = static_cast<int>(round_up(R, 8));
+    pn->Vth = static_cast<__half*>(pn->pool.bytes(static_cast<int64_t>(D) * pn->ldv * 2));
+    pn->Vtl = static_cast<__half*>(pn->pool.bytes(static_cast<int64_t>(D) * pn->ldv * 2));
+    if (pn->Vth == nullptr || pn->Vtl == nullptr) {
+      const int rc = fail(ctx, ROHM_ERR_CUDA, "workspace alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
+      delete pn;
+      return rc;
+    }
+  }
+
   // GEMM descriptors.  Input embedding: residual = cond embedding + positional rows (set per set_cond).
   TRY(setup_linear(pn, &pn->g_in, pn->Ain_h, pn->Ain_l, R, pn->C, pn->Kin_p, pn->w_in, pn->in_b));
   pn->g_in.residual = pn->condpe, pn->g_in.ldr = D;
@@ -1210,6 +1494,7 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   TRY(setup_linear(pn, &pn->g_out, pn->Xh, pn->Xl, R, D, D, pn->w_out, pn->out_b));
   pn->g_out.out = pn->OUT, pn->g_out.ldo = pn->Cout;
   pn->g_qkv.resize(pn->L), pn->g_proj.resize(pn->L), pn->g_ff1.resize(pn->L), pn->g_ff2.resize(pn->L);
+  pn->g_qk.resize(pn->L), pn->g_vt.resize(pn->L);
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
     TRY(setup_linear(pn, &pn->g_qkv[l], pn->Xh, pn->Xl, R, D, D, d.qkv, d.qkv_b));
@@ -1229,6 +1514,38 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     pn->g_ff1[l].out_hi = pn->Hh, pn->g_ff1[l].out_lo = pn->Hl, pn->g_ff1[l].lds = F;
     TRY(setup_linear(pn, &pn->g_ff2[l], pn->Hh, pn->Hl, R, F, F, d.ff2, d.ff2_b));
     pn->g_ff2[l].out = pn->Y, pn->g_ff2[l].ldo = D;
+    if (pn->tc_attention) {
+      __half* qk_hi = reinterpret_cast<__half*>(pn->QKV);
+      __half* qk_lo = qk_hi + R * 2 * D;
+      // Q | K projection -> fp16 planes [rows, 2D]
+      TRY(setup_linear(pn, &pn->g_qk[l], pn->Xh, pn->Xl, R, D, D, d.qk, d.qkv_b));
+      pn->g_qk[l].out_hi = qk_hi, pn->g_qk[l].out_lo = qk_lo, pn->g_qk[l].lds = 2 * D;
+      // V^T = W_v X^T + b_v 1^T: the weight is the A (row) operand, the tokens are the B (column) operand, so the
+      // result comes out [feature][token] -- K-major for the P V product -- without a transposition pass
+      GemmParams& gv = pn->g_vt[l];
+      gv = GemmParams{};
+      int rcm = make_tmap_2d(&gv.a_hi[0], d.v.hi, d.v.Np, d.v.Kp, d.v.Kp, kGemmBlockM, 1, pn->kind);
+      rcm |= make_tmap_2d(&gv.a_lo[0], d.v.lo, d.v.Np, d.v.Kp, d.v.Kp, kGemmBlockM, 1, pn->kind);
+      rcm |= make_tmap_2d(&gv.b_hi, pn->Xh, R, D, D, 128, 1, pn->kind);
+      rcm |= make_tmap_2d(&gv.b_lo, pn->Xl, R, D, D, 128, 1, pn->kind);
+      if (rcm != 0) {
+        const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", rcm);
+        delete pn;
+        return rc__;
+      }
+      gv.num_segs = 1, gv.seg_kblocks[0] = d.v.Kp / gemm_block_k(pn->kind), gv.seg_row_mul[0] = 1;
+      gv.acc_scale = 1.0f / d.v.scale;
+      gv.bias = d.qkv_b + 2 * D, gv.bias_per_row = 1;
+      gv.out_hi = pn->Vth, gv.out_lo = pn->Vtl, gv.lds = pn->ldv;
+      gv.M = D, gv.N = pn->ldv, gv.out_row_mul = 1;
+      for (GemmParams* g : {&pn->g_qk[l], &pn->g_vt[l]}) {
+        if (pn->use_tma_store && gemm_enable_tma_store(g, g == &pn->g_vt[l] ? D : R, pn->kind) != 0) {
+          const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
+          delete pn;
+          return rc__;
+        }
+      }
+    }
     for (GemmParams* g : {&pn->g_qkv[l], &pn->g_proj[l], &pn->g_ff1[l], &pn->g_ff2[l]}) {
       if (pn->use_tma_store && gemm_enable_tma_store(g, R, pn->kind) != 0) {
         const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
@@ -1268,6 +1585,22 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     set_f16(attention_f16_kernel<128, 10>, attention_f16_smem_bytes<128>(10));
     set_f16(attention_f16_kernel<64, 4>, attention_f16_smem_bytes<64>(4));
     set_f16(attention_f16_kernel<64, 10>, attention_f16_smem_bytes<64>(10));
+    set_f16(attention_tc_kernel, kAtSmemBytes);
+    if (pn->tc_attention) {
+      __half* qk_hi = reinterpret_cast<__half*>(pn->QKV);
+      __half* qk_lo = qk_hi + R * 2 * D;
+      int rcm = make_tmap_2d(&pn->attn_tc.qk_hi, qk_hi, R, 2 * D, 2 * D, kAtKeys, 1, kKindF16);
+      rcm |= make_tmap_2d(&pn->attn_tc.qk_lo, qk_lo, R, 2 * D, 2 * D, kAtKeys, 1, kKindF16);
+      rcm |= make_tmap_2d(&pn->attn_tc.vt_hi, pn->Vth, D, R, pn->ldv, 128, 1, kKindF16);
+      rcm |= make_tmap_2d(&pn->attn_tc.vt_lo, pn->Vtl, D, R, pn->ldv, 128, 1, kKindF16);
+      if (rcm != 0) {
+        delete pn;
+        return fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed (%d)", rcm);
+      }
+      pn->attn_tc.ctx_hi = reinterpret_cast<__half*>(pn->CTXh), pn->attn_tc.ctx_lo = reinterpret_cast<__half*>(pn->CTXl);
+      pn->attn_tc.D = D, pn->attn_tc.H = pn->H;
+      pn->attn_tc.scale = 1.0f / sqrtf(static_cast<float>(dh));
+    }
     if (ea != cudaSuccess) {
       delete pn;
       return fail(ctx, ROHM_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ea));
@@ -1358,8 +1691,14 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
 
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
-    if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
-    if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
+    if (pn->tc_attention && S <= kAtMaxTokens) {
+      if ((rc = run_gemm(pn, pn->g_qk[l], d.qk, rows, st)) != ROHM_OK) return rc;
+      if ((rc = run_gemm_vt(pn, pn->g_vt[l], rows, st)) != ROHM_OK) return rc;
+      if ((rc = run_attention_tc(pn, B, S, st)) != ROHM_OK) return rc;
+    } else {
+      if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
+      if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
+    }
     if ((rc = run_gemm(pn, pn->g_proj[l], d.proj, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_ln(pn, pn->Y, pn->X, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_ff1[l], d.ff1, rows, st)) != ROHM_OK) return rc;
