@@ -682,6 +682,10 @@ static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, in
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
 }
 
+int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half) {
+  return encode_store_map(map, base, rows, cols, ld, half);
+}
+
 int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind) {
   p->tma_store = 0;
   const bool plain = p->residual == nullptr && p->out_row_mul == 1 && p->out_row_add == 0 && p->clip_rows == 0 &&

@@ -773,14 +773,17 @@ size_t attention_f16_smem_bytes(int NK) { return sizeof(__half) * 4 * 16 * NK * 
 // logits are re-read from.
 //   TMEM columns: [32,192) S tile 0 (reused by O tile 1), [192,352) S tile 1, [352,480) O tile 0.
 //   smem: phase 1  Q {hi,lo} x {dh 0-63, 64-127} 4 x 20 KB | K likewise 4 x 20 KB
-//         phase 2  V^T {hi,lo} x 3 key chunks 6 x 16 KB (over Q/K once S is complete) | P likewise 6 x 16 KB
+//         phase 2  P {hi,lo} x 3 key chunks 6 x 20 KB (160 rows each: both query tiles side by side, so neither waits for
+//                  the other) | V^T likewise 6 x 16 KB -- both land over Q / K once every S MMA has completed
 struct AttnTcParams {
   CUtensorMap qk_hi, qk_lo;  // [rows, 2D] fp16, box {64, 160}
   CUtensorMap vt_hi, vt_lo;  // [D, ldv] fp16, box {64, 128}
+  CUtensorMap st_hi, st_lo;  // ctx planes [rows, D] fp16, 32 x 32 store boxes
   __half* ctx_hi;
   __half* ctx_lo;
   int S, D, H;
   float scale;
+  unsigned long long* debug_ts;  // developer instrumentation: CTA 0 records %globaltimer at 12 milestones
   int stages;  // developer bisection aid (ROHM_B200_ATTN_STAGES): 1 = loads only, 2 = + S MMAs, 3 = + softmax, 4 = everything
 };
 constexpr int kAtKeys = 160;                  // padded key count = UMMA N of the S product
@@ -788,8 +791,16 @@ constexpr int kAtMaxTokens = kAtKeys - 7;     // room for the alignment shift of
 constexpr uint32_t kAtColS = 32, kAtColO0 = 32 + 2 * kAtKeys;  // TMEM column map (see above)
 constexpr int kAtQKBuf = kAtKeys * 128;       // bytes of one {plane, dh-chunk} Q or K buffer (160 rows x 128 B)
 constexpr int kAtTile = 128 * 128;            // bytes of one {plane, key-chunk} V^T or P buffer (128 rows x 128 B)
-constexpr int kAtSmemBytes = 12 * kAtTile + 1024;
+constexpr int kAtSmemBytes = 6 * kAtQKBuf + 6 * kAtTile + 1024;
 constexpr int kAtThreads = 320;
+
+__device__ __forceinline__ void at_stamp(const AttnTcParams& p, int slot) {
+  if (p.debug_ts != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.debug_ts[slot] = t;
+  }
+}
 
 __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t at_smem_raw[];
@@ -805,9 +816,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   const bool full = p.stages == 4;
   const bool run_v = p.stages == 3 || p.stages == 4 || p.stages == 6;
   const bool run_p2 = p.stages == 3 || p.stages == 4 || p.stages == 5;
+  if (threadIdx.x == 0) at_stamp(p, 0);
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.qk_hi), ptx::prefetch_tmap(&p.qk_lo), ptx::prefetch_tmap(&p.vt_hi), ptx::prefetch_tmap(&p.vt_lo);
+    ptx::prefetch_tmap(&p.st_hi), ptx::prefetch_tmap(&p.st_lo);
     ptx::mbar_init(&qk_full, 1), ptx::mbar_init(&v_full, 1);
     for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 4), ptx::mbar_init(&o_full[t], 1);
     ptx::fence_barrier_init();
@@ -819,11 +832,12 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   const uint32_t tmem_base = tmem_base_smem;
   ptx::pdl_launch_dependents();
   ptx::pdl_wait_prior_grid();
+  if (threadIdx.x == 0) at_stamp(p, 1);
 
   uint8_t* const Qb = smem;                  // + (plane * 2 + kc) * kAtQKBuf
   uint8_t* const Kb = smem + 4 * kAtQKBuf;
-  uint8_t* const Vb = smem;                  // + (plane * 3 + c) * kAtTile
-  uint8_t* const Pb = smem + 6 * kAtTile;
+  uint8_t* const Pb = smem;                  // + (plane * 3 + c) * kAtQKBuf, rows of tile t at + t * kAtTile
+  uint8_t* const Vb = smem + 6 * kAtQKBuf;   // + (plane * 3 + c) * kAtTile
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -851,6 +865,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       constexpr uint32_t idesc_s = ptx::make_idesc(/*F16*/ 0, 128, kAtKeys);
       constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128);
       ptx::mbar_wait(&qk_full, 0);
+      at_stamp(p, 2);
       ptx::tc_fence_after_sync();
       if (p.stages < 2) goto done;
       for (int t = 0; t < ntiles; ++t) {
@@ -871,16 +886,18 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       }
       if (!full) goto done;
       ptx::mbar_wait(&v_full, 0);
+      at_stamp(p, 4);
       for (int t = 0; t < ntiles; ++t) {
         ptx::mbar_wait(&p_ready[t], 0);
+        at_stamp(p, 6 + 3 * t);
         ptx::tc_fence_after_sync();
         const uint32_t acc = tmem_base + (t == 0 ? kAtColO0 : kAtColS);
 #pragma unroll
         for (int ks = 0; ks < kAtKeys / 16; ++ks) {  // 16 keys per instruction
           const int c = ks >> 2;
           const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
-          const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (0 * 3 + c) * kAtTile)) + ko;
-          const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (1 * 3 + c) * kAtTile)) + ko;
+          const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (0 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
+          const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (1 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
           const uint64_t b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (0 * 3 + c) * kAtTile)) + ko;
           const uint64_t b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (1 * 3 + c) * kAtTile)) + ko;
           ptx::mma_f16_ss(acc, a_lo, b_hi, idesc_o, ks > 0 ? 1u : 0u);
@@ -892,53 +909,74 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     }
   } else {
     // ===================== softmax + output warps: tile t = (warp_idx - 2) / 4, one thread per query row =====================
+    // TMEM loads are software-pipelined (the load of chunk c + 1 is in flight while chunk c is processed) and the row
+    // reductions keep four partial accumulators: with one warp per scheduler the phase is latency-, not issue-bound.
     const int t = (warp_idx - 2) >> 2;
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int grow = t * 128 + row;  // token index inside the clip
     const bool valid = grow < S;
-    if (t < ntiles && p.stages >= 2) {
+    if (t < ntiles && p.stages >= 2 && t * 128 + q * 32 >= S) {
+      // no real query row in this warp's 32 lanes (the tail of tile 1): nothing to compute, just release the MMA warp
+      if (run_p2 && lane == 0) ptx::mbar_arrive(&p_ready[t]);
+    } else if (t < ntiles && p.stages >= 2) {
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
       const int d = row0 & 7;  // key-axis shift of P and V^T
+      constexpr int NC = kAtKeys / 32;
+      uint32_t r0[32], r1[32];
       ptx::mbar_wait(&s_full[t], 0);
+      if (t == 0 && warp_idx == 2 && lane == 0) at_stamp(p, 3);
       ptx::tc_fence_after_sync();
       // pass 1: row maximum over the real keys
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kAtKeys / 32; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(s_addr + c * 32, raw);
-        ptx::tmem_ld_wait();
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      ptx::tmem_ld_32x32(s_addr, r0);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
+        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
+        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32, nxt);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < S) mx = fmaxf(mx, __uint_as_float(raw[j]));
+          if (c * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
+        if (c + 1 < NC) ptx::tmem_ld_wait();
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (!run_p2) goto done;
-      if (!full && t == 1) goto done;
-      // the P tile overlaps K (tile 0: every S MMA must be done) / is still being read by the O MMAs of tile 0 (tile 1)
-      if (t == 0) ptx::mbar_wait(&s_full[ntiles - 1], 0);
-      else ptx::mbar_wait(&o_full[0], 0);
-      // pass 2: p = exp(scale (s - max)), row sum, fp16 hi/lo -> K-major SWIZZLE_128B tile (16-byte unit u of row r at
+      if (t == 0 && warp_idx == 2 && lane == 0) at_stamp(p, 5);
+      // the P buffers overlap Q and K: every S MMA must have completed
+      ptx::mbar_wait(&s_full[ntiles - 1], 0);
+      // pass 2: p = exp(scale (s - max)), row sum, fp16 hi/lo -> K-major SWIZZLE_128B rows (16-byte unit u of row r at
       // slot u ^ (r & 7)).  P column k holds key k - d: the logits are re-read from TMEM column k - d.
-      float sum = 0.0f;
-      const float ms = mx * p.scale;
-#pragma unroll 1
-      for (int c = 0; c < kAtKeys / 32; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(s_addr + c * 32 - d, raw);
-        ptx::tmem_ld_wait();
+      float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float sc2 = p.scale * 1.4426950408889634f;  // exp(x) = 2^(x log2 e): one FFMA + one MUFU.EX2 per element
+      const float ms2 = mx * sc2;
+      ptx::tmem_ld_32x32(s_addr - d, r0);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
+        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
+        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32 - d, nxt);
         float pv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j - d;
-          const float e = __expf(fmaf(__uint_as_float(raw[j]), p.scale, -ms));
-          pv[j] = (key >= 0 && key < S) ? e : 0.0f;
-          sum += pv[j];
+          const float x = fmaf(__uint_as_float(cur[j]), sc2, -ms2);  // <= 0
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[j]) : "f"(x));
         }
+        if (c * 32 - d < 0 || c * 32 + 31 - d >= S) {  // only the first and the last chunks hold padded keys
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = c * 32 + j - d;
+            pv[j] = (key >= 0 && key < S) ? pv[j] : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum4[j & 3] += pv[j];
         if (valid) {
-          uint8_t* ph = Pb + (0 * 3 + (c >> 1)) * kAtTile + row * 128;
-          uint8_t* pl = Pb + (1 * 3 + (c >> 1)) * kAtTile + row * 128;
+          uint8_t* ph = Pb + (0 * 3 + (c >> 1)) * kAtQKBuf + grow * 128;
+          uint8_t* pl = Pb + (1 * 3 + (c >> 1)) * kAtQKBuf + grow * 128;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t hw[4], lw[4];
@@ -949,42 +987,76 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
             *reinterpret_cast<uint4*>(pl + slot) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
+        if (c + 1 < NC) ptx::tmem_ld_wait();
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
       if (!full) goto done;
 
-      // output: O / sum -> fp16 hi/lo rows of ctx
+      // output: O / sum -> fp16 hi/lo rows of ctx.  Full 32-row groups go through a SWIZZLE_64B staging tile (carved out
+      // of the first P buffer, whose tile-0 rows are dead once the O MMAs of tile 0 have completed) and TMA stores; a
+      // group that straddles the end of the clip writes its real rows directly.
       ptx::mbar_wait(&o_full[t], 0);
+      if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 7 + 3 * t);
       ptx::tc_fence_after_sync();
       const float inv = 1.0f / sum;
       const uint32_t o_addr = tmem_base + lane_addr + (t == 0 ? kAtColO0 : kAtColS);
       const int64_t o = (static_cast<int64_t>(row0) + grow) * p.D + h * 128;
-#pragma unroll 1
+      const bool group_full = t == 0 && (q * 32 + 32 <= S);  // tile 0 only: the staging area belongs to tile 0's P rows
+      if (group_full) ptx::mbar_wait(&o_full[0], 0);
+      ptx::tmem_ld_32x32(o_addr, r0);
+      ptx::tmem_ld_wait();
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(o_addr + c * 32, raw);
-        ptx::tmem_ld_wait();
-        if (valid) {
+        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
+        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
+        if (c + 1 < 4) ptx::tmem_ld_32x32(o_addr + (c + 1) * 32, nxt);
+        if (group_full) {
+          // chunk c stages in the tile-0 rows of P buffer c (all four are dead now): no wait between chunks
+          uint8_t* const tb = Pb + c * kAtQKBuf + q * 4096;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              ptx::split_f16x2(__uint_as_float(raw[8 * u + 2 * i]) * inv, __uint_as_float(raw[8 * u + 2 * i + 1]) * inv, hw[i],
+              ptx::split_f16x2(__uint_as_float(cur[8 * u + 2 * i]) * inv, __uint_as_float(cur[8 * u + 2 * i + 1]) * inv, hw[i],
+                               lw[i]);
+            const int off = lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(tb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(tb + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&p.st_hi, tb, h * 128 + c * 32, row0 + q * 32);
+            ptx::tma_store_2d(&p.st_lo, tb + 2048, h * 128 + c * 32, row0 + q * 32);
+            ptx::bulk_commit();
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              ptx::split_f16x2(__uint_as_float(cur[8 * u + 2 * i]) * inv, __uint_as_float(cur[8 * u + 2 * i + 1]) * inv, hw[i],
                                lw[i]);
             *reinterpret_cast<uint4*>(p.ctx_hi + o + c * 32 + u * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(p.ctx_lo + o + c * 32 + u * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
+        if (c + 1 < 4) ptx::tmem_ld_wait();
       }
+      if (group_full && lane == 0) ptx::bulk_wait_all();
       ptx::tc_fence_before_sync();
+      if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 8 + 3 * t);
     }
   }
 done:
   __syncthreads();
+  if (threadIdx.x == 0) at_stamp(p, 12);
   if (warp_idx == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -1281,11 +1353,28 @@ static int run_attention_tc(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   prm.S = S;
   prm.stages = 4;
   if (const char* env = getenv("ROHM_B200_ATTN_STAGES")) prm.stages = atoi(env);
+  static unsigned long long* d_ts = nullptr;
+  static int ts_calls = 0;
+  const bool want_ts = getenv("ROHM_B200_ATTN_TS") != nullptr && ++ts_calls == 12;  // a warm call, outside graph capture
+  if (want_ts) {
+    if (d_ts == nullptr) cudaMalloc(&d_ts, 16 * sizeof(unsigned long long));
+    prm.debug_ts = d_ts;
+  }
   prof_begin(pn, kCatAttention, st);
   cudaError_t e = launch_chain(attention_tc_kernel, dim3(B * pn->H), dim3(kAtThreads), kAtSmemBytes, st,
                                pn->use_pdl && !pn->profiling, prm);
   prof_end(pn, st);
   ROHM_CUDA(pn->ctx, e);
+  if (want_ts) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "attention_tc CTA0 timeline (ns): prologue %llu | Q,K landed %llu | S0 done %llu | V^T landed %llu | pass1 done %llu | "
+            "P0 ready %llu | O0 done %llu | tile0 stored %llu | P1 ready %llu | O1 done %llu | tile1 stored %llu | exit %llu\n",
+            h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0],
+            h[10] - h[0], h[11] - h[0], h[12] - h[0]);
+  }
   pn->launches++;
   return ROHM_OK;
 }
@@ -1596,6 +1685,12 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
       if (rcm != 0) {
         delete pn;
         return fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed (%d)", rcm);
+      }
+      rcm |= make_store_tmap(&pn->attn_tc.st_hi, pn->CTXh, R, D, D, true);
+      rcm |= make_store_tmap(&pn->attn_tc.st_lo, pn->CTXl, R, D, D, true);
+      if (rcm != 0) {
+        delete pn;
+        return fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (attention store) failed (%d)", rcm);
       }
       pn->attn_tc.ctx_hi = reinterpret_cast<__half*>(pn->CTXh), pn->attn_tc.ctx_lo = reinterpret_cast<__half*>(pn->CTXl);
       pn->attn_tc.D = D, pn->attn_tc.H = pn->H;
