@@ -791,6 +791,10 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
     }
     g.num_segs = 1, g.seg_kblocks[0] = kBlendK / kGemmBlockK, g.seg_row_mul[0] = 1;
     g.out = bd->vposed, g.ldo = bd->blend.Np, g.N = bd->blend.Np, g.out_row_mul = 1;  // padded columns are exact zeros
+    if (gemm_enable_tma_store(&g, F, kKindTf32) != 0) {  // 32 x 32 fp32 chunks leave through TMA bulk stores
+      delete bd;
+      return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: store tensor map failed");
+    }
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {

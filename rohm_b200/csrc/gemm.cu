@@ -557,7 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
     }
     if (warp_idx == 2 && lane == 0) stamp(p, 13);  // this warp's last tile drained
-    if (lane == 0) ptx::bulk_wait_all();  // outstanding TMA stores of this warp (no-op without the TMA-store path)
+    // outstanding TMA stores of this warp must have finished reading the staging tile before the CTA's shared memory is
+    // released; their global writes are ordered before the grid's completion like any other store
+    if (lane == 0) ptx::bulk_wait_read_all();
     if (warp_idx == 2 && lane == 0) stamp(p, 14);
   }
 

@@ -779,6 +779,9 @@ struct AttnTcParams {
   CUtensorMap qk_hi, qk_lo;  // [rows, 2D] fp16, box {64, 160}
   CUtensorMap vt_hi, vt_lo;  // [D, ldv] fp16, box {64, 128}
   CUtensorMap st_hi, st_lo;  // ctx planes [rows, D] fp16, 32 x 32 store boxes
+  int v_mn;       // 1: V is read in its natural [token][feature] layout (columns [2D, 3D) of the qk maps) as an MN-major B
+                  // operand; 0: V^T [feature][token] through the vt maps as a K-major operand (key axis shifted, see above)
+  int k_col0;     // first K column of the qk maps (D for a Q|K buffer, D as well for Q|K|V)
   __half* ctx_hi;
   __half* ctx_lo;
   int S, D, H;
@@ -846,17 +849,26 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         const CUtensorMap* m = pl == 0 ? &p.qk_hi : &p.qk_lo;
         for (int kc = 0; kc < 2; ++kc) {
           ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h * 128 + kc * 64, row0);
-          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.k_col0 + h * 128 + kc * 64, row0);
         }
       }
       if (!run_v) goto done;
       // V^T lands on top of Q / K: wait until every S MMA has read them
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
-      ptx::mbar_expect_tx(&v_full, 6 * kAtTile);
-      for (int pl = 0; pl < 2; ++pl) {
-        const CUtensorMap* m = pl == 0 ? &p.vt_hi : &p.vt_lo;
-        for (int c = 0; c < 3; ++c)
-          ptx::tma_load_2d(Vb + (pl * 3 + c) * kAtTile, m, &v_full, (row0 & ~7) + c * 64, h * 128);
+      if (p.v_mn) {
+        ptx::mbar_expect_tx(&v_full, 4 * kAtQKBuf);
+        for (int pl = 0; pl < 2; ++pl) {
+          const CUtensorMap* m = pl == 0 ? &p.qk_hi : &p.qk_lo;
+          for (int kc = 0; kc < 2; ++kc)
+            ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h * 128 + kc * 64, row0);
+        }
+      } else {
+        ptx::mbar_expect_tx(&v_full, 6 * kAtTile);
+        for (int pl = 0; pl < 2; ++pl) {
+          const CUtensorMap* m = pl == 0 ? &p.vt_hi : &p.vt_lo;
+          for (int c = 0; c < 3; ++c)
+            ptx::tma_load_2d(Vb + (pl * 3 + c) * kAtTile, m, &v_full, (row0 & ~7) + c * 64, h * 128);
+        }
       }
       if (!full) ptx::mbar_wait(&v_full, 0);
     }
@@ -864,6 +876,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc(/*F16*/ 0, 128, kAtKeys);
       constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128);
+      constexpr uint32_t idesc_o_mn = ptx::make_idesc(/*F16*/ 0, 128, 128, /*b_mn_major=*/true);
       ptx::mbar_wait(&qk_full, 0);
       at_stamp(p, 2);
       ptx::tc_fence_after_sync();
@@ -898,11 +911,20 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
           const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
           const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (0 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
           const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (1 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
-          const uint64_t b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (0 * 3 + c) * kAtTile)) + ko;
-          const uint64_t b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (1 * 3 + c) * kAtTile)) + ko;
-          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc_o, ks > 0 ? 1u : 0u);
-          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc_o, 1u);
-          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc_o, 1u);
+          uint64_t b_hi, b_lo;
+          uint32_t idesc = idesc_o;
+          if (p.v_mn) {
+            // V[key][feature]: 16 keys of this step = two 8-row atoms (1024 B apart); features 64..127 in the next buffer
+            b_hi = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 0 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
+            b_lo = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 2 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
+            idesc = idesc_o_mn;
+          } else {
+            b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (0 * 3 + c) * kAtTile)) + ko;
+            b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (1 * 3 + c) * kAtTile)) + ko;
+          }
+          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc, 1u);
+          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc, 1u);
         }
         ptx::mma_commit(&o_full[t]);
       }
@@ -922,7 +944,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     } else if (t < ntiles && p.stages >= 2) {
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
-      const int d = row0 & 7;  // key-axis shift of P and V^T
+      const int d = p.v_mn ? 0 : (row0 & 7);  // key-axis shift of P and V^T
       constexpr int NC = kAtKeys / 32;
       uint32_t r0[32], r1[32];
       ptx::mbar_wait(&s_full[t], 0);
@@ -1049,7 +1071,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         }
         if (c + 1 < 4) ptx::tmem_ld_wait();
       }
-      if (group_full && lane == 0) ptx::bulk_wait_all();
+      if (group_full && lane == 0) ptx::bulk_wait_read_all();  // staging tiles must outlive the TMA reads, not the writes
       ptx::tc_fence_before_sync();
       if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 8 + 3 * t);
     }
@@ -1121,6 +1143,8 @@ struct rohm_posenet {
   // tcgen05 attention (F16X2, head dim 128, <= 160 tokens per clip; ROHM_B200_TC_ATTENTION=0 disables): Q|K as fp16 planes
   // [rows, 2D] inside the QKV buffer, V^T as fp16 planes [D, ldv]
   bool tc_attention = false;
+  bool attn_v_mn = true;  // V read in place from the fused Q|K|V projection as an MN-major operand (ROHM_B200_ATTN_VT=1: use
+                          // the separate V^T projection instead)
   int ldv = 0;
   __half *Vth = nullptr, *Vtl = nullptr;
   AttnTcParams attn_tc{};
@@ -1499,6 +1523,8 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   {
     const char* env = getenv("ROHM_B200_TC_ATTENTION");
     pn->tc_attention = pn->kind == kKindF16 && dh == 128 && (env == nullptr || env[0] != '0');
+    const char* envt = getenv("ROHM_B200_ATTN_VT");
+    pn->attn_v_mn = !(envt != nullptr && envt[0] == '1');
   }
   const int D = pn->D, F = pn->F;
   const int64_t R = pn->max_rows;
@@ -1676,10 +1702,13 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     set_f16(attention_f16_kernel<64, 10>, attention_f16_smem_bytes<64>(10));
     set_f16(attention_tc_kernel, kAtSmemBytes);
     if (pn->tc_attention) {
+      const int qcols = pn->attn_v_mn ? 3 * D : 2 * D;  // Q|K|V planes of the fused projection, or Q|K planes
       __half* qk_hi = reinterpret_cast<__half*>(pn->QKV);
-      __half* qk_lo = qk_hi + R * 2 * D;
-      int rcm = make_tmap_2d(&pn->attn_tc.qk_hi, qk_hi, R, 2 * D, 2 * D, kAtKeys, 1, kKindF16);
-      rcm |= make_tmap_2d(&pn->attn_tc.qk_lo, qk_lo, R, 2 * D, 2 * D, kAtKeys, 1, kKindF16);
+      __half* qk_lo = qk_hi + R * qcols;
+      pn->attn_tc.v_mn = pn->attn_v_mn ? 1 : 0;
+      pn->attn_tc.k_col0 = D;
+      int rcm = make_tmap_2d(&pn->attn_tc.qk_hi, qk_hi, R, qcols, qcols, kAtKeys, 1, kKindF16);
+      rcm |= make_tmap_2d(&pn->attn_tc.qk_lo, qk_lo, R, qcols, qcols, kAtKeys, 1, kKindF16);
       rcm |= make_tmap_2d(&pn->attn_tc.vt_hi, pn->Vth, D, R, pn->ldv, 128, 1, kKindF16);
       rcm |= make_tmap_2d(&pn->attn_tc.vt_lo, pn->Vtl, D, R, pn->ldv, 128, 1, kKindF16);
       if (rcm != 0) {
@@ -1787,8 +1816,12 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
     if (pn->tc_attention && S <= kAtMaxTokens) {
-      if ((rc = run_gemm(pn, pn->g_qk[l], d.qk, rows, st)) != ROHM_OK) return rc;
-      if ((rc = run_gemm_vt(pn, pn->g_vt[l], rows, st)) != ROHM_OK) return rc;
+      if (pn->attn_v_mn) {
+        if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
+      } else {
+        if ((rc = run_gemm(pn, pn->g_qk[l], d.qk, rows, st)) != ROHM_OK) return rc;
+        if ((rc = run_gemm_vt(pn, pn->g_vt[l], rows, st)) != ROHM_OK) return rc;
+      }
       if ((rc = run_attention_tc(pn, B, S, st)) != ROHM_OK) return rc;
     } else {
       if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;

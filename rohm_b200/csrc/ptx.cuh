@@ -185,10 +185,22 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(kRowBytes == 128 ? 2 : 4) << 61;
   return d;
 }
+// MN-major operand (the MN extent is the contiguous one) in SWIZZLE_128B atoms of 8 K-rows x 128 bytes: LBO = byte distance
+// between atoms along MN (the next 64 16-bit elements), SBO = byte distance between atoms along K (the next 8 rows).
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor (32-bit): c_format[4,6), a_format[7,10), b_format[10,13), a_major[15], b_major[16],
 // n_dim[17,23) = N>>3, m_dim[24,29) = M>>4.  Formats: 0=F16, 1=BF16, 2=TF32; C: 1=F32.  Both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
-  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N, bool b_mn_major = false) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (b_mn_major ? (1u << 16) : 0u) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
 }
 
 // Round-to-nearest TF32 (10-bit mantissa), result kept in an fp32 container.
