@@ -760,28 +760,20 @@ template <int DH>
 size_t attention_f16_smem_bytes(int NK) { return sizeof(__half) * 4 * 16 * NK * attn_f16_pitch<DH>(); }
 
 // ---- tcgen05 attention (ROHM_PRECISION_F16X2, head dim 128, clips of at most 160 tokens) ----------------------------
-// One CTA per (clip, head).  Q and K of the head are TMA-loaded as K-major SWIZZLE_128B tiles straight from the Q|K GEMM's
-// fp16 hi/lo output; S = Q K^T runs as UMMA 128 x 160 x 16 (two 128-row query tiles, 160 padded keys) into TMEM; one
-// thread per query row reads its logits back (tcgen05.ld), does the softmax in registers (two passes over TMEM: max,
-// then exp / sum) and writes the unnormalised P row as fp16 hi/lo into a K-major shared-memory tile; O = P V^T^T runs as
-// UMMA 128 x 128 x 16 against V^T, which the projection GEMM produced directly in [feature][token] order (a transposed
-// product, see g_vt), so both operands of both products are K-major and no transposition happens in this kernel.
+// One CTA per (clip, head).  Q and K of the head are TMA-loaded as K-major SWIZZLE_128B tiles straight from the fused
+// Q|K|V projection's fp16 hi/lo output; S = Q K^T runs as UMMA 128 x 160 x 16 (two 128-row query tiles, 160 padded keys)
+// into TMEM; one thread per query row reads its logits back (tcgen05.ld), does the softmax in registers (two passes over
+// TMEM: max, then exp / sum) and writes the unnormalised P row as fp16 hi/lo into a K-major shared-memory tile; O = P V
+// runs as UMMA 128 x 128 x 16 with V read in place -- its natural [token][feature] layout is an MN-major B operand
+// (SWIZZLE_128B atoms of 8 keys x 64 features), so no transposition happens anywhere.
 // Every product is the 3-term hi/lo expansion; all three terms accumulate into one TMEM accumulator.
-// TMA needs a 16-byte aligned global start, but a clip's first token column in V^T (clip * S) is arbitrary: the V^T box
-// starts at the aligned-down column and the d = (clip * S) % 8 extra leading keys are compensated by writing P shifted by
-// d columns (its first d columns zero), which costs nothing because the shift is applied to the TMEM column address the
-// logits are re-read from.
 //   TMEM columns: [32,192) S tile 0 (reused by O tile 1), [192,352) S tile 1, [352,480) O tile 0.
 //   smem: phase 1  Q {hi,lo} x {dh 0-63, 64-127} 4 x 20 KB | K likewise 4 x 20 KB
 //         phase 2  P {hi,lo} x 3 key chunks 6 x 20 KB (160 rows each: both query tiles side by side, so neither waits for
-//                  the other) | V^T likewise 6 x 16 KB -- both land over Q / K once every S MMA has completed
+//                  the other) | V {hi,lo} x {dh 0-63, 64-127} 4 x 20 KB -- both land over Q / K once every S MMA is done
 struct AttnTcParams {
-  CUtensorMap qk_hi, qk_lo;  // [rows, 2D] fp16, box {64, 160}
-  CUtensorMap vt_hi, vt_lo;  // [D, ldv] fp16, box {64, 128}
-  CUtensorMap st_hi, st_lo;  // ctx planes [rows, D] fp16, 32 x 32 store boxes
-  int v_mn;       // 1: V is read in its natural [token][feature] layout (columns [2D, 3D) of the qk maps) as an MN-major B
-                  // operand; 0: V^T [feature][token] through the vt maps as a K-major operand (key axis shifted, see above)
-  int k_col0;     // first K column of the qk maps (D for a Q|K buffer, D as well for Q|K|V)
+  CUtensorMap qkv_hi, qkv_lo;  // Q | K | V planes [rows, 3D] fp16, box {64 columns, 160 rows}
+  CUtensorMap st_hi, st_lo;    // ctx planes [rows, D] fp16, 32 x 32 store boxes
   __half* ctx_hi;
   __half* ctx_lo;
   int S, D, H;
@@ -790,11 +782,10 @@ struct AttnTcParams {
   int stages;  // developer bisection aid (ROHM_B200_ATTN_STAGES): 1 = loads only, 2 = + S MMAs, 3 = + softmax, 4 = everything
 };
 constexpr int kAtKeys = 160;                  // padded key count = UMMA N of the S product
-constexpr int kAtMaxTokens = kAtKeys - 7;     // room for the alignment shift of the P / V^T key axis
 constexpr uint32_t kAtColS = 32, kAtColO0 = 32 + 2 * kAtKeys;  // TMEM column map (see above)
-constexpr int kAtQKBuf = kAtKeys * 128;       // bytes of one {plane, dh-chunk} Q or K buffer (160 rows x 128 B)
-constexpr int kAtTile = 128 * 128;            // bytes of one {plane, key-chunk} V^T or P buffer (128 rows x 128 B)
-constexpr int kAtSmemBytes = 6 * kAtQKBuf + 6 * kAtTile + 1024;
+constexpr int kAtQKBuf = kAtKeys * 128;       // bytes of one 160-row x 128-byte buffer: {plane, dh-chunk} of Q, K or V, {plane, key-chunk} of P
+constexpr int kAtTile = 128 * 128;            // bytes of the 128 rows of one query tile inside such a buffer
+constexpr int kAtSmemBytes = 10 * kAtQKBuf + 1024;
 constexpr int kAtThreads = 320;
 
 __device__ __forceinline__ void at_stamp(const AttnTcParams& p, int slot) {
@@ -822,8 +813,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   if (threadIdx.x == 0) at_stamp(p, 0);
 
   if (warp_idx == 0 && lane == 0) {
-    ptx::prefetch_tmap(&p.qk_hi), ptx::prefetch_tmap(&p.qk_lo), ptx::prefetch_tmap(&p.vt_hi), ptx::prefetch_tmap(&p.vt_lo);
-    ptx::prefetch_tmap(&p.st_hi), ptx::prefetch_tmap(&p.st_lo);
+    ptx::prefetch_tmap(&p.qkv_hi), ptx::prefetch_tmap(&p.qkv_lo), ptx::prefetch_tmap(&p.st_hi), ptx::prefetch_tmap(&p.st_lo);
     ptx::mbar_init(&qk_full, 1), ptx::mbar_init(&v_full, 1);
     for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 4), ptx::mbar_init(&o_full[t], 1);
     ptx::fence_barrier_init();
@@ -840,43 +830,33 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   uint8_t* const Qb = smem;                  // + (plane * 2 + kc) * kAtQKBuf
   uint8_t* const Kb = smem + 4 * kAtQKBuf;
   uint8_t* const Pb = smem;                  // + (plane * 3 + c) * kAtQKBuf, rows of tile t at + t * kAtTile
-  uint8_t* const Vb = smem + 6 * kAtQKBuf;   // + (plane * 3 + c) * kAtTile
+  uint8_t* const Vb = smem + 6 * kAtQKBuf;   // + (plane * 2 + kc) * kAtQKBuf
 
   if (warp_idx == 0) {
     if (lane == 0) {
       ptx::mbar_expect_tx(&qk_full, 8 * kAtQKBuf);
       for (int pl = 0; pl < 2; ++pl) {
-        const CUtensorMap* m = pl == 0 ? &p.qk_hi : &p.qk_lo;
+        const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
         for (int kc = 0; kc < 2; ++kc) {
           ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h * 128 + kc * 64, row0);
-          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.k_col0 + h * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h * 128 + kc * 64, row0);
         }
       }
       if (!run_v) goto done;
-      // V^T lands on top of Q / K: wait until every S MMA has read them
+      // V lands on top of K: wait until every S MMA has read it
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
-      if (p.v_mn) {
-        ptx::mbar_expect_tx(&v_full, 4 * kAtQKBuf);
-        for (int pl = 0; pl < 2; ++pl) {
-          const CUtensorMap* m = pl == 0 ? &p.qk_hi : &p.qk_lo;
-          for (int kc = 0; kc < 2; ++kc)
-            ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h * 128 + kc * 64, row0);
-        }
-      } else {
-        ptx::mbar_expect_tx(&v_full, 6 * kAtTile);
-        for (int pl = 0; pl < 2; ++pl) {
-          const CUtensorMap* m = pl == 0 ? &p.vt_hi : &p.vt_lo;
-          for (int c = 0; c < 3; ++c)
-            ptx::tma_load_2d(Vb + (pl * 3 + c) * kAtTile, m, &v_full, (row0 & ~7) + c * 64, h * 128);
-        }
+      ptx::mbar_expect_tx(&v_full, 4 * kAtQKBuf);
+      for (int pl = 0; pl < 2; ++pl) {
+        const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
+        for (int kc = 0; kc < 2; ++kc)
+          ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h * 128 + kc * 64, row0);
       }
       if (!full) ptx::mbar_wait(&v_full, 0);
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc(/*F16*/ 0, 128, kAtKeys);
-      constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128);
-      constexpr uint32_t idesc_o_mn = ptx::make_idesc(/*F16*/ 0, 128, 128, /*b_mn_major=*/true);
+      constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128, /*b_mn_major=*/true);
       ptx::mbar_wait(&qk_full, 0);
       at_stamp(p, 2);
       ptx::tc_fence_after_sync();
@@ -911,20 +891,13 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
           const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
           const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (0 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
           const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Pb + (1 * 3 + c) * kAtQKBuf + t * kAtTile)) + ko;
-          uint64_t b_hi, b_lo;
-          uint32_t idesc = idesc_o;
-          if (p.v_mn) {
-            // V[key][feature]: 16 keys of this step = two 8-row atoms (1024 B apart); features 64..127 in the next buffer
-            b_hi = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 0 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
-            b_lo = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 2 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
-            idesc = idesc_o_mn;
-          } else {
-            b_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (0 * 3 + c) * kAtTile)) + ko;
-            b_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Vb + (1 * 3 + c) * kAtTile)) + ko;
-          }
-          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
-          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc, 1u);
-          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc, 1u);
+          // V[key][feature]: the 16 keys of this step are two 8-row atoms (1024 B apart); features 64..127 live in the
+          // next buffer (LBO)
+          const uint64_t b_hi = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 0 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
+          const uint64_t b_lo = ptx::make_desc_mnmajor_sw128(ptx::smem_u32(Vb + 2 * kAtQKBuf + ks * 2048), kAtQKBuf, 1024);
+          ptx::mma_f16_ss(acc, a_lo, b_hi, idesc_o, ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(acc, a_hi, b_lo, idesc_o, 1u);
+          ptx::mma_f16_ss(acc, a_hi, b_hi, idesc_o, 1u);
         }
         ptx::mma_commit(&o_full[t]);
       }
@@ -944,7 +917,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     } else if (t < ntiles && p.stages >= 2) {
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
-      const int d = p.v_mn ? 0 : (row0 & 7);  // key-axis shift of P and V^T
       constexpr int NC = kAtKeys / 32;
       uint32_t r0[32], r1[32];
       ptx::mbar_wait(&s_full[t], 0);
@@ -970,29 +942,26 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       // the P buffers overlap Q and K: every S MMA must have completed
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
       // pass 2: p = exp(scale (s - max)), row sum, fp16 hi/lo -> K-major SWIZZLE_128B rows (16-byte unit u of row r at
-      // slot u ^ (r & 7)).  P column k holds key k - d: the logits are re-read from TMEM column k - d.
+      // slot u ^ (r & 7))
       float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       const float sc2 = p.scale * 1.4426950408889634f;  // exp(x) = 2^(x log2 e): one FFMA + one MUFU.EX2 per element
       const float ms2 = mx * sc2;
-      ptx::tmem_ld_32x32(s_addr - d, r0);
+      ptx::tmem_ld_32x32(s_addr, r0);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
         uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
-        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32 - d, nxt);
+        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32, nxt);
         float pv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float x = fmaf(__uint_as_float(cur[j]), sc2, -ms2);  // <= 0
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[j]) : "f"(x));
         }
-        if (c * 32 - d < 0 || c * 32 + 31 - d >= S) {  // only the first and the last chunks hold padded keys
+        if (c * 32 + 31 >= S) {  // only the last chunk(s) hold padded keys
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = c * 32 + j - d;
-            pv[j] = (key >= 0 && key < S) ? pv[j] : 0.0f;
-          }
+          for (int j = 0; j < 32; ++j) pv[j] = (c * 32 + j < S) ? pv[j] : 0.0f;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum4[j & 3] += pv[j];
@@ -1099,7 +1068,6 @@ size_t attention_smem_bytes(int S, int DH) {
 // ------------------------------------------------------------------------------------------------------------
 struct PoseNetLayerDev {
   PackedWeight qkv, proj, ff1, ff2;
-  PackedWeight qk, v;  // tcgen05-attention path: Q|K projection and the V projection used as the A operand of V^T = W_v X^T
   float *qkv_b, *proj_b, *ff1_b, *ff2_b, *n1_w, *n1_b, *n2_w, *n2_b;
 };
 
@@ -1140,15 +1108,9 @@ struct rohm_posenet {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_tma_store = true;  // ROHM_B200_TMA_STORE=0 falls back to the per-thread store epilogue (developer switch)
-  // tcgen05 attention (F16X2, head dim 128, <= 160 tokens per clip; ROHM_B200_TC_ATTENTION=0 disables): Q|K as fp16 planes
-  // [rows, 2D] inside the QKV buffer, V^T as fp16 planes [D, ldv]
+  // tcgen05 attention (F16X2, head dim 128, <= 160 tokens per clip; ROHM_B200_TC_ATTENTION=0 selects the mma.sync kernel)
   bool tc_attention = false;
-  bool attn_v_mn = true;  // V read in place from the fused Q|K|V projection as an MN-major operand (ROHM_B200_ATTN_VT=1: use
-                          // the separate V^T projection instead)
-  int ldv = 0;
-  __half *Vth = nullptr, *Vtl = nullptr;
   AttnTcParams attn_tc{};
-  std::vector<GemmParams> g_qk, g_vt;
   cudaStream_t capture_stream = nullptr;
   ~rohm_posenet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -1361,17 +1323,6 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
                       pn->CTXl, S, pn->D, pn->H, scale, pn->kind == kKindF16 ? 1 : 0);
 }
 
-// V^T = W_v X^T: M = d_model output features, N = token rows of this call.
-static int run_gemm_vt(rohm_posenet* pn, GemmParams& g, int rows, cudaStream_t st) {
-  g.M = pn->D;
-  g.N = rows;
-  prof_begin(pn, kCatGemm, st);
-  ROHM_CUDA(pn->ctx, launch_gemm(g, pn->D, rows, 128, 3, st, pn->use_pdl && !pn->profiling, kKindF16));
-  prof_end(pn, st);
-  pn->launches++;
-  return ROHM_OK;
-}
-
 static int run_attention_tc(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   AttnTcParams prm = pn->attn_tc;
   prm.S = S;
@@ -1523,8 +1474,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   {
     const char* env = getenv("ROHM_B200_TC_ATTENTION");
     pn->tc_attention = pn->kind == kKindF16 && dh == 128 && (env == nullptr || env[0] != '0');
-    const char* envt = getenv("ROHM_B200_ATTN_VT");
-    pn->attn_v_mn = !(envt != nullptr && envt[0] == '1');
   }
   const int D = pn->D, F = pn->F;
   const int64_t R = pn->max_rows;
@@ -1551,10 +1500,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     const rohm_posenet_layer& s = w->layers[l];
     PoseNetLayerDev& d = pn->layers[l];
     TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv, pn->kind));
-    if (pn->tc_attention) {
-      TRY(pack_weight(pn, s.in_proj_w, 2 * D, D, &d.qk, pn->kind));
-      TRY(pack_weight(pn, s.in_proj_w + static_cast<int64_t>(2) * D * D, D, D, &d.v, pn->kind));
-    }
     TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj, pn->kind));
     TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1, pn->kind));
     TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2, pn->kind));
@@ -1585,17 +1530,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     }
   }
 
-  if (pn->tc_attention) {
-    pn->ldv = static_cast<int>(round_up(R, 8));
-    pn->Vth = static_cast<__half*>(pn->pool.bytes(static_cast<int64_t>(D) * pn->ldv * 2));
-    pn->Vtl = static_cast<__half*>(pn->pool.bytes(static_cast<int64_t>(D) * pn->ldv * 2));
-    if (pn->Vth == nullptr || pn->Vtl == nullptr) {
-      const int rc = fail(ctx, ROHM_ERR_CUDA, "workspace alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
-      delete pn;
-      return rc;
-    }
-  }
-
   // GEMM descriptors.  Input embedding: residual = cond embedding + positional rows (set per set_cond).
   TRY(setup_linear(pn, &pn->g_in, pn->Ain_h, pn->Ain_l, R, pn->C, pn->Kin_p, pn->w_in, pn->in_b));
   pn->g_in.residual = pn->condpe, pn->g_in.ldr = D;
@@ -1609,7 +1543,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   TRY(setup_linear(pn, &pn->g_out, pn->Xh, pn->Xl, R, D, D, pn->w_out, pn->out_b));
   pn->g_out.out = pn->OUT, pn->g_out.ldo = pn->Cout;
   pn->g_qkv.resize(pn->L), pn->g_proj.resize(pn->L), pn->g_ff1.resize(pn->L), pn->g_ff2.resize(pn->L);
-  pn->g_qk.resize(pn->L), pn->g_vt.resize(pn->L);
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
     TRY(setup_linear(pn, &pn->g_qkv[l], pn->Xh, pn->Xl, R, D, D, d.qkv, d.qkv_b));
@@ -1629,38 +1562,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     pn->g_ff1[l].out_hi = pn->Hh, pn->g_ff1[l].out_lo = pn->Hl, pn->g_ff1[l].lds = F;
     TRY(setup_linear(pn, &pn->g_ff2[l], pn->Hh, pn->Hl, R, F, F, d.ff2, d.ff2_b));
     pn->g_ff2[l].out = pn->Y, pn->g_ff2[l].ldo = D;
-    if (pn->tc_attention) {
-      __half* qk_hi = reinterpret_cast<__half*>(pn->QKV);
-      __half* qk_lo = qk_hi + R * 2 * D;
-      // Q | K projection -> fp16 planes [rows, 2D]
-      TRY(setup_linear(pn, &pn->g_qk[l], pn->Xh, pn->Xl, R, D, D, d.qk, d.qkv_b));
-      pn->g_qk[l].out_hi = qk_hi, pn->g_qk[l].out_lo = qk_lo, pn->g_qk[l].lds = 2 * D;
-      // V^T = W_v X^T + b_v 1^T: the weight is the A (row) operand, the tokens are the B (column) operand, so the
-      // result comes out [feature][token] -- K-major for the P V product -- without a transposition pass
-      GemmParams& gv = pn->g_vt[l];
-      gv = GemmParams{};
-      int rcm = make_tmap_2d(&gv.a_hi[0], d.v.hi, d.v.Np, d.v.Kp, d.v.Kp, kGemmBlockM, 1, pn->kind);
-      rcm |= make_tmap_2d(&gv.a_lo[0], d.v.lo, d.v.Np, d.v.Kp, d.v.Kp, kGemmBlockM, 1, pn->kind);
-      rcm |= make_tmap_2d(&gv.b_hi, pn->Xh, R, D, D, 128, 1, pn->kind);
-      rcm |= make_tmap_2d(&gv.b_lo, pn->Xl, R, D, D, 128, 1, pn->kind);
-      if (rcm != 0) {
-        const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", rcm);
-        delete pn;
-        return rc__;
-      }
-      gv.num_segs = 1, gv.seg_kblocks[0] = d.v.Kp / gemm_block_k(pn->kind), gv.seg_row_mul[0] = 1;
-      gv.acc_scale = 1.0f / d.v.scale;
-      gv.bias = d.qkv_b + 2 * D, gv.bias_per_row = 1;
-      gv.out_hi = pn->Vth, gv.out_lo = pn->Vtl, gv.lds = pn->ldv;
-      gv.M = D, gv.N = pn->ldv, gv.out_row_mul = 1;
-      for (GemmParams* g : {&pn->g_qk[l], &pn->g_vt[l]}) {
-        if (pn->use_tma_store && gemm_enable_tma_store(g, g == &pn->g_vt[l] ? D : R, pn->kind) != 0) {
-          const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
-          delete pn;
-          return rc__;
-        }
-      }
-    }
     for (GemmParams* g : {&pn->g_qkv[l], &pn->g_proj[l], &pn->g_ff1[l], &pn->g_ff2[l]}) {
       if (pn->use_tma_store && gemm_enable_tma_store(g, R, pn->kind) != 0) {
         const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
@@ -1702,19 +1603,10 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     set_f16(attention_f16_kernel<64, 10>, attention_f16_smem_bytes<64>(10));
     set_f16(attention_tc_kernel, kAtSmemBytes);
     if (pn->tc_attention) {
-      const int qcols = pn->attn_v_mn ? 3 * D : 2 * D;  // Q|K|V planes of the fused projection, or Q|K planes
-      __half* qk_hi = reinterpret_cast<__half*>(pn->QKV);
-      __half* qk_lo = qk_hi + R * qcols;
-      pn->attn_tc.v_mn = pn->attn_v_mn ? 1 : 0;
-      pn->attn_tc.k_col0 = D;
-      int rcm = make_tmap_2d(&pn->attn_tc.qk_hi, qk_hi, R, qcols, qcols, kAtKeys, 1, kKindF16);
-      rcm |= make_tmap_2d(&pn->attn_tc.qk_lo, qk_lo, R, qcols, qcols, kAtKeys, 1, kKindF16);
-      rcm |= make_tmap_2d(&pn->attn_tc.vt_hi, pn->Vth, D, R, pn->ldv, 128, 1, kKindF16);
-      rcm |= make_tmap_2d(&pn->attn_tc.vt_lo, pn->Vtl, D, R, pn->ldv, 128, 1, kKindF16);
-      if (rcm != 0) {
-        delete pn;
-        return fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed (%d)", rcm);
-      }
+      __half* qkv_hi = reinterpret_cast<__half*>(pn->QKV);
+      __half* qkv_lo = qkv_hi + R * 3 * D;
+      int rcm = make_tmap_2d(&pn->attn_tc.qkv_hi, qkv_hi, R, 3 * D, 3 * D, kAtKeys, 1, kKindF16);
+      rcm |= make_tmap_2d(&pn->attn_tc.qkv_lo, qkv_lo, R, 3 * D, 3 * D, kAtKeys, 1, kKindF16);
       rcm |= make_store_tmap(&pn->attn_tc.st_hi, pn->CTXh, R, D, D, true);
       rcm |= make_store_tmap(&pn->attn_tc.st_lo, pn->CTXl, R, D, D, true);
       if (rcm != 0) {
@@ -1815,16 +1707,10 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
 
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
-    if (pn->tc_attention && S <= kAtMaxTokens) {
-      if (pn->attn_v_mn) {
-        if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
-      } else {
-        if ((rc = run_gemm(pn, pn->g_qk[l], d.qk, rows, st)) != ROHM_OK) return rc;
-        if ((rc = run_gemm_vt(pn, pn->g_vt[l], rows, st)) != ROHM_OK) return rc;
-      }
+    if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
+    if (pn->tc_attention && S <= kAtKeys) {
       if ((rc = run_attention_tc(pn, B, S, st)) != ROHM_OK) return rc;
     } else {
-      if ((rc = run_gemm(pn, pn->g_qkv[l], d.qkv, rows, st)) != ROHM_OK) return rc;
       if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
     }
     if ((rc = run_gemm(pn, pn->g_proj[l], d.proj, rows, st)) != ROHM_OK) return rc;

@@ -54,7 +54,9 @@ def test_forward_matches_reference_golden(posenet, cuda_device):
         assert err < TOL, (c, err)
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 143), (5, 144), (2, 200)])
+# T + 1 tokens per clip: 128 / 129 straddle the query-tile boundary of the tcgen05 attention kernel, 160 is its largest clip,
+# 161 and 201 take the mma.sync / SIMT fallbacks
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 143), (5, 144), (2, 127), (2, 128), (3, 159), (1, 160), (2, 200)])
 def test_forward_matches_oracle(posenet, cuda_device, B, T):
     m, sd = posenet
     gen = torch.Generator().manual_seed(1000 + B * 7 + T)
@@ -86,6 +88,25 @@ def test_every_precision_mode_against_oracle(posenet, cuda_device, prec, tol):
         m.precision = None
     assert m._engine.precision == prec
     assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()) / 10.0)
+
+
+def test_mma_sync_attention_fallback_matches_oracle(posenet, cuda_device, monkeypatch):
+    """ROHM_B200_TC_ATTENTION=0 routes f16x2 attention to the mma.sync m16n8k16 kernel (also used for head dim 64)."""
+    m, sd = posenet
+    B, T = 3, 144
+    gen = torch.Generator().manual_seed(31337)
+    x = torch.randn(B, 294, 1, T, generator=gen)
+    cond = synthetic.posenet_batch(B, T, 11)['cond']
+    ts = torch.tensor([1, 400, 998])
+    ref = posenet_oracle.posenet_forward(sd, x, cond, ts)
+    monkeypatch.setenv("ROHM_B200_TC_ATTENTION", "0")
+    m.invalidate_engine()
+    try:
+        y = m({'x_t': x.to(cuda_device), 'cond': cond.to(cuda_device)}, ts.to(cuda_device)).cpu()
+    finally:
+        monkeypatch.delenv("ROHM_B200_TC_ATTENTION")
+        m._engine = None
+    assert float((y - ref).abs().max()) < TOL
 
 
 def test_forward_noncontiguous_inputs_and_cond_updates(posenet, cuda_device):
