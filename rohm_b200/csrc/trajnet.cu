@@ -285,7 +285,21 @@ int make_act(rohm_trajnet* tn, const std::string& name, int C, int level, bool w
   return ROHM_OK;
 }
 
-int pick_bn(int N) { return N >= 128 ? 128 : N > 32 ? 64 : 32; }
+// Output-tile width of a convolution GEMM.  The deep pyramid levels have few 128-row tiles (11 at level 3 with 64 clips), so
+// 128-wide tiles would leave most of the 148 SMs idle; a narrower tile multiplies the tile count at a modest cost per tile
+// (operand fill per 32 K-columns: 32 KB of A + BLOCK_N / 4 KB of B).  Choose the width that minimises waves x fill.
+int pick_bn(int N, int64_t rows) {
+  const int64_t m_tiles = (rows + kGemmBlockM - 1) / kGemmBlockM;
+  int best = 0;
+  double best_cost = 0.0;
+  for (int bn : {128, 64, 32}) {
+    if (bn > 32 && bn > N) continue;
+    const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
+    const double cost = static_cast<double>((tiles + 147) / 148) * (32.0 + bn / 4.0);
+    if (best == 0 || cost < best_cost) best = bn, best_cost = cost;
+  }
+  return best;
+}
 
 // Builds one convolution as a segmented GEMM.
 //   kind 0: Conv1d(ks, stride, pad = ks/2 for stride 1, 1 for the stride-2 k3 downsample)
@@ -317,7 +331,7 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
     for (auto* s : srcs) Ktot += static_cast<int>(round_up(s->C, kGemmBlockK));
   PackedWeight& pw = cv.w;
   pw.N = Cout, pw.K = Ktot, pw.Kp = Ktot;
-  pw.block_n = pick_bn(Cout);
+  pw.block_n = pick_bn(Cout, rows_of(tn, (kind == 0) ? out->level : srcs[0]->level));
   pw.Np = static_cast<int>(round_up(Cout, pw.block_n));
   pw.hi = tn->pool.floats(static_cast<int64_t>(pw.Np) * Ktot);
   pw.lo = tn->pool.floats(static_cast<int64_t>(pw.Np) * Ktot);
