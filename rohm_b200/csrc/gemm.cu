@@ -3,7 +3,9 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 namespace rohm {
@@ -590,6 +592,19 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
   for (; i < n; i += stride) ptx::split_f16(x[i] * scale, hi[i], lo[i]);
 }
 
+// max |w| over n elements (the bit pattern of a non-negative float is monotonic in its value)
+__global__ void absmax_kernel(const float* __restrict__ w, int64_t n, unsigned int* __restrict__ out) {
+  float m = 0.0f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float a = fabsf(w[i]);
+    m = (a <= 3.0e38f && a > m) ? a : m;  // ignores NaN / inf
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -746,6 +761,33 @@ cudaError_t gemm_init_attributes() {
   if ((e = set_attr<64, 3, kKindF16>()) != cudaSuccess) return e;
   if ((e = set_attr<96, 3, kKindF16>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 3, kKindF16>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t f16_weight_scale(const float* w_dev, int64_t n, float* scale_out) {
+  *scale_out = 1.0f;
+  if (n <= 0) return cudaSuccess;
+  unsigned int* d_max = nullptr;
+  cudaError_t e = cudaMalloc(&d_max, sizeof(unsigned int));
+  if (e != cudaSuccess) return e;
+  unsigned int bits = 0;
+  e = cudaMemset(d_max, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) {
+    absmax_kernel<<<148, 256>>>(w_dev, n, d_max);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&bits, d_max, sizeof bits, cudaMemcpyDeviceToHost);
+  cudaFree(d_max);
+  if (e != cudaSuccess) return e;
+  float wmax;
+  memcpy(&wmax, &bits, sizeof wmax);
+  if (wmax > 0.0f) {
+    int e2 = 0;
+    frexpf(wmax, &e2);  // wmax = f * 2^e2, f in [0.5, 1)
+    int sh = 14 - e2;
+    sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+    *scale_out = ldexpf(1.0f, sh);
+  }
   return cudaSuccess;
 }
 

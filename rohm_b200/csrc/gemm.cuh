@@ -124,6 +124,11 @@ cudaError_t gemm_init_attributes();
 
 // fp32 -> (hi, lo) TF32 split, elementwise; n elements.
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
+// Power-of-two scale 2^s for storing a weight tensor as fp16 hi/lo pairs: max |w| 2^s lies in [2^13, 2^14), so every
+// weight within 2^-13 of the largest keeps a normal-range lo half and nothing overflows (1.0 for an all-zero tensor).
+// Synchronous (reads the maximum back); call at engine creation only.
+cudaError_t f16_weight_scale(const float* w_dev, int64_t n, float* scale_out);
+
 // fp32 -> (hi, lo) fp16 split of x * scale, elementwise; n elements.
 cudaError_t launch_split_f16(const float* x, void* hi, void* lo, int64_t n, float scale, cudaStream_t stream);
 

@@ -1176,19 +1176,6 @@ static __global__ void pack_weight_kernel(const float* __restrict__ w, float* __
   }
 }
 
-// max |w| over n elements (bit pattern of a non-negative float is monotonic in its value)
-static __global__ void absmax_kernel(const float* __restrict__ w, int64_t n, unsigned int* __restrict__ out) {
-  float m = 0.0f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float a = fabsf(w[i]);
-    m = (a <= 3.0e38f && a > m) ? a : m;  // ignores NaN / inf
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
-}
-
 // kind == kKindF16: the matrix is stored as fp16 hi/lo of w * 2^s, s chosen per matrix so that max |w| 2^s lies in
 // [2^13, 2^14): every weight within 2^-13 of the largest keeps a normal-range lo half, and nothing overflows.
 static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out, int kind = kKindTf32) {
@@ -1204,23 +1191,7 @@ static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWei
   if (out->hi == nullptr || out->lo == nullptr)
     return fail(pn->ctx, ROHM_ERR_CUDA, "weight alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
   const int64_t n = static_cast<int64_t>(N) * K;
-  if (kind == kKindF16) {
-    unsigned int* d_max = static_cast<unsigned int*>(pn->pool.bytes(16));
-    if (d_max == nullptr) return fail(pn->ctx, ROHM_ERR_CUDA, "weight alloc failed");
-    absmax_kernel<<<148, 256>>>(w, n, d_max);
-    ROHM_CUDA(pn->ctx, cudaGetLastError());
-    unsigned int bits = 0;
-    ROHM_CUDA(pn->ctx, cudaMemcpy(&bits, d_max, sizeof bits, cudaMemcpyDeviceToHost));
-    float wmax;
-    memcpy(&wmax, &bits, sizeof wmax);
-    if (wmax > 0.0f) {
-      int e2 = 0;
-      frexpf(wmax, &e2);  // wmax = f * 2^e2, f in [0.5, 1)
-      int s = 14 - e2;
-      s = s > 100 ? 100 : (s < -100 ? -100 : s);
-      out->scale = ldexpf(1.0f, s);
-    }
-  }
+  if (kind == kKindF16) ROHM_CUDA(pn->ctx, f16_weight_scale(w, n, &out->scale));
   pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w, out->hi, out->lo, N, K, out->Kp,
                                                                      kind == kKindF16 ? 1 : 0, out->scale);
   ROHM_CUDA(pn->ctx, cudaGetLastError());

@@ -30,7 +30,7 @@ __device__ __forceinline__ float mish_f(float x) {
 
 // [B, T, C] channels-last API tensor -> padded-clip hi/lo rows (b * Tp + t), pitch ld.  Pad rows stay zero.
 __global__ void pack_rows_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int T,
-                                 int Tp, int C, int ld, int64_t total) {
+                                 int Tp, int C, int ld, int64_t total, int f16) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % C);
@@ -38,10 +38,14 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, float* __restrict_
   const int t = static_cast<int>(bt % T);
   const int64_t b = bt / T;
   const float v = x[i];
-  const float h = ptx::to_tf32(v);
   const int64_t o = (b * Tp + t) * ld + c;
-  hi[o] = h;
-  lo[o] = v - h;
+  if (f16) {
+    ptx::split_f16(v, reinterpret_cast<__half*>(hi)[o], reinterpret_cast<__half*>(lo)[o]);
+  } else {
+    const float h = ptx::to_tf32(v);
+    hi[o] = h;
+    lo[o] = v - h;
+  }
 }
 
 // Timestep path of TrajNet (trajnet.py:120-125, 189) and the per-block time projections (heads.py:34-38, 51-52):
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
                                                       const float* __restrict__ r1, const float* __restrict__ r2,
                                                       float* __restrict__ out, float* __restrict__ out_hi,
                                                       float* __restrict__ out_lo, int C, int Tp, int T, int groups,
-                                                      int64_t total4) {
+                                                      int64_t total4, int f16) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -133,7 +137,12 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
     }
   }
   if (out != nullptr) reinterpret_cast<float4*>(out)[i] = v;
-  if (out_hi != nullptr) {
+  if (out_hi != nullptr && f16) {
+    uint2 h, l;
+    ptx::split_f16x4(v, h, l);
+    reinterpret_cast<uint2*>(out_hi)[i] = h;
+    reinterpret_cast<uint2*>(out_lo)[i] = l;
+  } else if (out_hi != nullptr) {
     float4 h, l;
     h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
     l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
@@ -159,15 +168,20 @@ __global__ void unpack_rows_kernel(const float* __restrict__ x, float* __restric
 // transposed: w[src_off + c][co][tap]  (ConvTranspose1d weight [Cin, Cout, k])
 __global__ void pack_conv_segment_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
                                          int Cout, int Cin_total, int ks, int src_off, int Cs, int tap, int seg_off,
-                                         int Ktot, int transposed) {
+                                         int Ktot, int transposed, int f16, float scale) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(Cout) * Cs) return;
   const int co = static_cast<int>(i / Cs), c = static_cast<int>(i % Cs);
   const float v = transposed ? w[(static_cast<int64_t>(src_off + c) * Cout + co) * ks + tap]
                              : w[(static_cast<int64_t>(co) * Cin_total + src_off + c) * ks + tap];
-  const float h = ptx::to_tf32(v);
-  hi[static_cast<int64_t>(co) * Ktot + seg_off + c] = h;
-  lo[static_cast<int64_t>(co) * Ktot + seg_off + c] = v - h;
+  const int64_t o = static_cast<int64_t>(co) * Ktot + seg_off + c;
+  if (f16) {
+    ptx::split_f16(v * scale, reinterpret_cast<__half*>(hi)[o], reinterpret_cast<__half*>(lo)[o]);
+  } else {
+    const float h = ptx::to_tf32(v);
+    hi[o] = h;
+    lo[o] = v - h;
+  }
 }
 
 constexpr int kLevels = 5;
@@ -203,6 +217,7 @@ struct rohm_trajnet {
   int time_dim = 32, cond_dim = 13, traj_dim = 13, mid = 512, control_dim = 272;
   bool control = false;
   int passes = 3;
+  int kind = kKindTf32;  // operand element type of the convolution GEMMs (kKindF16 in ROHM_PRECISION_F16X2)
   int max_batch = 0, T = 0;
   int Tl[kLevels], Tp[kLevels];
   std::map<std::string, std::pair<const float*, int64_t>> sd;  // caller's tensors, valid during create only
@@ -275,7 +290,7 @@ float* dev_copy(rohm_trajnet* tn, const float* src, int64_t n, int* rc) {
 // Allocates an activation (fp32 and/or hi/lo) at a level.
 int make_act(rohm_trajnet* tn, const std::string& name, int C, int level, bool want_f32, bool want_split) {
   Act a;
-  a.C = C, a.level = level, a.ld = static_cast<int>(round_up(C, 4));
+  a.C = C, a.level = level, a.ld = static_cast<int>(round_up(C, tn->kind == kKindF16 ? 8 : 4));  // 16-byte row pitch
   const int64_t n = rows_of(tn, level) * a.ld;
   if (want_f32) a.f32 = tn->pool.floats(n);
   if (want_split) a.hi = tn->pool.floats(n), a.lo = tn->pool.floats(n);
@@ -326,16 +341,19 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   }
   const int nseg = static_cast<int>(taps.size() * srcs.size());
   if (nseg > kMaxSegs) return fail(tn->ctx, ROHM_ERR_INVALID, "conv '%s' needs %d segments", name.c_str(), nseg);
+  const int kblk = gemm_block_k(tn->kind);  // every source's channels are padded to a whole K block (zero columns)
   int Ktot = 0;
   for (size_t i = 0; i < taps.size(); ++i)
-    for (auto* s : srcs) Ktot += static_cast<int>(round_up(s->C, kGemmBlockK));
+    for (auto* s : srcs) Ktot += static_cast<int>(round_up(s->C, kblk));
   PackedWeight& pw = cv.w;
   pw.N = Cout, pw.K = Ktot, pw.Kp = Ktot;
   pw.block_n = pick_bn(Cout, rows_of(tn, (kind == 0) ? out->level : srcs[0]->level));
   pw.Np = static_cast<int>(round_up(Cout, pw.block_n));
-  pw.hi = tn->pool.floats(static_cast<int64_t>(pw.Np) * Ktot);
-  pw.lo = tn->pool.floats(static_cast<int64_t>(pw.Np) * Ktot);
+  pw.kind = tn->kind;
+  pw.hi = static_cast<float*>(tn->pool.bytes(static_cast<int64_t>(pw.Np) * Ktot * gemm_elem_bytes(tn->kind)));
+  pw.lo = static_cast<float*>(tn->pool.bytes(static_cast<int64_t>(pw.Np) * Ktot * gemm_elem_bytes(tn->kind)));
   if (!pw.hi || !pw.lo) return fail(tn->ctx, ROHM_ERR_CUDA, "weight alloc failed");
+  if (tn->kind == kKindF16) ROHM_CUDA(tn->ctx, f16_weight_scale(w, static_cast<int64_t>(Cout) * Cin * ks, &pw.scale));
   cv.bias = dev_copy(tn, b, Cout, &rc);
   if (rc != ROHM_OK) return rc;
 
@@ -351,21 +369,24 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
       const int Cs = s->C;
       const int64_t n = static_cast<int64_t>(Cout) * Cs;
       pack_conv_segment_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w, pw.hi, pw.lo, Cout, Cin, ks, src_off,
-                                                                              Cs, tap.first, seg_off, Ktot, kind != 0);
-      int e1 = make_tmap_2d(&g.a_hi[seg], s->hi, rows_of(tn, in_level), Cs, s->ld, kGemmBlockM, stride);
-      int e2 = make_tmap_2d(&g.a_lo[seg], s->lo, rows_of(tn, in_level), Cs, s->ld, kGemmBlockM, stride);
+                                                                              Cs, tap.first, seg_off, Ktot, kind != 0,
+                                                                              tn->kind == kKindF16 ? 1 : 0, pw.scale);
+      int e1 = make_tmap_2d(&g.a_hi[seg], s->hi, rows_of(tn, in_level), Cs, s->ld, kGemmBlockM, stride, tn->kind);
+      int e2 = make_tmap_2d(&g.a_lo[seg], s->lo, rows_of(tn, in_level), Cs, s->ld, kGemmBlockM, stride, tn->kind);
       if (e1 || e2) return fail(tn->ctx, ROHM_ERR_CUDA, "tensor map failed for conv '%s' (%d, %d)", name.c_str(), e1, e2);
-      g.seg_kblocks[seg] = static_cast<int>(round_up(Cs, kGemmBlockK)) / kGemmBlockK;
+      g.seg_kblocks[seg] = static_cast<int>(round_up(Cs, kblk)) / kblk;
       g.seg_row_shift[seg] = tap.second;
       g.seg_row_mul[seg] = stride;
-      seg_off += static_cast<int>(round_up(Cs, kGemmBlockK));
+      seg_off += static_cast<int>(round_up(Cs, kblk));
       src_off += Cs;
       ++seg;
     }
   }
   ROHM_CUDA(tn->ctx, cudaGetLastError());
   g.num_segs = nseg;
-  if (make_tmap_2d(&g.b_hi, pw.hi, pw.Np, Ktot, Ktot, pw.block_n) || make_tmap_2d(&g.b_lo, pw.lo, pw.Np, Ktot, Ktot, pw.block_n))
+  g.acc_scale = 1.0f / pw.scale;
+  if (make_tmap_2d(&g.b_hi, pw.hi, pw.Np, Ktot, Ktot, pw.block_n, 1, tn->kind) ||
+      make_tmap_2d(&g.b_lo, pw.lo, pw.Np, Ktot, Ktot, pw.block_n, 1, tn->kind))
     return fail(tn->ctx, ROHM_ERR_CUDA, "tensor map failed for weights of '%s'", name.c_str());
   g.bias = cv.bias;
   g.N = Cout;
@@ -436,7 +457,7 @@ int run_conv(rohm_trajnet* tn, const std::string& name, int B, cudaStream_t st) 
   Conv& cv = it->second;
   const int rows = B * tn->Tp[cv.level_out];
   cv.g.M = rows;
-  ROHM_CUDA(tn->ctx, launch_gemm(cv.g, rows, cv.w.N, cv.w.block_n, tn->passes, st));
+  ROHM_CUDA(tn->ctx, launch_gemm(cv.g, rows, cv.w.N, cv.w.block_n, tn->passes, st, false, tn->kind));
   tn->launches++;
   return ROHM_OK;
 }
@@ -448,7 +469,7 @@ int run_gn(rohm_trajnet* tn, const std::string& conv_name, const std::string& no
   const int64_t total4 = static_cast<int64_t>(B) * tn->Tp[level] * C / 4;
   gn_mish_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
       y, cv.stats, nb.first, nb.second, tp, tn->tp_total, r1, r2, out->f32, out->hi, out->lo, C, tn->Tp[level],
-      tn->Tl[level], kGroups, total4);
+      tn->Tl[level], kGroups, total4, tn->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(tn->ctx, cudaGetLastError());
   tn->launches++;
   return ROHM_OK;
@@ -489,15 +510,16 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
                 "stride-2 stages)", frames);
   if (mid_dim % 64 != 0 || time_dim % 2 != 0 || time_dim > 64)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: mid_dim must be a multiple of 64, time_dim even and <= 64");
-  if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32)
-    return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: precision must be 3 or 1");
+  if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32 && precision != ROHM_PRECISION_F16X2)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: precision must be 3 (TF32x3), 2 (F16x2) or 1 (TF32)");
   ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
   ROHM_CUDA(ctx, gemm_init_attributes());
   rohm_trajnet* tn = new (std::nothrow) rohm_trajnet();
   if (tn == nullptr) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
   tn->ctx = ctx;
   tn->time_dim = time_dim, tn->cond_dim = cond_dim, tn->traj_dim = traj_feat_dim, tn->mid = mid_dim;
-  tn->control = trajcontrol != 0, tn->control_dim = control_cond_dim, tn->passes = precision;
+  tn->control = trajcontrol != 0, tn->control_dim = control_cond_dim, tn->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
+  tn->kind = precision == ROHM_PRECISION_F16X2 ? kKindF16 : kKindTf32;
   tn->max_batch = max_batch, tn->T = frames;
   for (int l = 0; l < kLevels; ++l) tn->Tl[l] = frames >> l, tn->Tp[l] = (frames + 32) >> l;
   for (int i = 0; i < n_params; ++i) tn->sd[names[i]] = {ptrs[i], numels[i]};
@@ -689,7 +711,7 @@ extern "C" int rohm_trajnet_launches_per_forward(const rohm_trajnet* tn) { retur
 static int trajnet_pack(rohm_trajnet* tn, const float* x, const Act& a, int B, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * tn->T * a.C;
   pack_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, a.hi, a.lo, tn->T, tn->Tp[0], a.C, a.ld,
-                                                                             total);
+                                                                             total, tn->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(tn->ctx, cudaGetLastError());
   tn->launches++;
   return ROHM_OK;
@@ -859,7 +881,7 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
   void* a_o = out;
   {
     cudaKernelNodeParams kp = fg->p_pack;
-    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 8);
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 9);
     args[0] = &a_x;
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_pack, &kp));

@@ -22,7 +22,7 @@ DEFAULT_PRECISION = "f16x2"
 
 def _precision_from_env(supports_f16=True):
     """ROHM_B200_PRECISION: 'f16x2' (default: fp16 hi/lo pairs, fp32-grade), 'tf32x3' (TF32 hi/lo pairs, fp32-grade),
-    'tf32' (single pass, fast, ~1e-3).  Engines without an fp16 path (TrajNet) run 'f16x2' as 'tf32x3'."""
+    'tf32' (single pass, fast, ~1e-3).  Engines without an fp16 path (the LBS blend GEMM) run 'f16x2' as 'tf32x3'."""
     v = os.environ.get("ROHM_B200_PRECISION", DEFAULT_PRECISION).lower()
     if v in ("f16x2", "fp16x2", "parity"):
         return _lib.PRECISION_F16X2 if supports_f16 else _lib.PRECISION_TF32X3

@@ -77,7 +77,7 @@ def get_engine(module, B, T, device):
     if module.training:
         raise RohmB200Error("TrajNet: the CUDA engine implements the inference path (model.eval()); training is out of "
                             "scope")
-    prec = module.precision if module.precision is not None else _precision_from_env(supports_f16=False)
+    prec = module.precision if module.precision is not None else _precision_from_env()
     e = module._engine
     if e is None or e.device != device or B > e.max_batch or T != e.frames or e.precision != prec:
         mb = max(B, e.max_batch if (e is not None and e.device == device and e.frames == T) else 0)

@@ -44,6 +44,26 @@ def test_forward_matches_reference_golden(nets, cuda_device):
         assert err < TOL, (c, err)
 
 
+@pytest.mark.parametrize("prec", [2, 3])
+def test_both_parity_precision_modes(nets, cuda_device, prec):
+    """fp16 hi/lo pairs (2, default) and TF32 hi/lo pairs (3) are both fp32-grade."""
+    m, sd = nets[True]
+    B, T = 4, 144
+    gen = torch.Generator().manual_seed(99)
+    x = torch.randn(B, T, 13, generator=gen)
+    batch = synthetic.trajnet_batch(B, T, 8, control=True)
+    ts = torch.tensor([0, 17, 500, 999])
+    ref = trajnet_oracle.trajnet_forward(sd, x, batch['cond'], ts, batch.get('control_cond'))
+    gb = {k: v.to(cuda_device) for k, v in batch.items()}
+    gb['x_t'] = x.to(cuda_device)
+    m.precision = prec
+    try:
+        y = m(gb, ts.to(cuda_device)).cpu()
+    finally:
+        m.precision = None
+    assert float((y - ref).abs().max()) < TOL
+
+
 @pytest.mark.parametrize("control", [False, True])
 @pytest.mark.parametrize("B,T", [(1, 16), (3, 48), (5, 144), (2, 160)])
 def test_forward_matches_oracle(nets, cuda_device, control, B, T):
