@@ -198,6 +198,8 @@ def main():
     torch.cuda.set_device(dev)
     distributed = world > 1
     if distributed:
+        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     model, sd = build_posenet(dev)

@@ -105,6 +105,46 @@ struct EpiParams {
   int ldr, ldo, lds, act, M, N, out_row_mul, out_row_add, clip_rows, clip_valid, gn_groups, gn_group_size;
 };
 
+// GroupNorm statistics of one 32-column chunk (one row per lane): per (clip, group) sum and sum of squares of the stored
+// values over the rows that contribute, added to e.gn_stats with double atomics (one per warp when the warp's rows all
+// belong to one clip).
+__device__ __forceinline__ void gn_partial_sums(const float (&v)[32], const EpiParams& e, int nb, bool contrib, int clip,
+                                                int lane) {
+  const int gs = e.gn_group_size;
+  const int clip0 = __shfl_sync(0xffffffffu, clip, 0);
+  const bool uniform = __all_sync(0xffffffffu, clip == clip0);
+  for (int jg = 0; jg < 32 && nb + jg < e.N; jg += (gs < 32 ? gs : 32)) {
+    const int span = gs < 32 ? gs : 32;
+    float s1 = 0.0f, s2 = 0.0f;
+    if (contrib) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j >= jg && j < jg + span && nb + j < e.N) {
+          s1 += v[j];
+          s2 += v[j] * v[j];
+        }
+      }
+    }
+    const int g = (nb + jg) / gs;
+    if (uniform) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+      }
+      if (lane == 0) {
+        double* dst = e.gn_stats + (static_cast<int64_t>(clip0) * e.gn_groups + g) * 2;
+        atomicAdd(dst, static_cast<double>(s1));
+        atomicAdd(dst + 1, static_cast<double>(s2));
+      }
+    } else if (contrib) {
+      double* dst = e.gn_stats + (static_cast<int64_t>(clip) * e.gn_groups + g) * 2;
+      atomicAdd(dst, static_cast<double>(s1));
+      atomicAdd(dst + 1, static_cast<double>(s2));
+    }
+  }
+}
+
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
 // (N-tile index fastest, so CTAs running concurrently share the same A rows in L2).
 // Epilogue variants: 0 = bias + residual + fp32 / hi-lo stores (the PoseNet linears), 1 = the same + exact GELU (FFN1),
@@ -317,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (PASSES == 3) ptx::tmem_ld_32x32(taddr + BLOCK_N, raw2);
         const int nb = n0 + c0;
         const bool full = vec_ok && (nb + 32 <= e.N);
-        if (LEAN && e.tma_store && full && (m0 + q * 32 + 32 <= e.M)) {
+        if (e.tma_store && full && (m0 + q * 32 + 32 <= e.M)) {
           // ---- TMA-store path: row-per-thread registers -> swizzled staging tile -> bulk tensor store ----
           ptx::tmem_ld_wait();
           float v[32];
@@ -345,6 +385,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           if (EPI == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (!LEAN) {  // TrajNet: other activations, zeroed pad rows, GroupNorm partial sums
+            if (e.act == kActGelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (e.act == kActSilu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + expf(-v[j]));
+            } else if (e.act == kActMish) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], kActMish);
+            }
+            if (!row_real) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            }
+            if (e.gn_stats != nullptr) gn_partial_sums(v, e, nb, row_real, clip, lane);
           }
           // the previous chunk's bulk store must have finished reading the staging tile
           if (lane == 0) ptx::bulk_wait_read_all();
@@ -444,47 +501,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         }
 
         // ---- GroupNorm partial statistics over real rows ----
-        if (!LEAN && e.gn_stats != nullptr) {
-          const int gs = e.gn_group_size;
-          const bool contrib = row_ok && row_real;
-          const int clip0 = __shfl_sync(0xffffffffu, clip, 0);
-          const bool uniform = __all_sync(0xffffffffu, clip == clip0);
-          for (int jg = 0; jg < 32 && nb + jg < e.N; jg += (gs < 32 ? gs : 32)) {
-            const int span = gs < 32 ? gs : 32;
-            float s1 = 0.0f, s2 = 0.0f;
-            if (contrib) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j >= jg && j < jg + span && nb + j < e.N) {
-                  s1 += v[j];
-                  s2 += v[j] * v[j];
-                }
-              }
-            }
-            const int g = (nb + jg) / gs;
-            if (uniform) {
-#pragma unroll
-              for (int off = 16; off > 0; off >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-              }
-              if (lane == 0) {
-                double* dst = e.gn_stats + (static_cast<int64_t>(clip0) * e.gn_groups + g) * 2;
-                atomicAdd(dst, static_cast<double>(s1));
-                atomicAdd(dst + 1, static_cast<double>(s2));
-              }
-            } else if (contrib) {
-              double* dst = e.gn_stats + (static_cast<int64_t>(clip) * e.gn_groups + g) * 2;
-              atomicAdd(dst, static_cast<double>(s1));
-              atomicAdd(dst + 1, static_cast<double>(s2));
-            }
-          }
-        }
+        if (!LEAN && e.gn_stats != nullptr) gn_partial_sums(v, e, nb, row_ok && row_real, clip, lane);
 
         if (tcount == 0 && warp_idx == 2 && lane == 0 && c0 == 0) stamp(p, 9);
         if (full) {
           // ---- coalesced path through the staging tile ----
-          if (LEAN && e.tma_store) {  // an earlier chunk's bulk store may still be reading the tile
+          if (e.tma_store) {  // an earlier chunk's bulk store may still be reading the tile
             if (lane == 0) ptx::bulk_wait_read_all();
             __syncwarp();
           }
@@ -705,8 +727,7 @@ int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 
 int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind) {
   p->tma_store = 0;
-  const bool plain = p->residual == nullptr && p->out_row_mul == 1 && p->out_row_add == 0 && p->clip_rows == 0 &&
-                     p->gn_stats == nullptr && (p->act == kActNone || p->act == kActGelu);
+  const bool plain = p->residual == nullptr && p->out_row_mul == 1 && p->out_row_add == 0;
   const bool only_out = p->out != nullptr && p->out_hi == nullptr;
   const bool only_pair = p->out == nullptr && p->out_hi != nullptr && kind == kKindF16;
   if (!plain || !(only_out || only_pair)) return 0;

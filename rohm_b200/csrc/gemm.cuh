@@ -83,9 +83,9 @@ struct alignas(64) GemmParams {
   int gn_groups;
   int gn_group_size;  // channels per group
   // TMA-store epilogue (gemm_enable_tma_store): 32 x 32 output chunks go registers -> swizzled shared-memory tile ->
-  // cp.async.bulk.tensor store.  Eligible launches: no residual, identity output row map, no clip mask / GroupNorm
-  // statistics, and either only `out` (fp32) or only an fp16 out_hi/out_lo pair.  Chunks on a ragged M or N edge still
-  // take the per-thread path.
+  // cp.async.bulk.tensor store.  Eligible launches: no residual, identity output row map (not the transposed-conv
+  // phases), and either only `out` (fp32) or only an fp16 out_hi/out_lo pair.  Chunks on a ragged M or N edge still take
+  // the per-thread path.
   CUtensorMap st_out;
   CUtensorMap st_hi;
   CUtensorMap st_lo;

@@ -409,6 +409,10 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
     g.gn_group_size = Cout / kGroups;
   }
   (void)out_compact_T;
+  // fp32-only or fp16-pair-only outputs with the identity row map leave through TMA bulk stores (the transposed-conv phases
+  // and the few convolutions that write both forms keep the per-thread epilogue)
+  if (gemm_enable_tma_store(&g, rows_of(tn, row_level), tn->kind) != 0)
+    return fail(tn->ctx, ROHM_ERR_CUDA, "store tensor map failed for conv '%s'", name.c_str());
   tn->convs[name] = cv;
   return ROHM_OK;
 }

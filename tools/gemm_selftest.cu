@@ -331,6 +331,10 @@ static void case_conv(int B, int T_in, int Tp_in, int Cin, int Cout, int ks, int
   p.out_row_mul = 1, p.out_row_add = 0;
   p.clip_rows = Tp_out, p.clip_valid = T_out;
   p.gn_stats = dstats, p.gn_groups = groups, p.gn_group_size = Cout / groups;
+  if (gemm_enable_tma_store(&p, Mrows, kKindTf32) != 0 || !p.tma_store) {  // masks + statistics through the TMA-store path
+    printf("gemm_enable_tma_store refused the convolution\n");
+    exit(2);
+  }
   CK(launch_gemm(p, Mrows, Cout, block_n, 3, 0));
   CK(cudaDeviceSynchronize());
   auto y = host(dy, (size_t)Mrows * Cout);
