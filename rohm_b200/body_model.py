@@ -27,7 +27,7 @@ class BodyOutput:
 class BodyKernels:
     """One rohm_body handle (device copies of the model + per-call workspace for up to ``max_frames`` frames)."""
 
-    def __init__(self, model, device, max_frames, with_vertices, precision=_lib.PRECISION_TF32X3):
+    def __init__(self, model, device, max_frames, with_vertices, precision=_lib.PRECISION_F16X2):
         self.lib = _lib.load()
         self.ctx = _lib.ctx(device.index)
         self.device, self.max_frames, self.with_vertices = device, int(max_frames), bool(with_vertices)

@@ -32,7 +32,7 @@ constexpr int kJ = 55;        // SMPL-X joints
 constexpr int kBodyJ = 22;    // global + 21 body joints
 constexpr int kBetas = 10;
 constexpr int kPoseFeat = 189;  // (22 - 1) * 9 non-zero pose-corrective features (hands / jaw / eyes are identity)
-constexpr int kBlendK = 224;    // 189 pose features + 10 betas + 1 (template) padded to a multiple of 32
+constexpr int kBlendK = 256;    // 189 pose features + 10 betas + 1 (template), zero-padded to whole K blocks (64 fp16 / 32 TF32)
 constexpr int kMaxBones = 8;    // compressed skinning weights per vertex
 
 __constant__ int c_parents[kJ];
@@ -158,10 +158,10 @@ __global__ void joint_regress_kernel(const float* __restrict__ Jreg, const float
 }
 
 // Blend matrix for the GEMM: Wb[n = v*3 + k][col]: cols [0,189) posedirs[col][n], [189,199) shapedirs[v][k][l],
-// col 199 = v_template[v][k], rest 0; stored as TF32 hi/lo.
+// col 199 = v_template[v][k], rest 0; stored as TF32 hi/lo, or (f16) as fp16 hi/lo of the value times `scale`.
 __global__ void build_blend_kernel(const float* __restrict__ posedirs, const float* __restrict__ sdirs,
                                    const float* __restrict__ vt, int V, int sd_comps, float* __restrict__ hi,
-                                   float* __restrict__ lo, int64_t total) {
+                                   float* __restrict__ lo, int64_t total, int f16, float scale) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int col = static_cast<int>(i % kBlendK);
@@ -172,9 +172,24 @@ __global__ void build_blend_kernel(const float* __restrict__ posedirs, const flo
     else if (col < kPoseFeat + kBetas) v = sdirs[n * sd_comps + (col - kPoseFeat)];
     else if (col == kPoseFeat + kBetas) v = vt[n];
   }
-  const float h = ptx::to_tf32(v);
-  hi[i] = h;
-  lo[i] = v - h;
+  if (f16) {
+    ptx::split_f16(v * scale, reinterpret_cast<__half*>(hi)[i], reinterpret_cast<__half*>(lo)[i]);
+  } else {
+    const float h = ptx::to_tf32(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// one element of a GEMM operand pair: TF32 hi/lo in fp32 containers, or fp16 hi/lo
+__device__ __forceinline__ void store_pair(float* hi, float* lo, int64_t i, float v, int f16) {
+  if (f16) {
+    ptx::split_f16(v, reinterpret_cast<__half*>(hi)[i], reinterpret_cast<__half*>(lo)[i]);
+  } else {
+    const float h = ptx::to_tf32(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
 }
 
 // up to kMaxBones (index, weight) pairs per vertex; overflow flag if a vertex has more non-zeros
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __r
                                                                 const float* __restrict__ Jt, const float* __restrict__ Jd,
                                                                 int N, float* __restrict__ joints, int nj,
                                                                 float* __restrict__ A, float* __restrict__ feat_hi,
-                                                                float* __restrict__ feat_lo) {
+                                                                float* __restrict__ feat_lo, int f16) {
   __shared__ float sW[kFkWarps][kJ][12];   // world transforms [R | t] row-major 3x4
   __shared__ float sJ[kFkWarps][kJ][3];    // rest joints
   __shared__ int sDone[kFkWarps][kJ];
@@ -240,25 +255,17 @@ __global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __r
       if (j > 0 && feat_hi != nullptr) {
         const float pf[9] = {R.c0.x - 1.f, R.c1.x, R.c2.x, R.c0.y, R.c1.y - 1.f, R.c2.y, R.c0.z, R.c1.z, R.c2.z - 1.f};
 #pragma unroll
-        for (int e = 0; e < 9; ++e) {
-          const float hh = ptx::to_tf32(pf[e]);
-          feat_hi[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = hh;
-          feat_lo[static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e] = pf[e] - hh;
-        }
+        for (int e = 0; e < 9; ++e) store_pair(feat_hi, feat_lo, static_cast<int64_t>(n) * kBlendK + (j - 1) * 9 + e, pf[e], f16);
       }
     }
     Rl[h] = R;
     sDone[warp][j] = 0;
   }
-  if (feat_hi != nullptr && lane < kBlendK - kPoseFeat) {
-    const int c = kPoseFeat + lane;  // betas | 1 | zero padding
-    const float v = lane < kBetas ? be[lane] : (lane == kBetas ? 1.0f : 0.0f);
-    const float hh = ptx::to_tf32(v);
-    feat_hi[static_cast<int64_t>(n) * kBlendK + c] = hh;
-    feat_lo[static_cast<int64_t>(n) * kBlendK + c] = v - hh;
-    if (lane + 32 < kBlendK - kPoseFeat) {
-      feat_hi[static_cast<int64_t>(n) * kBlendK + c + 32] = 0.0f;
-      feat_lo[static_cast<int64_t>(n) * kBlendK + c + 32] = 0.0f;
+  if (feat_hi != nullptr) {
+    for (int c = kPoseFeat + lane; c < kBlendK; c += 32) {  // betas | 1 | zero padding
+      const int k = c - kPoseFeat;
+      const float v = k < kBetas ? be[k < kBetas ? k : 0] : (k == kBetas ? 1.0f : 0.0f);
+      store_pair(feat_hi, feat_lo, static_cast<int64_t>(n) * kBlendK + c, v, f16);
     }
   }
   __syncwarp();
@@ -717,6 +724,7 @@ struct rohm_body {
   rohm_ctx* ctx = nullptr;
   DevicePool pool;
   int V = 0, sd_comps = 0, passes = 3;
+  int kind = kKindTf32;  // operand element type of the blend GEMM (kKindF16 in ROHM_PRECISION_F16X2)
   int64_t max_frames = 0;
   float *Jt = nullptr, *Jd = nullptr;
   const float* lbs_w = nullptr;  // dense weights copy
@@ -724,7 +732,7 @@ struct rohm_body {
   int* bone_idx = nullptr;
   float* bone_w = nullptr;
   bool sparse_ok = true;
-  PackedWeight blend;  // [V*3 (padded), 224]
+  PackedWeight blend;  // [V*3 (padded), kBlendK]
   // per-frame workspace
   float *go = nullptr, *bp = nullptr, *betas = nullptr, *transl = nullptr, *A = nullptr, *feat_h = nullptr,
         *feat_l = nullptr, *vposed = nullptr;
@@ -745,7 +753,8 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
   ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
   rohm_body* bd = new (std::nothrow) rohm_body();
   if (!bd) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
-  bd->ctx = ctx, bd->V = num_verts, bd->sd_comps = shape_comps, bd->max_frames = max_frames, bd->passes = precision;
+  bd->ctx = ctx, bd->V = num_verts, bd->sd_comps = shape_comps, bd->max_frames = max_frames, bd->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
+  bd->kind = precision == ROHM_PRECISION_F16X2 ? kKindF16 : kKindTf32;
   ROHM_CUDA(ctx, cudaMemcpyToSymbol(c_parents, parents_host, sizeof(int) * kJ));
   const int V = num_verts;
   const int64_t F = max_frames;
@@ -782,8 +791,21 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
     cudaMemcpy(bd->lbs_w_copy, lbs_weights, sizeof(float) * V * kJ, cudaMemcpyDeviceToDevice);
     compress_weights_kernel<<<(V + 255) / 256, 256>>>(lbs_weights, V, bd->bone_idx, bd->bone_w, overflow);
     const int64_t total = static_cast<int64_t>(bd->blend.Np) * kBlendK;
+    bd->blend.kind = bd->kind;
+    if (bd->kind == kKindF16) {  // one power-of-two scale for the whole matrix: the smallest of its three sources' scales
+      float s1 = 1.0f, s2 = 1.0f, s3 = 1.0f;
+      cudaError_t es = f16_weight_scale(posedirs, static_cast<int64_t>(kPoseFeat) * V * 3, &s1);
+      if (es == cudaSuccess) es = f16_weight_scale(shapedirs, static_cast<int64_t>(V) * 3 * shape_comps, &s2);
+      if (es == cudaSuccess) es = f16_weight_scale(v_template, static_cast<int64_t>(V) * 3, &s3);
+      if (es != cudaSuccess) {
+        delete bd;
+        return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: %s", cudaGetErrorString(es));
+      }
+      bd->blend.scale = fminf(s1, fminf(s2, s3));
+    }
     build_blend_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(posedirs, shapedirs, v_template, V,
-                                                                            shape_comps, bd->blend.hi, bd->blend.lo, total);
+                                                                            shape_comps, bd->blend.hi, bd->blend.lo, total,
+                                                                            bd->kind == kKindF16 ? 1 : 0, bd->blend.scale);
     int h_over = 0;
     cudaError_t e = cudaMemcpy(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
@@ -794,17 +816,18 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
     cudaError_t ea = gemm_init_attributes();
     GemmParams& g = bd->g_blend;
     g = GemmParams{};
-    int rc = make_tmap_2d(&g.a_hi[0], bd->feat_h, F, kBlendK, kBlendK, kGemmBlockM);
-    rc |= make_tmap_2d(&g.a_lo[0], bd->feat_l, F, kBlendK, kBlendK, kGemmBlockM);
-    rc |= make_tmap_2d(&g.b_hi, bd->blend.hi, bd->blend.Np, kBlendK, kBlendK, 128);
-    rc |= make_tmap_2d(&g.b_lo, bd->blend.lo, bd->blend.Np, kBlendK, kBlendK, 128);
+    int rc = make_tmap_2d(&g.a_hi[0], bd->feat_h, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
+    rc |= make_tmap_2d(&g.a_lo[0], bd->feat_l, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
+    rc |= make_tmap_2d(&g.b_hi, bd->blend.hi, bd->blend.Np, kBlendK, kBlendK, 128, 1, bd->kind);
+    rc |= make_tmap_2d(&g.b_lo, bd->blend.lo, bd->blend.Np, kBlendK, kBlendK, 128, 1, bd->kind);
     if (rc != 0 || ea != cudaSuccess) {
       delete bd;
       return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: GEMM setup failed (%d)", rc);
     }
-    g.num_segs = 1, g.seg_kblocks[0] = kBlendK / kGemmBlockK, g.seg_row_mul[0] = 1;
+    g.num_segs = 1, g.seg_kblocks[0] = kBlendK / gemm_block_k(bd->kind), g.seg_row_mul[0] = 1;
+    g.acc_scale = 1.0f / bd->blend.scale;
     g.out = bd->vposed, g.ldo = bd->blend.Np, g.N = bd->blend.Np, g.out_row_mul = 1;  // padded columns are exact zeros
-    if (gemm_enable_tma_store(&g, F, kKindTf32) != 0) {  // 32 x 32 fp32 chunks leave through TMA bulk stores
+    if (gemm_enable_tma_store(&g, F, bd->kind) != 0) {  // 32 x 32 fp32 chunks leave through TMA bulk stores
       delete bd;
       return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: store tensor map failed");
     }
@@ -837,12 +860,12 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
   const bool verts = vertices != nullptr;
   fk_full_kernel<<<static_cast<unsigned>((N + kFkWarps - 1) / kFkWarps), 32 * kFkWarps, 0, st>>>(
       global_orient, body_pose, betas, transl, bd->Jt, bd->Jd, static_cast<int>(N), joints, num_joints,
-      verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr);
+      verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr, bd->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(ctx, cudaGetLastError());
   if (verts) {
     GemmParams g = bd->g_blend;
     g.M = static_cast<int>(N);
-    ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 128, bd->passes, st));
+    ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 128, bd->passes, st, false, bd->kind));
     dim3 grid((bd->V + 255) / 256, static_cast<unsigned>(N));
     if (bd->sparse_ok)
       skin_kernel<<<dim3((bd->V + 255) / 256, static_cast<unsigned>((N + kSkinFrames - 1) / kSkinFrames)), 256, 0, st>>>(
