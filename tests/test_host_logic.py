@@ -146,3 +146,23 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.rohm_version() >= 100
+
+
+def test_precision_modes_env_and_header_agree(monkeypatch):
+    """ROHM_B200_PRECISION parsing and the enum values shared between include/rohm_b200.h and the ctypes layer."""
+    from rohm_b200.posenet import _precision_from_env
+    header = open(os.path.join(ROOT, "include", "rohm_b200.h")).read()
+    for name, const in (("ROHM_PRECISION_TF32X3", _lib.PRECISION_TF32X3), ("ROHM_PRECISION_F16X2", _lib.PRECISION_F16X2),
+                        ("ROHM_PRECISION_TF32", _lib.PRECISION_TF32)):
+        m = re.search(name + r"\s*=\s*(\d+)", header)
+        assert m and int(m.group(1)) == const, name
+    monkeypatch.delenv("ROHM_B200_PRECISION", raising=False)
+    assert _precision_from_env() == _lib.PRECISION_F16X2                      # default: fp16 hi/lo pairs
+    assert _precision_from_env(supports_f16=False) == _lib.PRECISION_TF32X3  # engines without an fp16 path
+    for text, want in (("tf32x3", _lib.PRECISION_TF32X3), ("F16X2", _lib.PRECISION_F16X2), ("tf32", _lib.PRECISION_TF32),
+                       ("fast", _lib.PRECISION_TF32)):
+        monkeypatch.setenv("ROHM_B200_PRECISION", text)
+        assert _precision_from_env() == want
+    monkeypatch.setenv("ROHM_B200_PRECISION", "bf16")
+    with pytest.raises(_lib.RohmB200Error):
+        _precision_from_env()
