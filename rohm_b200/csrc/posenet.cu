@@ -779,7 +779,6 @@ struct AttnTcParams {
   int S, D, H;
   float scale;
   unsigned long long* debug_ts;  // developer instrumentation: CTA 0 records %globaltimer at 12 milestones
-  int stages;  // developer bisection aid (ROHM_B200_ATTN_STAGES): 1 = loads only, 2 = + S MMAs, 3 = + softmax, 4 = everything
 };
 constexpr int kAtKeys = 160;                  // padded key count = UMMA N of the S product
 constexpr uint32_t kAtColS = 32, kAtColO0 = 32 + 2 * kAtKeys;  // TMEM column map (see above)
@@ -807,9 +806,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   const int S = p.S;
   const int ntiles = S > 128 ? 2 : 1;
   const int row0 = b * S;  // first token row of this clip
-  const bool full = p.stages == 4;
-  const bool run_v = p.stages == 3 || p.stages == 4 || p.stages == 6;
-  const bool run_p2 = p.stages == 3 || p.stages == 4 || p.stages == 5;
   if (threadIdx.x == 0) at_stamp(p, 0);
 
   if (warp_idx == 0 && lane == 0) {
@@ -842,7 +838,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
           ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h * 128 + kc * 64, row0);
         }
       }
-      if (!run_v) goto done;
       // V lands on top of K: wait until every S MMA has read it
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
       ptx::mbar_expect_tx(&v_full, 4 * kAtQKBuf);
@@ -851,7 +846,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         for (int kc = 0; kc < 2; ++kc)
           ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h * 128 + kc * 64, row0);
       }
-      if (!full) ptx::mbar_wait(&v_full, 0);
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
@@ -860,7 +854,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       ptx::mbar_wait(&qk_full, 0);
       at_stamp(p, 2);
       ptx::tc_fence_after_sync();
-      if (p.stages < 2) goto done;
       for (int t = 0; t < ntiles; ++t) {
         const uint32_t acc = tmem_base + kAtColS + static_cast<uint32_t>(t * kAtKeys);
 #pragma unroll
@@ -877,7 +870,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         }
         ptx::mma_commit(&s_full[t]);
       }
-      if (!full) goto done;
       ptx::mbar_wait(&v_full, 0);
       at_stamp(p, 4);
       for (int t = 0; t < ntiles; ++t) {
@@ -911,10 +903,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     const int row = q * 32 + lane;
     const int grow = t * 128 + row;  // token index inside the clip
     const bool valid = grow < S;
-    if (t < ntiles && p.stages >= 2 && t * 128 + q * 32 >= S) {
+    if (t < ntiles && t * 128 + q * 32 >= S) {
       // no real query row in this warp's 32 lanes (the tail of tile 1): nothing to compute, just release the MMA warp
-      if (run_p2 && lane == 0) ptx::mbar_arrive(&p_ready[t]);
-    } else if (t < ntiles && p.stages >= 2) {
+      if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
+    } else if (t < ntiles) {
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
       constexpr int NC = kAtKeys / 32;
@@ -937,7 +929,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         if (c + 1 < NC) ptx::tmem_ld_wait();
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      if (!run_p2) goto done;
       if (t == 0 && warp_idx == 2 && lane == 0) at_stamp(p, 5);
       // the P buffers overlap Q and K: every S MMA must have completed
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
@@ -985,7 +976,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
-      if (!full) goto done;
 
       // output: O / sum -> fp16 hi/lo rows of ctx.  Full 32-row groups go through a SWIZZLE_64B staging tile (carved out
       // of the first P buffer, whose tile-0 rows are dead once the O MMAs of tile 0 have completed) and TMA stores; a
@@ -1045,7 +1035,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 8 + 3 * t);
     }
   }
-done:
   __syncthreads();
   if (threadIdx.x == 0) at_stamp(p, 12);
   if (warp_idx == 1) {
@@ -1297,8 +1286,6 @@ static cudaError_t launch_attention_mma(rohm_posenet* pn, int B, int S, float sc
 static int run_attention_tc(rohm_posenet* pn, int B, int S, cudaStream_t st) {
   AttnTcParams prm = pn->attn_tc;
   prm.S = S;
-  prm.stages = 4;
-  if (const char* env = getenv("ROHM_B200_ATTN_STAGES")) prm.stages = atoi(env);
   static unsigned long long* d_ts = nullptr;
   static int ts_calls = 0;
   const bool want_ts = getenv("ROHM_B200_ATTN_TS") != nullptr && ++ts_calls == 12;  // a warm call, outside graph capture
