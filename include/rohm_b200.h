@@ -39,7 +39,7 @@ typedef enum {
 typedef enum {
   ROHM_PRECISION_TF32X3 = 3, /* error-compensated TF32 hi/lo pairs: fp32-grade results (parity mode) */
   ROHM_PRECISION_F16X2 = 2,  /* error-compensated fp16 hi/lo pairs: the same 2 x 11 significant bits per value in half
-                                the bytes (fp32-grade results, PoseNet default; activations must stay below 1.3e5) */
+                                the bytes (fp32-grade results, the default of every engine; activations must stay below 1.3e5) */
   ROHM_PRECISION_TF32 = 1    /* single-pass TF32: ~1e-3 relative (fast mode) */
 } rohm_precision;
 

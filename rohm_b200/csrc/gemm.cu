@@ -1,4 +1,4 @@
-// tcgen05 / TMA implementation of the segmented-A 3xTF32 GEMM declared in gemm.cuh.
+// tcgen05 / TMA implementation of the segmented-A hi/lo-pair GEMM declared in gemm.cuh.
 #include "gemm.cuh"
 #include "ptx.cuh"
 

@@ -1,22 +1,24 @@
-// Segmented-A GEMM on tcgen05 tensor cores with error-compensated TF32 ("3xTF32") for fp32-grade results.
+// Segmented-A GEMM on tcgen05 tensor cores with error-compensated hi/lo operand pairs for fp32-grade results.
 //
 //   C[m, n] = epilogue( sum_s sum_k A_s[m * row_mul_s + row_shift_s, k] * W[n, koff_s + k] )
 //
-// * A is a list of up to kMaxSegs "segments": each is a row-major fp32 matrix (given as a hi/lo TF32 split
-//   pair) read through its own TMA descriptor with a row shift.  One segment = a plain linear layer
-//   (PoseNet, reference model/posenet.py:59-72).  Several segments = the taps of a Conv1d / the halves of a
-//   channel concat (TrajNet, reference model/heads.py:90-106, model/trajnet.py:222-271): a k-tap convolution
-//   over channels-last activations is k shifted copies of the same matrix, so no im2col buffer ever exists.
-//   Out-of-range rows/columns are zero-filled by TMA, which is exactly Conv1d's zero padding.
-// * W is [N, K_total] K-major (torch Linear layout), also a hi/lo pair.
-// * PASSES == 3: D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (drops only the lo*lo term, ~2^-22 relative).
+// * A is a list of up to kMaxSegs "segments": each is a row-major matrix (given as a hi/lo pair: fp16 halves or TF32
+//   values in fp32 containers, see GemmKind) read through its own TMA descriptor with a row shift.  One segment = a plain
+//   linear layer (PoseNet, reference model/posenet.py:59-72).  Several segments = the taps of a Conv1d / the halves of a
+//   channel concat (TrajNet, reference model/heads.py:90-106, model/trajnet.py:222-271): a k-tap convolution over
+//   channels-last activations is k shifted copies of the same matrix, so no im2col buffer ever exists.  Out-of-range
+//   rows/columns are zero-filled by TMA, which is exactly Conv1d's zero padding.
+// * W is [N, K_total] K-major (torch Linear layout), also a hi/lo pair.  The roles are symmetric: the weight may just as
+//   well be the A operand (transposed products, bias_per_row).
+// * PASSES == 3: D += A_lo*W_hi + A_hi*W_lo + A_hi*W_hi  (drops only the lo*lo term, ~2^-22 relative).
 //   PASSES == 1: D += A_hi*W_hi (plain TF32, ~2^-11 relative) -- the documented fast mode.
 //
 // Kernel shape: persistent, grid = min(#tiles, #SMs), 128 x BLOCK_N output tiles, 320 threads per CTA:
-//   warp 0   : TMA producer (one elected lane)        smem ring: full[]/empty[] mbarriers
+//   warp 0   : TMA producer (one elected lane)        smem ring of 64 KB stages: full[]/empty[] mbarriers
 //   warp 1   : TMEM allocator + tcgen05.mma issuer    two accumulator stages in TMEM (tmem_full[]/tmem_empty[])
-//   warps 2-9: epilogue (tcgen05.ld -> bias/act/residual -> global, optional hi/lo split for the next GEMM),
-//              draining tile i while the MMA warp already accumulates tile i+1
+//   warps 2-9: epilogue (tcgen05.ld -> scale / bias / activation / row mask / GroupNorm sums -> swizzled smem tile ->
+//              TMA bulk store, or per-thread stores with a residual), draining tile i while the MMA warp already
+//              accumulates tile i+1
 #pragma once
 #include <cstdint>
 #include <cuda.h>

@@ -3,12 +3,14 @@
 //
 // Token-major layout: every activation is a row-major [B*S, width] matrix, S = T + 1 tokens per clip (token 0 is the
 // timestep embedding), clips contiguous.  All linear layers run on the tcgen05 GEMM (gemm.cu); operands that feed a
-// GEMM are kept as TF32 hi/lo pairs written by the producing kernel, so no separate conversion pass exists.
+// tensor-core product are kept as hi/lo pairs (fp16 halves by default, TF32 in the tf32 modes) written by the
+// producing kernel's epilogue, so no separate conversion pass exists.
 //
-//   x_t [B,C,1,T] --pack--> A_in --GEMM(+bias+cond_embed+pe)--> X  (token 0 <- time MLP)
-//   8 x { X --GEMM--> QKV --attention--> CTX --GEMM(+bias+X)--> Y --LN--> X
-//         X --GEMM(+bias,GELU)--> H --GEMM(+bias+X)--> Y --LN--> X }
+//   x_t [B,C,1,T] --pack--> A_in --GEMM(+bias+cond_embed+pe)--> X  (token 0 <- time-embedding table gather)
+//   8 x { X --GEMM--> Q|K|V --attention (tcgen05: S = QK^T, softmax from TMEM, O = PV)--> CTX --GEMM(+bias)--> Y
+//         --LN(Y + X)--> X --GEMM(+bias,GELU)--> H --GEMM(+bias)--> Y --LN(Y + X)--> X }
 //   X --GEMM--> OUT_tok --unpack(+copy cond[:, :traj])--> out [B,C,1,T]
+// One forward = 61 launches, replayed as one CUDA graph with programmatic dependent launch along the chain.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
