@@ -1,0 +1,127 @@
+"""CPU models of the arithmetic the CUDA kernels rely on (no GPU, no library calls): the fp16 hi/lo operand pairs with
+three products and the branch-free erf GELU whose coefficients live in rohm_b200/csrc/gemm.cu.
+These pin the accuracy claims and the constants in the kernel source against float64."""
+import math
+import os
+import re
+
+import numpy as np
+from scipy.special import erf
+
+from helpers import ROOT
+
+f16, f32, f64 = np.float16, np.float32, np.float64
+
+
+def split_f16(x):
+    """ptx::split_f16: hi = rn_f16(clamp(x, +-65504)), lo = rn_f16(x - hi) (both as float32 values of halves)."""
+    x = np.asarray(x, dtype=f32)
+    hi = np.clip(x, -65504.0, 65504.0).astype(f16)
+    lo = (x - hi.astype(f32)).astype(f16)
+    return hi.astype(f32), lo.astype(f32)
+
+
+def weight_scale(w):
+    """f16_weight_scale: 2^s with max|w| 2^s in [2^13, 2^14)."""
+    wmax = float(np.abs(w).max())
+    if wmax == 0.0:
+        return 1.0
+    _, e2 = math.frexp(wmax)
+    return math.ldexp(1.0, max(-100, min(100, 14 - e2)))
+
+
+def gemm_f16x2(a, w):
+    """D = A_lo W_hi^T + A_hi W_lo^T (small terms, own accumulator) + A_hi W_hi^T, products exact, fp32 accumulation."""
+    s = weight_scale(w)
+    ah, al = split_f16(a)
+    wh, wl = split_f16((w * f32(s)).astype(f32))
+    # fp16 x fp16 products are exact in fp32; the accumulation is modelled in float64 and rounded once per accumulator
+    # (the tensor core's fp32 accumulation error is measured on the GPU, not modelled here)
+    main = (ah.astype(f64) @ wh.astype(f64).T).astype(f32)
+    cross = (al.astype(f64) @ wh.astype(f64).T + ah.astype(f64) @ wl.astype(f64).T).astype(f32)
+    return ((main + cross) * f32(1.0 / s)).astype(f32)
+
+
+def test_weight_scale_places_the_largest_weight_in_the_upper_fp16_range():
+    rng = np.random.default_rng(0)
+    for scale in (1e-6, 3e-3, 0.02, 1.0, 77.0, 4e4):
+        w = (rng.standard_normal((64, 48)) * scale).astype(f32)
+        s = weight_scale(w)
+        top = float(np.abs(w).max()) * s
+        assert 2.0 ** 13 <= top < 2.0 ** 14
+        assert math.log2(s) == round(math.log2(s))  # a power of two: undone exactly by acc_scale
+    assert weight_scale(np.zeros((4, 4), f32)) == 1.0
+
+
+def test_pair_split_keeps_22_bits_and_degrades_gracefully():
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(200000) * 3).astype(f32)
+    hi, lo = split_f16(x)
+    rel = np.abs((hi.astype(f64) + lo.astype(f64)) - x.astype(f64)) / np.maximum(np.abs(x.astype(f64)), 1e-30)
+    assert rel[np.abs(x) > 0.2].max() < 2.0 ** -21          # both halves in the normal range: 2 x 11 bits
+    tiny = (rng.standard_normal(10000) * 1e-4).astype(f32)   # lo halves subnormal: bounded absolute error instead
+    hi, lo = split_f16(tiny)
+    assert np.abs((hi.astype(f64) + lo.astype(f64)) - tiny.astype(f64)).max() <= 2.0 ** -25
+    big = np.array([70000.0, -120000.0, 131000.0], dtype=f32)  # beyond fp16's largest finite value
+    hi, lo = split_f16(big)
+    assert np.all(np.isfinite(hi)) and np.all(np.isfinite(lo))
+    assert np.abs((hi + lo) - big).max() <= 64.0               # still 11+ bits; the documented range limit is 1.3e5
+
+
+def test_three_product_gemm_is_fp32_grade():
+    rng = np.random.default_rng(2)
+    for K, a_scale, w_scale in ((512, 1.0, 1 / math.sqrt(512)), (1024, 30.0, 0.02), (320, 1e-3, 0.1)):
+        a = (rng.standard_normal((96, K)) * a_scale).astype(f32)
+        w = (rng.standard_normal((80, K)) * w_scale).astype(f32)
+        ref = a.astype(f64) @ w.astype(f64).T
+        got = gemm_f16x2(a, w).astype(f64)
+        fp32_ref = (a @ w.T).astype(f64)
+        bound = np.abs(a.astype(f64)) @ np.abs(w.astype(f64)).T  # sum |a||w|: the natural scale of the rounding error
+        # only lo*lo (2^-22 relative per product) is dropped; activations whose lo half is subnormal (|a| < 0.12) add an
+        # absolute 2^-25 per element instead (the 1e-3-scaled case)
+        floor = 2.0 ** -25 * np.abs(w.astype(f64)).sum(axis=1)[None, :]
+        assert (np.abs(got - ref) / (2.0 ** -20 * bound + floor)).max() < 1.0
+        if a_scale >= 1.0:
+            assert np.abs(got - ref).max() <= 4.0 * np.abs(fp32_ref - ref).max()  # same class as a plain fp32 GEMM
+            # a single product (what a one-pass fp16 / TF32 tensor-core GEMM does) is orders of magnitude worse
+            ah, _ = split_f16(a)
+            wh, _ = split_f16(w)
+            one_pass = ah.astype(f64) @ wh.astype(f64).T
+            assert np.abs(one_pass - ref).max() > 100.0 * np.abs(got - ref).max()
+
+
+def _gelu_coefficients():
+    src = open(os.path.join(ROOT, "rohm_b200", "csrc", "gemm.cu")).read()
+    body = src[src.index("__device__ __forceinline__ float gelu_erf(float x)"):]
+    body = body[:body.index("struct EpiParams")]
+    small = [float(v) for v in re.findall(r"r = (?:fmaf\(r, s, )?(-?\d\.\d+e[+-]\d+)f", body)]
+    large = [float(v) for v in re.findall(r"q = (?:fmaf\(q, t, )?(-?\d\.\d+e[+-]\d+)f", body)]
+    assert len(small) == 7 and len(large) == 8, (small, large)
+    return small, large  # highest degree first, as the Horner chains in the kernel evaluate them
+
+
+def test_branch_free_erf_gelu_constants_match_float64():
+    small, large = _gelu_coefficients()
+
+    def fma(a, b, c):
+        return (a.astype(f64) * b.astype(f64) + np.asarray(c, dtype=f64)).astype(f32)
+
+    x = np.concatenate([np.linspace(-12.0, 12.0, 400001), np.random.default_rng(3).standard_normal(200000) * 3]).astype(f32)
+    z = (x * f32(0.70710678118654752440)).astype(f32)
+    s = (z * z).astype(f32)
+    r = np.full_like(z, f32(small[0]))
+    for c in small[1:]:
+        r = fma(r, s, f32(c))
+    e_small = fma(r, z, z)
+    t = np.minimum(np.abs(z), f32(4.0)).astype(f32)
+    q = np.full_like(z, f32(large[0]))
+    for c in large[1:]:
+        q = fma(q, t, f32(c))
+    e_large = np.copysign((f32(1.0) - np.exp(q.astype(f64)).astype(f32)).astype(f32), z)
+    e = np.where(np.abs(z) < f32(1.0), e_small, e_large).astype(f32)
+    h = (f32(0.5) * x).astype(f32)
+    gelu = fma(h, e, h).astype(f64)
+    x64 = x.astype(f64)
+    ref = 0.5 * x64 * (1.0 + erf(x64 / math.sqrt(2.0)))
+    assert np.abs(gelu - ref).max() < 4e-7  # tools/fit_gelu_erf.py reports 3.0e-7 (fp32 erff formulation: 4.5e-7)
+    assert gelu[x > 8.0].tolist() == x64[x > 8.0].tolist() and np.all(gelu[x < -8.0] == 0.0)  # exact saturation
