@@ -205,11 +205,70 @@ ROHM_API int rohm_body_forward(rohm_body* bd, const float* global_orient, const 
 ROHM_API int rohm_body_from_repr(rohm_body* bd, const float* x, const float* mean, const float* stdv, int B, int T,
                                  float* joints, int num_joints, float* vertices, void* stream);
 
+/* The same with an explicit layout: channels_last = 0 -> x is [B,294,1,T] (PoseNet tensors); 1 -> x is [B,T,294] (the
+ * drivers' tensors, test_amass_full.py:279-293, 386-428). */
+ROHM_API int rohm_body_from_repr_layout(rohm_body* bd, const float* x, int channels_last, const float* mean,
+                                        const float* stdv, int B, int T, float* joints, int num_joints, float* vertices,
+                                        void* stream);
+
 /* PoseNet.guide_skating_with_smpl(compute_grad='x_0'): grad [B,294,1,T] = d(-(loss_smpl + loss_abs))/d x0 with the
  * channels [0,22) and the 4 contact channels zero.  Analytic VJP (no autograd); all-zero if nothing skates.
  * loss_out: optional device float[4] = {sum_abs, count_abs, sum_smpl, count_smpl}. */
 ROHM_API int rohm_skating_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
                                    float* grad, float* loss_out, void* stream);
+
+/* PoseNet.guide_2d_projection_with_smpl(compute_grad='x_0') (model/posenet.py:260-317, utils/other_utils.py:150-185):
+ * grad [B,294,1,T] = d(-loss_2d)/d x0, loss_2d = mean over (clip, frame, 10 selected joints, 2) of
+ * |perspective_projection(camera <- scene <- canonical joints) - keypoints| * confidence; channels [0,22) and the 4 contact
+ * channels zero.  cam_affine [B,12]: rows of the 3x4 map canonical -> camera coordinates per clip
+ * (inv(cam_R) (inv(transf_matrix) p - cam_t)); focal, center [B,2]; keypoints_2d [B, kp_frames >= T, 22, 3] = (u, v, conf).
+ * Analytic VJP through the 22-joint kinematic tree (no autograd).  loss_out: optional device float = the un-normalised sum. */
+ROHM_API int rohm_projection_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                      const float* cam_affine, const float* focal, const float* center,
+                                      const float* keypoints_2d, int kp_frames, float* grad, float* loss_out,
+                                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Either side of the sampling loops: the drivers' inter-round glue and representation recovery, on the device
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* test_amass_full.py:268-311 (per-clip host loop in the reference): TrajNet output traj_out [B,T,traj_dim] (z-scored,
+ * traj_dim = 13 for repr_abs_only else <= 22) is scattered into repr_clean [B,T,294] -> composite_out [B,T,294]
+ * (z-scored with the trajectory dataset's mean/std) -> SMPL-X joints (rot6d -> axis-angle -> FK) -> get_repr_smplx
+ * (data_loaders/motion_representation.py:187-282: forward direction, root quaternion incl. the first-NaN repair, velocities,
+ * global-orient 6-D / angular velocity, translation) -> traj_full_out [B,T-1,22], z-scored with the pose dataset's stats. */
+ROHM_API int rohm_traj_glue(rohm_body* bd, const float* traj_out, int traj_dim, const float* repr_clean,
+                            const float* traj_mean, const float* traj_std, const float* pose_mean, const float* pose_std,
+                            int B, int T, float* composite_out, float* traj_full_out, void* stream);
+
+/* The last stage of rohm_traj_glue on its own: get_repr_smplx's trajectory block (motion_representation.py:187-282) from
+ * joints [B,T,22,3], global-orient axis-angles [B*T,3] and translations [B*T,3] -> traj_full_out [B,T-1,22], z-scored with
+ * mean/stdv (the first 22 entries are read). */
+ROHM_API int rohm_traj_repr_from_joints(rohm_ctx* ctx, const float* joints, const float* global_orient_aa,
+                                        const float* transl, const float* mean, const float* stdv, int B, int T,
+                                        float* traj_full_out, void* stream);
+
+/* test_amass_full.py:256-258: control_cond [B,T,cond_feats] from the PoseNet output pose_out [B,traj_feats+cond_feats,1,Tp]
+ * (frames [0,Tp) copied, frames [Tp,T) repeat frame Tp-1). */
+ROHM_API int rohm_pose_to_control_cond(rohm_ctx* ctx, const float* pose_out, int B, int Tp, int T, int traj_feats,
+                                       int cond_feats, float* control_cond, void* stream);
+
+/* test_amass_full.py:320-370: PoseNet condition cond_out [B,294,1,Tp] = src (channel-major [B,294,1,src_T] or channels-last
+ * [B,src_T,294]) with channels [0,22) replaced by traj_full [B,Tp,22] (NULL keeps src) and channels >= 22 zeroed where
+ * chan_keep[c] == 0 (294 bytes, NULL = keep all: the 'lower' / 'upper' joint masks), where frame_lo[b] <= t < frame_hi[b]
+ * (int [B], NULL = none: the 'full' scheme) and, with zero_contact, in the 4 contact channels. */
+ROHM_API int rohm_build_pose_cond(rohm_ctx* ctx, const float* src, int src_channel_major, int src_T, const float* traj_full,
+                                  const unsigned char* chan_keep, const int* frame_lo, const int* frame_hi,
+                                  int zero_contact, int B, int Tp, float* cond_out, void* stream);
+
+/* rot6d_to_rotmat (quaternion.py:482-501) and rotation_matrix_to_angle_axis (konia_transform.py:317-340 -> :350-444 ->
+ * :561-631) on n 6-D rotations: aa [n,3] and/or rotmat [n,9] (row-major), either may be NULL. */
+ROHM_API int rohm_rot6d_to_aa(rohm_ctx* ctx, const float* rot6d, int64_t n, float* aa, float* rotmat, void* stream);
+
+/* recover_from_repr_smpl(recover_mode='joint_abs_traj' | 'joint_rel_traj') (motion_representation.py:285-371) on a z-scored
+ * representation in either layout -> joints [B,T,22,3]. */
+ROHM_API int rohm_joints_from_traj(rohm_ctx* ctx, const float* x, int channels_last, const float* mean, const float* stdv,
+                                   int B, int T, int relative, float* joints, void* stream);
 
 #ifdef __cplusplus
 }

@@ -77,14 +77,19 @@ class BodyKernels:
         _lib.check(rc, self.ctx)
         return joints, verts
 
-    def from_repr(self, x, mean, std, want_vertices, num_joints=22):
-        """x: normalised [B, 294, 1, T] -> joints [B, T, num_joints, 3] (+ vertices [B, T, V, 3])."""
-        B, _, _, T = x.shape
+    def from_repr(self, x, mean, std, want_vertices, num_joints=22, channels_last=False):
+        """x: normalised [B, 294, 1, T] (or [B, T, 294] with channels_last) -> joints [B, T, num_joints, 3]
+        (+ vertices [B, T, V, 3])."""
+        if channels_last:
+            B, T, _ = x.shape
+        else:
+            B, _, _, T = x.shape
         joints = torch.empty(B * T, num_joints, 3, device=self.device)
         verts = torch.empty(B * T, self.V, 3, device=self.device) if want_vertices else None
-        rc = self.lib.rohm_body_from_repr(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(mean.data_ptr()),
-                                          C.c_void_p(std.data_ptr()), B, T, C.c_void_p(joints.data_ptr()), num_joints,
-                                          C.c_void_p(verts.data_ptr() if verts is not None else 0), self._stream())
+        rc = self.lib.rohm_body_from_repr_layout(self.handle, C.c_void_p(x.data_ptr()), int(bool(channels_last)),
+                                                 C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), B, T,
+                                                 C.c_void_p(joints.data_ptr()), num_joints,
+                                                 C.c_void_p(verts.data_ptr() if verts is not None else 0), self._stream())
         _lib.check(rc, self.ctx)
         joints = joints.reshape(B, T, num_joints, 3)
         return (joints, verts.reshape(B, T, self.V, 3)) if want_vertices else joints
@@ -98,6 +103,33 @@ class BodyKernels:
                                             C.c_void_p(loss.data_ptr() if loss is not None else 0), self._stream())
         _lib.check(rc, self.ctx)
         return (grad, loss) if want_loss else grad
+
+
+    def projection_guidance(self, x0, mean, std, cam_affine, focal, center, keypoints_2d, want_loss=False):
+        """d(-loss_2d)/dx0 of guide_2d_projection_with_smpl (reference posenet.py:260-317): x0 [B,294,1,T] normalised,
+        cam_affine [B,3,4] canonical -> camera, focal / center [B,2], keypoints_2d [B,>=T,22,3]."""
+        B, _, _, T = x0.shape
+        grad = torch.empty_like(x0)
+        loss = torch.empty(1, device=self.device) if want_loss else None
+        rc = self.lib.rohm_projection_guidance(
+            self.handle, C.c_void_p(x0.data_ptr()), C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), B, T,
+            C.c_void_p(cam_affine.data_ptr()), C.c_void_p(focal.data_ptr()), C.c_void_p(center.data_ptr()),
+            C.c_void_p(keypoints_2d.data_ptr()), int(keypoints_2d.shape[1]), C.c_void_p(grad.data_ptr()),
+            C.c_void_p(loss.data_ptr() if loss is not None else 0), self._stream())
+        _lib.check(rc, self.ctx)
+        return (grad, loss) if want_loss else grad
+
+    def traj_glue(self, traj_out, repr_clean, traj_mean, traj_std, pose_mean, pose_std):
+        """test_amass_full.py:268-311 on the device: -> (composite [B,T,294], traj_full [B,T-1,22])."""
+        B, T, D = traj_out.shape
+        composite = torch.empty(B, T, 294, device=self.device)
+        traj_full = torch.empty(B, T - 1, 22, device=self.device)
+        rc = self.lib.rohm_traj_glue(self.handle, C.c_void_p(traj_out.data_ptr()), D, C.c_void_p(repr_clean.data_ptr()),
+                                     C.c_void_p(traj_mean.data_ptr()), C.c_void_p(traj_std.data_ptr()),
+                                     C.c_void_p(pose_mean.data_ptr()), C.c_void_p(pose_std.data_ptr()), B, T,
+                                     C.c_void_p(composite.data_ptr()), C.c_void_p(traj_full.data_ptr()), self._stream())
+        _lib.check(rc, self.ctx)
+        return composite, traj_full
 
 
 def kernels_for(model, device, frames, with_vertices):
@@ -125,10 +157,17 @@ class BodyModel(nn.Module):
         self._handle = None
 
     @staticmethod
-    def create(body_model_path='', device=None, seed=0):
-        """Loads ``<path>/smplx/SMPLX_NEUTRAL.npz`` when it exists (official file layout), otherwise builds the
-        seeded synthetic SMPL-X-shaped model (tests / benchmarks)."""
+    def create(body_model_path='', device=None, seed=0, synthetic_ok=None):
+        """Loads ``<path>/smplx/SMPLX_NEUTRAL.npz`` (official file layout).  The seeded synthetic SMPL-X-shaped model
+        (tests / benchmarks; NOT a human body) is built only on an explicit opt-in: ``body_model_path=''`` (the
+        constructor default) or ``synthetic_ok=True``.  A non-empty path without the model file raises -- guiding the
+        sampler with a made-up body would be a silent wrong answer."""
         npz = os.path.join(body_model_path or '', 'smplx', 'SMPLX_NEUTRAL.npz')
+        if body_model_path and not os.path.exists(npz) and not synthetic_ok:
+            raise RohmB200Error(
+                f"BodyModel.create: {npz} not found.  Pass the directory that contains smplx/SMPLX_NEUTRAL.npz (the "
+                "official SMPL-X download), or body_model_path='' / synthetic_ok=True to opt in to the synthetic "
+                "SMPL-X-shaped test model.")
         if body_model_path and os.path.exists(npz):
             d = np.load(npz, allow_pickle=True)
             shapedirs = np.concatenate([d['shapedirs'][:, :, :10], d['shapedirs'][:, :, 300:310]], axis=-1)
@@ -145,6 +184,32 @@ class BodyModel(nn.Module):
         m = BodyModel(tensors)
         return m.to(device) if device is not None else m
 
+    # smplx's own buffer names -> ours, for checkpoints saved from a reference PoseNet (its state dict contains the whole
+    # body model under ``smplx_model.*``, reference posenet.py:57)
+    def load_smplx_state(self, sd):
+        """Adopts the body-model tensors found in a ``smplx_model.*`` state-dict slice (real smplx naming: v_template,
+        shapedirs [V,3,10] + expr_dirs [V,3,10], posedirs, J_regressor, lbs_weights, parents); other keys (faces,
+        default pose parameters, landmark tables) are not needed by RoHM's calls and are ignored.  Returns the list of
+        adopted names."""
+        took = []
+        if "shapedirs" in sd:
+            sdirs = sd["shapedirs"].to(torch.float32)
+            if "expr_dirs" in sd and sdirs.shape[-1] == 10:
+                sdirs = torch.cat([sdirs, sd["expr_dirs"].to(torch.float32)], dim=-1)
+            self.shapedirs = sdirs.to(self.shapedirs.device).contiguous()
+            took.append("shapedirs")
+        for name in ("v_template", "posedirs", "J_regressor", "lbs_weights"):
+            if name in sd:
+                setattr(self, name, sd[name].to(device=getattr(self, name).device, dtype=torch.float32).contiguous())
+                took.append(name)
+        if "parents" in sd:
+            par = sd["parents"].to(torch.long).clone()
+            par[0] = -1
+            self.parents = par.to(self.parents.device)
+            took.append("parents")
+        self.__dict__.pop("_rohm_kernels", None)
+        return took
+
     def as_dict(self):
         return {"v_template": self.v_template, "shapedirs": self.shapedirs, "posedirs": self.posedirs,
                 "J_regressor": self.J_regressor, "lbs_weights": self.lbs_weights, "parents": self.parents.tolist()}
@@ -160,6 +225,17 @@ class BodyModel(nn.Module):
         dev = self.v_template.device
         if dev.type != "cuda":
             raise RohmB200Error("BodyModel: the model must live on a CUDA device (no CPU path)")
+        for name, val in zeros.items():
+            # jaw_pose / leye_pose / reye_pose / left_hand_pose / right_hand_pose / expression: RoHM always passes zeros
+            # (motion_representation.py:383-388) and the kernels hard-wire that; anything else must fail loudly.
+            if name in ("return_full_pose", "pose2rot", "return_joints"):
+                continue
+            if isinstance(val, torch.Tensor):
+                if val.numel() and bool(torch.count_nonzero(val)):
+                    raise RohmB200Error(f"BodyModel.forward: {name} must be all zeros (RoHM's call convention); the "
+                                        "B200 kernels do not evaluate hands / jaw / eyes / expression")
+            elif val is not None:
+                raise RohmB200Error(f"BodyModel.forward: unsupported argument {name}={val!r}")
         N = global_orient.shape[0]
         k = kernels_for(self, dev, N, with_vertices=return_verts)
         joints, verts = k.forward(global_orient, body_pose, betas, transl, return_verts)

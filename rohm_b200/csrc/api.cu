@@ -18,9 +18,13 @@ extern "C" int rohm_ctx_create(int device, rohm_ctx** out) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaSetDevice(device) != cudaSuccess) {
-    delete ctx;
-    return ROHM_ERR_CUDA;
+  {
+    // initialise the device's primary context without leaving the caller's current device changed
+    rohm::DeviceGuard guard(ctx);
+    if (cudaFree(nullptr) != cudaSuccess) {
+      delete ctx;
+      return ROHM_ERR_CUDA;
+    }
   }
   *out = ctx;
   return ROHM_OK;

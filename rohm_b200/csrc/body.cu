@@ -19,14 +19,18 @@
 // from the joint rotation matrices to the 6-D inputs (differences to the reference's autograd: its eps clamps below
 // ~2e-3 rad and fp32 round-off of the round trip).
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "common.h"
 #include "gemm.cuh"
+#include "kin.cuh"
 #include "ptx.cuh"
 
 namespace rohm {
 namespace {
+
+using namespace kin;
 
 constexpr int kJ = 55;        // SMPL-X joints
 constexpr int kBodyJ = 22;    // global + 21 body joints
@@ -36,95 +40,6 @@ constexpr int kBlendK = 256;    // 189 pose features + 10 betas + 1 (template), 
 constexpr int kMaxBones = 8;    // compressed skinning weights per vertex
 
 __constant__ int c_parents[kJ];
-
-struct V3 {
-  float x, y, z;
-};
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-struct M3 {  // columns
-  V3 c0, c1, c2;
-};
-__device__ __forceinline__ V3 mul(const M3& R, V3 v) { return v.x * R.c0 + v.y * R.c1 + v.z * R.c2; }
-__device__ __forceinline__ V3 mulT(const M3& R, V3 v) { return {dot(R.c0, v), dot(R.c1, v), dot(R.c2, v)}; }
-__device__ __forceinline__ M3 mul(const M3& A, const M3& B) { return {mul(A, B.c0), mul(A, B.c1), mul(A, B.c2)}; }
-
-// rot6d (row-major 3x2: a1 = x[0,2,4], a2 = x[1,3,5]) -> rotation matrix with columns b1, b2, b3.
-__device__ __forceinline__ M3 rot6d_to_mat(const float* x, float* n1 = nullptr, float* n2 = nullptr, float* s = nullptr) {
-  const V3 a1 = {x[0], x[2], x[4]}, a2 = {x[1], x[3], x[5]};
-  const float l1 = fmaxf(sqrtf(dot(a1, a1)), 1e-12f);
-  const V3 b1 = (1.0f / l1) * a1;
-  const float d = dot(b1, a2);
-  const V3 u2 = a2 - d * b1;
-  const float l2 = fmaxf(sqrtf(dot(u2, u2)), 1e-12f);
-  const V3 b2 = (1.0f / l2) * u2;
-  if (n1) *n1 = l1, *n2 = l2, *s = d;
-  return {b1, b2, cross(b1, b2)};
-}
-
-// VJP of rot6d_to_mat: G = dL/dR (columns g1, g2, g3) -> dL/dx[6].
-__device__ __forceinline__ void rot6d_backward(const float* x, const M3& G, float* gx) {
-  float l1, l2, s;
-  const M3 R = rot6d_to_mat(x, &l1, &l2, &s);
-  const V3 a2 = {x[1], x[3], x[5]};
-  V3 gb1 = G.c0 + cross(R.c1, G.c2);   // b3 = b1 x b2
-  V3 gb2 = G.c1 + cross(G.c2, R.c0);
-  const V3 gu2 = (1.0f / l2) * (gb2 - dot(gb2, R.c1) * R.c1);
-  const V3 ga2 = gu2 - dot(R.c0, gu2) * R.c0;
-  gb1 = gb1 - s * gu2 - dot(gu2, R.c0) * a2;
-  const V3 ga1 = (1.0f / l1) * (gb1 - dot(gb1, R.c0) * R.c0);
-  gx[0] = ga1.x, gx[2] = ga1.y, gx[4] = ga1.z;
-  gx[1] = ga2.x, gx[3] = ga2.y, gx[5] = ga2.z;
-}
-
-// rotation matrix -> axis-angle through the reference's quaternion route (kornia WXYZ, eps = 1e-6 everywhere)
-__device__ __forceinline__ float safe_div(float n, float d) { return n / (fabsf(d) < 1e-6f ? d + 1e-6f : d); }
-__device__ __forceinline__ float safe_atan2(float y, float x) {
-  if (fabsf(y) < 1e-6f && fabsf(x) < 1e-6f) y += 1e-6f;
-  return atan2f(y, x);
-}
-__device__ __forceinline__ V3 mat_to_aa(const M3& R) {
-  const float m00 = R.c0.x, m10 = R.c0.y, m20 = R.c0.z, m01 = R.c1.x, m11 = R.c1.y, m21 = R.c1.z, m02 = R.c2.x,
-              m12 = R.c2.y, m22 = R.c2.z;
-  const float trace = m00 + m11 + m22;
-  float qw, qx, qy, qz;
-  if (trace > 0.0f) {
-    const float sq = sqrtf(fmaxf(trace + 1.0f, 1e-6f)) * 2.0f;
-    qw = 0.25f * sq, qx = safe_div(m21 - m12, sq), qy = safe_div(m02 - m20, sq), qz = safe_div(m10 - m01, sq);
-  } else if (m00 > m11 && m00 > m22) {
-    const float sq = sqrtf(fmaxf(1.0f + m00 - m11 - m22, 1e-6f)) * 2.0f;
-    qw = safe_div(m21 - m12, sq), qx = 0.25f * sq, qy = safe_div(m01 + m10, sq), qz = safe_div(m02 + m20, sq);
-  } else if (m11 > m22) {
-    const float sq = sqrtf(fmaxf(1.0f + m11 - m00 - m22, 1e-6f)) * 2.0f;
-    qw = safe_div(m02 - m20, sq), qx = safe_div(m01 + m10, sq), qy = 0.25f * sq, qz = safe_div(m12 + m21, sq);
-  } else {
-    const float sq = sqrtf(fmaxf(1.0f + m22 - m00 - m11, 1e-6f)) * 2.0f;
-    qw = safe_div(m10 - m01, sq), qx = safe_div(m02 + m20, sq), qy = safe_div(m12 + m21, sq), qz = 0.25f * sq;
-  }
-  const float s2 = qx * qx + qy * qy + qz * qz;
-  const float sn = sqrtf(fmaxf(s2, 1e-6f));
-  const float two_theta = 2.0f * (qw < 0.0f ? safe_atan2(-sn, -qw) : safe_atan2(sn, qw));
-  const float k = s2 > 0.0f ? safe_div(two_theta, sn) : 2.0f;
-  return {qx * k, qy * k, qz * k};
-}
-// smplx batch_rodrigues: the 1e-8 is added to the VECTOR before the norm
-__device__ __forceinline__ M3 rodrigues(V3 r) {
-  const V3 e = {r.x + 1e-8f, r.y + 1e-8f, r.z + 1e-8f};
-  const float ang = sqrtf(dot(e, e));
-  const V3 k = (1.0f / ang) * r;
-  float sn, cs;
-  sincosf(ang, &sn, &cs);
-  const float c1 = 1.0f - cs;
-  // I + sin K + (1 - cos) K^2
-  M3 R;
-  R.c0 = {1.0f + c1 * (-k.z * k.z - k.y * k.y), sn * k.z + c1 * k.x * k.y, -sn * k.y + c1 * k.x * k.z};
-  R.c1 = {-sn * k.z + c1 * k.x * k.y, 1.0f + c1 * (-k.z * k.z - k.x * k.x), sn * k.x + c1 * k.y * k.z};
-  R.c2 = {sn * k.y + c1 * k.x * k.z, -sn * k.x + c1 * k.y * k.z, 1.0f + c1 * (-k.y * k.y - k.x * k.x)};
-  return R;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // model preparation
@@ -415,7 +330,10 @@ constexpr int kC = 294;
 constexpr int kChAngle = 0, kChRootPos = 2, kChHeight = 6, kChRot6d = 7, kChTrans = 16, kChLocalPos = 22,
               kChBodyPose = 154, kChBetas = 280, kChContact = 290;
 
-__global__ void repr_to_smplx_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+// element (b, c, t) of x lives at x[b * sb + c * sc + t * st]: channel-major [B,294,1,T] (sb = 294 T, sc = T, st = 1,
+// PoseNet tensors) or channels-last [B,T,294] (sb = 294 T, sc = 1, st = 294: TrajNet-side / driver tensors)
+__global__ void repr_to_smplx_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t st,
+                                     const float* __restrict__ mean,
                                      const float* __restrict__ stdv, int B, int T, float* __restrict__ go,
                                      float* __restrict__ bp, float* __restrict__ betas, float* __restrict__ transl) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -424,7 +342,7 @@ __global__ void repr_to_smplx_kernel(const float* __restrict__ x, const float* _
   const int j = static_cast<int>(i % kBodyJ);
   const int64_t f = i / kBodyJ;
   const int b = static_cast<int>(f / T), t = static_cast<int>(f % T);
-  auto ch = [&](int c) { return x[(static_cast<int64_t>(b) * kC + c) * T + t] * stdv[c] + mean[c]; };
+  auto ch = [&](int c) { return x[b * sb + c * sc + t * st] * stdv[c] + mean[c]; };
   const int c0 = (j == 0) ? kChRot6d : kChBodyPose + (j - 1) * 6;
   float r6[6];
 #pragma unroll
@@ -720,37 +638,19 @@ __global__ void __launch_bounds__(128) guide_backward_kernel(const float* __rest
 
 using namespace rohm;
 
-struct rohm_body {
-  rohm_ctx* ctx = nullptr;
-  DevicePool pool;
-  int V = 0, sd_comps = 0, passes = 3;
-  int kind = kKindTf32;  // operand element type of the blend GEMM (kKindF16 in ROHM_PRECISION_F16X2)
-  int64_t max_frames = 0;
-  float *Jt = nullptr, *Jd = nullptr;
-  const float* lbs_w = nullptr;  // dense weights copy
-  float* lbs_w_copy = nullptr;
-  int* bone_idx = nullptr;
-  float* bone_w = nullptr;
-  bool sparse_ok = true;
-  PackedWeight blend;  // [V*3 (padded), kBlendK]
-  // per-frame workspace
-  float *go = nullptr, *bp = nullptr, *betas = nullptr, *transl = nullptr, *A = nullptr, *feat_h = nullptr,
-        *feat_l = nullptr, *vposed = nullptr;
-  float *foot = nullptr, *gdir = nullptr, *sums = nullptr;
-  GemmParams g_blend{};
-};
+#include "body_internal.h"
 
 extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const float* shapedirs, int shape_comps,
                                 const float* posedirs, const float* J_regressor, const float* lbs_weights,
                                 const int* parents_host, int num_verts, int64_t max_frames, int with_vertices,
                                 int precision, rohm_body** out) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (!v_template || !shapedirs || !J_regressor || !parents_host || !out || num_verts <= 0 || max_frames <= 0 ||
       shape_comps < kBetas || (with_vertices && (!posedirs || !lbs_weights)))
     return fail(ctx, ROHM_ERR_INVALID, "rohm_body_create: bad arguments");
   for (int j = 0; j < kJ; ++j)
     if (parents_host[j] >= j) return fail(ctx, ROHM_ERR_INVALID, "rohm_body_create: parents must precede children");
-  ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
   rohm_body* bd = new (std::nothrow) rohm_body();
   if (!bd) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
   bd->ctx = ctx, bd->V = num_verts, bd->sd_comps = shape_comps, bd->max_frames = max_frames, bd->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
@@ -762,10 +662,14 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
   bd->Jd = bd->pool.floats(kJ * 30);
   bd->foot = bd->pool.floats(2 * F * 12);
   bd->gdir = bd->pool.floats(2 * F * 12);
-  bd->sums = bd->pool.floats(4);
+  bd->sums = bd->pool.floats(16);
   bd->go = bd->pool.floats(F * 3), bd->bp = bd->pool.floats(F * 63), bd->betas = bd->pool.floats(F * kBetas);
   bd->transl = bd->pool.floats(F * 3);
-  bool ok = bd->Jt && bd->Jd && bd->foot && bd->gdir && bd->sums && bd->go && bd->bp && bd->betas && bd->transl;
+  bd->jwork = bd->pool.floats(F * kBodyJ * 3), bd->gwork = bd->pool.floats(F * kBodyJ * 3);
+  bd->parents_dev = static_cast<int*>(bd->pool.bytes(sizeof(int) * kJ));
+  bool ok = bd->Jt && bd->Jd && bd->foot && bd->gdir && bd->sums && bd->go && bd->bp && bd->betas && bd->transl &&
+            bd->jwork && bd->gwork && bd->parents_dev;
+  if (ok) ok = cudaMemcpy(bd->parents_dev, parents_host, sizeof(int) * kJ, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok && with_vertices) {
     bd->A = bd->pool.floats(F * kJ * 12);
     bd->feat_h = bd->pool.floats(F * kBlendK), bd->feat_l = bd->pool.floats(F * kBlendK);
@@ -813,6 +717,8 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
       return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: %s", cudaGetErrorString(e));
     }
     bd->sparse_ok = (h_over == 0);
+    // developer / test switch: run the dense skinning kernel (the fallback for models with > 8 bones per vertex)
+    if (const char* env = getenv("ROHM_B200_DENSE_SKIN")) bd->sparse_ok = bd->sparse_ok && env[0] == '0';
     cudaError_t ea = gemm_init_attributes();
     GemmParams& g = bd->g_blend;
     g = GemmParams{};
@@ -850,6 +756,7 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
                                  void* stream) {
   if (bd == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = bd->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   if (!global_orient || !body_pose || !betas || !transl || N <= 0 || N > bd->max_frames || num_joints < 0 ||
       num_joints > kJ || (joints == nullptr && vertices == nullptr))
     return fail(ctx, ROHM_ERR_INVALID, "rohm_body_forward: bad arguments (N=%lld, capacity %lld)",
@@ -881,15 +788,24 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
 // joints [B*T, num_joints, 3] and optionally vertices [B*T, V, 3].
 extern "C" int rohm_body_from_repr(rohm_body* bd, const float* x, const float* mean, const float* stdv, int B, int T,
                                    float* joints, int num_joints, float* vertices, void* stream) {
+  return rohm_body_from_repr_layout(bd, x, 0, mean, stdv, B, T, joints, num_joints, vertices, stream);
+}
+
+extern "C" int rohm_body_from_repr_layout(rohm_body* bd, const float* x, int channels_last, const float* mean,
+                                          const float* stdv, int B, int T, float* joints, int num_joints,
+                                          float* vertices, void* stream) {
   if (bd == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = bd->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   const int64_t N = static_cast<int64_t>(B) * T;
   if (!x || !mean || !stdv || B <= 0 || T <= 0 || N > bd->max_frames)
-    return fail(ctx, ROHM_ERR_INVALID, "rohm_body_from_repr: bad arguments");
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_body_from_repr: bad arguments (B*T=%lld, capacity %lld)",
+                static_cast<long long>(N), static_cast<long long>(bd->max_frames));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = N * kBodyJ;
-  repr_to_smplx_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, mean, stdv, B, T, bd->go, bd->bp,
-                                                                                 bd->betas, bd->transl);
+  const int64_t sb = static_cast<int64_t>(kC) * T, sc = channels_last ? 1 : T, stt = channels_last ? kC : 1;
+  repr_to_smplx_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, sb, sc, stt, mean, stdv, B, T, bd->go,
+                                                                                 bd->bp, bd->betas, bd->transl);
   ROHM_CUDA(ctx, cudaGetLastError());
   return rohm_body_forward(bd, bd->go, bd->bp, bd->betas, bd->transl, N, joints, num_joints, vertices, stream);
 }
@@ -902,6 +818,7 @@ extern "C" int rohm_skating_guidance(rohm_body* bd, const float* x0, const float
                                      float* grad, float* loss_out, void* stream) {
   if (bd == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = bd->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   const int64_t N = static_cast<int64_t>(B) * T;
   if (!x0 || !mean || !stdv || !grad || B <= 0 || T <= 0 || N > bd->max_frames)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_skating_guidance: bad arguments (B*T=%lld, capacity %lld)",

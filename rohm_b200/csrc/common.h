@@ -38,6 +38,27 @@ inline int fail(rohm_ctx* ctx, int status, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Makes ctx->device the calling thread's current device for the lifetime of the guard and restores the previous one
+// afterwards: every entry point launches on the device its context was created for, whatever the caller's current
+// device is (a process that drives several GPUs), and never changes it as a side effect.
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(const rohm_ctx* ctx) {
+    if (ctx != nullptr && cudaGetDevice(&prev_) == cudaSuccess && prev_ != ctx->device) {
+      restore_ = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (restore_) cudaSetDevice(prev_);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+ private:
+  int prev_ = -1;
+  bool restore_ = false;
+};
+
 // Owns a set of cudaMalloc'ed buffers; frees them on destruction.
 class DevicePool {
  public:

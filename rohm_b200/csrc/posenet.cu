@@ -98,11 +98,16 @@ __global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, 
                                          float* __restrict__ Xl, int S, int D, int f16) {
   const int b = blockIdx.x;
   int64_t t = timesteps[b];
-  t = t < 0 ? 0 : (t >= table_rows ? table_rows - 1 : t);
+  // The reference indexes pe[timesteps] and raises on a bad index (heads.py:145).  A kernel cannot raise, so an
+  // out-of-range timestep poisons the clip's timestep token with NaN (which attention spreads over the whole clip's
+  // output) instead of being clamped to a plausible but wrong embedding.
+  const bool bad = t < 0 || t >= table_rows;
+  t = bad ? 0 : t;
   const float4* src = reinterpret_cast<const float4*>(table + t * D);
   const int64_t o = static_cast<int64_t>(b) * S * D;
+  const float nan = __int_as_float(0x7fc00000);
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
-    const float4 v = src[i];
+    const float4 v = bad ? make_float4(nan, nan, nan, nan) : src[i];
     reinterpret_cast<float4*>(X + o)[i] = v;
     if (f16) {
       uint2 h, l;
@@ -1408,6 +1413,7 @@ static int build_time_table(rohm_posenet* pn, const rohm_posenet_weights* w) {
 extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w, int max_batch, int max_frames,
                                    int precision, rohm_posenet** out) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (w == nullptr || out == nullptr || max_batch <= 0 || max_frames <= 0)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: bad arguments");
   if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32 && precision != ROHM_PRECISION_F16X2)
@@ -1418,7 +1424,6 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   if (dh != 64 && dh != 128) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: head dim must be 64 or 128");
   if (max_frames + 1 > 256) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: at most 255 frames per clip");
   if (max_frames + 1 > w->pe_len) return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_create: clip longer than pe table");
-  ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
 
   rohm_posenet* pn = new (std::nothrow) rohm_posenet();
   if (pn == nullptr) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
@@ -1612,6 +1617,7 @@ extern "C" int rohm_posenet_launches_per_forward(const rohm_posenet* pn) { retur
 extern "C" int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B, int T, void* stream) {
   if (pn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = pn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   if (cond == nullptr || B <= 0 || T <= 0 || B > pn->max_batch || T > pn->max_frames)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_set_cond: B=%d T=%d outside the created capacity (%d, %d)", B, T,
                 pn->max_batch, pn->max_frames);
@@ -1645,6 +1651,7 @@ extern "C" int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B,
 static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                             cudaStream_t st) {
   rohm_ctx* ctx = pn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   const int S = T + 1, D = pn->D;
   const int rows = B * S;
   pn->launches = 0;
@@ -1724,6 +1731,7 @@ extern "C" int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const in
 static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                                cudaStream_t st, rohm_posenet::FwdGraph* fg) {
   rohm_ctx* ctx = pn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
   // Nothing executes during capture; the instantiated graph is then launched on the caller's stream.
   (void)st;
@@ -1767,6 +1775,7 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
                                     int T, void* stream) {
   if (pn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = pn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   if (x_t == nullptr || timesteps == nullptr || out == nullptr)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_posenet_forward: null pointer");
   if (B != pn->cond_B || T != pn->cond_T)

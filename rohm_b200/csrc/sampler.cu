@@ -100,6 +100,7 @@ extern "C" int rohm_ddpm_step(rohm_ctx* ctx, const float* x0, const float* x_t, 
                               const float* grad1, int n_grads, float* out, int64_t n_clips, int64_t clip_elems,
                               const float* coef, int64_t coef_clip_stride, void* stream) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (n_clips < 0 || clip_elems < 0 || x0 == nullptr || x_t == nullptr || noise == nullptr || out == nullptr ||
       coef == nullptr || n_grads < 0 || n_grads > 2 || (n_grads > 0 && grad0 == nullptr) ||
       (n_grads > 1 && grad1 == nullptr) || n_clips > 65535)
@@ -128,6 +129,7 @@ extern "C" int rohm_ddpm_step(rohm_ctx* ctx, const float* x0, const float* x_t, 
 extern "C" int rohm_q_sample(rohm_ctx* ctx, const float* x_start, const float* noise, float* out, int64_t n,
                              float sqrt_ac, float sqrt_one_minus_ac, void* stream) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (n < 0 || x_start == nullptr || noise == nullptr || out == nullptr)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_q_sample: bad arguments");
   if (n == 0) return ROHM_OK;
@@ -141,6 +143,7 @@ extern "C" int rohm_ddim_step(rohm_ctx* ctx, const float* x0, const float* x_t, 
                               int64_t n, float sqrt_recip_ac, float sqrt_recipm1_ac, float sqrt_ac_prev, float dir_coef,
                               float sigma, void* stream) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (n < 0 || x0 == nullptr || x_t == nullptr || noise == nullptr || out == nullptr)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_ddim_step: bad arguments");
   if (n == 0) return ROHM_OK;

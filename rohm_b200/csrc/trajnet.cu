@@ -509,6 +509,7 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
                                    int trajcontrol, int control_cond_dim, int max_batch, int frames, int precision,
                                    rohm_trajnet** out) {
   if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
   if (names == nullptr || ptrs == nullptr || numels == nullptr || out == nullptr || max_batch <= 0)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: bad arguments");
   if (frames <= 0 || frames % 16 != 0)
@@ -518,7 +519,6 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
     return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: mid_dim must be a multiple of 64, time_dim even and <= 64");
   if (precision != ROHM_PRECISION_TF32X3 && precision != ROHM_PRECISION_TF32 && precision != ROHM_PRECISION_F16X2)
     return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_create: precision must be 3 (TF32x3), 2 (F16x2) or 1 (TF32)");
-  ROHM_CUDA(ctx, cudaSetDevice(ctx->device));
   ROHM_CUDA(ctx, gemm_init_attributes());
   rohm_trajnet* tn = new (std::nothrow) rohm_trajnet();
   if (tn == nullptr) return fail(ctx, ROHM_ERR_INVALID, "out of host memory");
@@ -728,6 +728,7 @@ static int trajnet_pack(rohm_trajnet* tn, const float* x, const Act& a, int B, c
 extern "C" int rohm_trajnet_set_cond(rohm_trajnet* tn, const float* cond, const float* control_cond, int B, void* stream) {
   if (tn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = tn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   if (cond == nullptr || B <= 0 || B > tn->max_batch || (tn->control && control_cond == nullptr))
     return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_set_cond: bad arguments (B=%d, capacity %d)", B, tn->max_batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -754,6 +755,7 @@ extern "C" int rohm_trajnet_set_cond(rohm_trajnet* tn, const float* cond, const 
 static int trajnet_forward_launches(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
                                     cudaStream_t st) {
   rohm_ctx* ctx = tn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   int rc;
   tn->launches = 0;
   auto A = [&](const char* n) { return &tn->acts[n]; };
@@ -830,6 +832,7 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
                                     void* stream) {
   if (tn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = tn->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
   if (x_t == nullptr || time == nullptr || out == nullptr) return fail(ctx, ROHM_ERR_INVALID, "rohm_trajnet_forward: null pointer");
   if (B != tn->cond_B)
     return fail(ctx, ROHM_ERR_STATE, "rohm_trajnet_forward: B=%d but set_cond was called with B=%d", B, tn->cond_B);

@@ -280,6 +280,24 @@ class _GaussianDiffusion:
         return {"sample": sample, "pred_xstart": x0, "x_t": x}
 
     # ------------------------------------------------------------------ loops
+    def _begin_loop(self, model, grad_type=None):
+        """Once per sampling loop, before any step: drop the denoiser's cached step-invariant condition embedding (a
+        condition tensor can never outlive the loop it was embedded for) and reject what cannot run BEFORE a thousand
+        denoiser steps are spent (the reference would fail, or silently do nothing, at the first guided step)."""
+        inner = model.model if isinstance(model, _WrappedModel) else model
+        inv = getattr(inner, "invalidate_cond", None)
+        if inv is not None:
+            inv()
+        if grad_type is not None and self._POSENET and grad_type in _GUIDANCE:
+            for kind, _, _ in _GUIDANCE[grad_type]:
+                hook = 'guide_skating_with_smpl' if kind == 'skating' else 'guide_2d_projection_with_smpl'
+                if not hasattr(inner, hook):
+                    raise RohmB200Error(f"grad_type={grad_type!r} needs model.{hook}")
+        tmap = getattr(self, "timestep_map", None)
+        pe = getattr(getattr(inner, "sequence_pos_encoder", None), "pe", None)
+        if tmap is not None and pe is not None and len(tmap) and max(tmap) >= pe.shape[0]:
+            raise RohmB200Error(f"timestep {max(tmap)} exceeds the positional table ({pe.shape[0]} rows) that embeds it")
+
     def p_sample_loop(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, grad_type=None, early_stop=False, dump_steps=None,
@@ -321,6 +339,7 @@ class _GaussianDiffusion:
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
+        self._begin_loop(model, grad_type if cond_fn_with_grad else None)
         img = noise if noise is not None else self._randn(*shape, device=device)
         if skip_timesteps and init_image is None:
             init_image = th.zeros_like(img)
@@ -369,6 +388,10 @@ class _GaussianDiffusion:
                          randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
         if dump_steps is not None or const_noise:
             raise NotImplementedError()
+        if cond_fn_with_grad:
+            raise RohmB200Error("ddim_sample_loop: test-time guidance (cond_fn_with_grad / grad_type) is defined for the "
+                                "ancestral sampler only (the reference's ddim_sample_with_grad cannot run, SURVEY D4); "
+                                "use a non-'ddim' respacing or cond_fn_with_grad=False")
         final = None
         for sample in self.ddim_sample_loop_progressive(
                 model, batch, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
@@ -383,6 +406,7 @@ class _GaussianDiffusion:
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
+        self._begin_loop(model)
         img = noise if noise is not None else self._randn(*shape, device=device)
         if skip_timesteps and init_image is None:
             init_image = th.zeros_like(img)
@@ -410,7 +434,11 @@ class _GaussianDiffusion:
                          grad_type=None, early_stop=False):
         inner = model.model if isinstance(model, _WrappedModel) else model
         if isinstance(timestep_respacing, str) and timestep_respacing.startswith('ddim'):
-            # the branch the reference left commented out (:949-952)
+            # the branch the reference left commented out (:949-952); it has no guidance / early-stop variant, so asking
+            # for them is an error rather than a silently unguided run
+            if early_stop or (cond_fn_with_grad and grad_type is not None):
+                raise RohmB200Error("eval_losses(timestep_respacing='ddim...'): grad_type / early_stop are only defined "
+                                    "for the ancestral sampler; drop them or use a non-'ddim' respacing")
             return self.ddim_sample_loop(model=inner, batch=batch, shape=shape, progress=progress,
                                          clip_denoised=clip_denoised, eta=0.0)
         kw = dict(grad_type=grad_type, early_stop=early_stop) if self._POSENET else {}

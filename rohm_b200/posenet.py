@@ -83,7 +83,10 @@ class PoseNetEngine:
             self.lib.rohm_posenet_set_option(handle, 1, 0)
         if os.environ.get("ROHM_B200_GRAPH", "1") == "0":
             self.lib.rohm_posenet_set_option(handle, 0, 0)
-        self.cond_key = None
+        # the condition whose step-invariant embedding the engine currently holds: a STRONG reference (so the caching
+        # allocator cannot hand its address to a different tensor while it is cached) plus its version counter
+        self.cond_ref = None
+        self.cond_version = -1
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -209,9 +212,28 @@ class PoseNet(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
+    def load_state_dict(self, state_dict, strict=True, **k):
+        """nn.Module.load_state_dict, plus: when the body model is the package's own BodyModel (no ``smplx`` package
+        installed), the ``smplx_model.*`` entries of a reference checkpoint are adopted by buffer name
+        (BodyModel.load_smplx_state) instead of being matched key by key -- real smplx registers more buffers than
+        RoHM's calls need, so a strict key match could never succeed."""
         self._engine = None
-        return super().load_state_dict(*a, **k)
+        from .body_model import BodyModel
+        if isinstance(self.smplx_model, BodyModel):
+            prefix = "smplx_model."
+            body = {key[len(prefix):]: v for key, v in state_dict.items() if key.startswith(prefix)}
+            rest = {key: v for key, v in state_dict.items() if not key.startswith(prefix)}
+            own = {prefix + n: b for n, b in self.smplx_model.state_dict().items()}
+            foreign = [n for n in body if (prefix + n) not in own or own[prefix + n].shape != body[n].shape]
+            if foreign:
+                self.smplx_model.load_smplx_state(body)
+                rest.update({prefix + n: b for n, b in self.smplx_model.state_dict().items()})
+            else:
+                rest.update({prefix + n: v for n, v in body.items()})
+                for key, v in own.items():
+                    rest.setdefault(key, v)
+            state_dict = rest
+        return super().load_state_dict(state_dict, strict=strict, **k)
 
     def engine(self, B, T, device):
         if self.training:
@@ -234,16 +256,23 @@ class PoseNet(nn.Module):
             raise RohmB200Error("PoseNet: batch tensors must live on a CUDA device (no CPU path)")
         B, Cc, _, T = cond.shape
         e = self.engine(B, T, cond.device)
-        key = (cond.data_ptr(), cond._version, tuple(cond.shape), tuple(cond.stride()))
-        if e.cond_key != key:
+        # Same tensor OBJECT, unmodified since it was embedded -> reuse.  Identity (not data_ptr): a freed condition's
+        # address and version count can be handed to the next batch's tensor by the caching allocator.
+        if e.cond_ref is not cond or e.cond_version != cond._version:
             fp = self._fingerprint()  # parameters are re-checked once per new condition, not per step
             if fp != self._engine_fingerprint:
                 self._engine = None
                 e = self.engine(B, T, cond.device)
             c = cond if (cond.is_contiguous() and cond.dtype == torch.float32) else cond.contiguous().float()
             e.set_cond(c)
-            e.cond_key = key
+            e.cond_ref, e.cond_version = cond, cond._version
         return e
+
+    def invalidate_cond(self):
+        """Forget the cached step-invariant condition embedding (the samplers call this at the start of every loop,
+        so a condition can never outlive the loop it was embedded for)."""
+        if self._engine is not None:
+            self._engine.cond_ref, self._engine.cond_version = None, -1
 
     # ---------------------------------------------------------------- test-time guidance
     def _norm_stats(self, device):
@@ -271,13 +300,52 @@ class PoseNet(nn.Module):
         k = kernels_for(self.smplx_model, x.device, B * T, with_vertices=False)
         return k.skating_guidance(x, mean, std)
 
+    def _camera_affine(self, batch, device):
+        """[B, 3, 4] canonical -> camera map of guide_2d_projection_with_smpl (reference posenet.py:285-297):
+        p_cam = inv(cam_R) (inv(transf_matrix) p_cano - cam_t).  Per-clip 4x4 inverses: host-sized work, cached per
+        transf_matrix tensor so the guided steps of one loop compute it once."""
+        tm = batch['transf_matrix']
+        cache = getattr(self, "_cam_cache", None)
+        if cache is not None and cache[0] is tm and cache[1] == tm._version:
+            return cache[2]
+        cano2scene = torch.linalg.inv(tm.to(device=device, dtype=torch.float32))  # [B, 4, 4]
+        cam_R = torch.as_tensor(self.dataset.cam_R, dtype=torch.float32, device=device).reshape(3, 3)
+        cam_t = torch.as_tensor(self.dataset.cam_t, dtype=torch.float32, device=device).reshape(3)
+        Rinv = torch.linalg.inv(cam_R)
+        M = Rinv @ cano2scene[:, 0:3, 0:3]                                   # [B, 3, 3]
+        m = (Rinv @ (cano2scene[:, 0:3, 3] - cam_t).unsqueeze(-1))           # [B, 3, 1]
+        aff = torch.cat([M, m], dim=-1).contiguous()
+        self._cam_cache = (tm, tm._version, aff)
+        return aff
+
     def guide_2d_projection_with_smpl(self, batch, out, denoise_t, compute_grad='x_t'):
-        raise NotImplementedError("2-D reprojection guidance (grad_type='prox') is a listed next row (SURVEY.md 8f N2), "
-                                  "not part of this build")
+        """Gradient of -(2-D reprojection loss of 10 SMPL-X body joints against batch['keypoints_2d']) w.r.t. x_t or
+        the predicted x_0 (reference posenet.py:260-317), [bs, body_feat_dim, 1, T], trajectory and contact channels
+        zero.  One analytic forward + VJP kernel (rohm_projection_guidance) instead of autograd through the body model."""
+        from .body_model import kernels_for
+        x = batch['x_t'] if compute_grad == 'x_t' else out['pred_xstart']
+        x = x.detach()
+        x = x if (x.is_contiguous() and x.dtype == torch.float32) else x.contiguous().float()
+        if self.dataset.traj_feat_dim != 22 or x.shape[1] != 294:
+            raise RohmB200Error("guide_2d_projection_with_smpl: implemented for the 294-channel representation with the "
+                                "22-channel trajectory block (the configuration RoHM ships)")
+        B, _, _, T = x.shape
+        dev = x.device
+        mean, std = self._norm_stats(dev)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        kp = f32(batch['keypoints_2d'])
+        if kp.dim() != 4 or kp.shape[0] != B or kp.shape[1] < T or kp.shape[2] != 22 or kp.shape[3] != 3:
+            raise RohmB200Error(f"guide_2d_projection_with_smpl: batch['keypoints_2d'] must be [{B}, >={T}, 22, 3], got "
+                                f"{tuple(kp.shape)}")
+        k = kernels_for(self.smplx_model, dev, B * T, with_vertices=False)
+        return k.projection_guidance(x, mean, std, self._camera_affine(batch, dev), f32(batch['focal_length']),
+                                     f32(batch['camera_center']), kp)
 
     def compute_losses_with_smpl(self, batch, model_output, smplx_model=None, epoch=0):
-        raise NotImplementedError("training / evaluation losses are out of scope of the inference hot path; call "
-                                  "eval_losses(..., compute_loss=False) as test_amass_full.py does")
+        """The evaluation loss dictionary of reference posenet.py:99-193 (what eval_losses returns with its default
+        compute_loss=True, test_posenet.py:178); off the hot path, see rohm_b200/eval_losses.py."""
+        from .eval_losses import posenet_losses
+        return posenet_losses(self, batch, model_output, smplx_model, epoch)
 
     # ---------------------------------------------------------------- forward
     def forward(self, batch, timesteps):
@@ -287,6 +355,9 @@ class PoseNet(nn.Module):
         if x_t.dim() != 4 or x_t.shape[2] != 1 or x_t.shape != cond.shape or x_t.shape[1] != self.input_feats:
             raise RohmB200Error(f"PoseNet: expected x_t/cond of shape [B, {self.input_feats}, 1, T], got "
                                 f"{tuple(x_t.shape)} / {tuple(cond.shape)}")
+        if timesteps.is_floating_point():
+            # the reference indexes pe[timesteps]: a float index raises there too (rescale_timesteps is never enabled)
+            raise RohmB200Error("PoseNet: timesteps must be an integer tensor (they index the positional table)")
         e = self.prepare_cond(cond)
         x = x_t if (x_t.is_contiguous() and x_t.dtype == torch.float32) else x_t.contiguous().float()
         ts = timesteps.to(device=x.device, dtype=torch.int64).contiguous()

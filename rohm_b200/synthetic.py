@@ -113,6 +113,22 @@ def plausible_motion(B, T, seed, dataset=None):
     return x.permute(0, 2, 1).unsqueeze(-2).contiguous()
 
 
+def pipeline_batches(B, seed, ds_pose, frames=144, device="cpu"):
+    """The two dataloader batches of test_amass_full.py:202-216 (pose task / traj task, repr_abs_only) on a synthetic
+    plausible motion: z-scored clean representation, a noisy copy, the 13-channel absolute trajectory condition and the
+    272-channel TrajControl condition.  Shared by tools/gen_golden.py, the GPU replay test and bench.py."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    clean = plausible_motion(B, frames, seed, ds_pose)[:, :, 0].permute(0, 2, 1).contiguous()  # [B, frames, 294]
+    noisy = clean + 0.1 * torch.randn(clean.shape, generator=g)
+    noisy[..., -4:] = clean[..., -4:]
+    sel = [0, 2, 3, 6] + list(range(7, 13)) + list(range(16, 19))
+    pose = {'motion_repr_clean': clean.clone().to(device), 'motion_repr_noisy': noisy.clone().to(device)}
+    traj = {'motion_repr_clean': clean.clone().to(device), 'motion_repr_noisy': noisy.clone().to(device),
+            'cond': noisy[..., sel].clone().to(device), 'control_cond': noisy[..., 22:].clone().to(device)}
+    return pose, traj
+
+
 def smplx_like_model(seed=0, num_verts=10475, dtype=torch.float32):
     """A synthetic body model with SMPL-X's exact tensor shapes, kinematic tree and sparsity pattern:
     v_template [V,3], shapedirs [V,3,20], posedirs [486, V*3], J_regressor [55,V] (sparse rows, convex weights),

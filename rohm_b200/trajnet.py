@@ -119,6 +119,11 @@ class TrajNet(nn.Module):
     def invalidate_engine(self):
         self._engine = None
 
+    def invalidate_cond(self):
+        """Forget the cached condition pyramid (called by the samplers at the start of every loop)."""
+        if self._engine is not None:
+            self._engine.cond_ref, self._engine.control_ref = None, None
+
     def _apply(self, fn, *a, **k):
         self._engine = None
         return super()._apply(fn, *a, **k)
@@ -128,8 +133,10 @@ class TrajNet(nn.Module):
         return super().load_state_dict(*a, **k)
 
     def compute_losses_with_smpl(self, batch, model_output, smplx_model=None):
-        raise NotImplementedError("training / evaluation losses are out of scope of the inference hot path; call "
-                                  "eval_losses(..., compute_loss=False) as test_amass_full.py does")
+        """The evaluation loss dictionary of reference trajnet.py:278-400 (what eval_losses returns with its default
+        compute_loss=True, test_trajnet.py:154); off the hot path, see rohm_b200/eval_losses.py."""
+        from .eval_losses import trajnet_losses
+        return trajnet_losses(self, batch, model_output, smplx_model)
 
     def forward(self, batch, time):
         """batch['x_t'], batch['cond']: [bs, T, traj_dim]; batch['control_cond']: [bs, T, 272] when trajcontrol;

@@ -28,7 +28,10 @@ class TrajNetEngine:
                                               module.control_cond_dim, max_batch, frames, precision, C.byref(handle))
         _lib.check(rc, self.ctx)
         self.handle = handle
-        self.cond_key = None
+        # strong references to the tensors whose step-invariant pyramid the engine holds (see PoseNetEngine)
+        self.cond_ref, self.cond_version = None, -1
+        self.control_ref, self.control_version = None, -1
+        self.cond_B = -1
         del sd
 
     def __del__(self):
@@ -65,10 +68,6 @@ def _fingerprint(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
-def _tensor_key(t):
-    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
-
-
 def _f32c(t):
     return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
 
@@ -103,12 +102,15 @@ def run_forward(module, batch, time):
     if module.trajcontrol and (control is None or tuple(control.shape) != (B, T, module.control_cond_dim)):
         raise RohmB200Error(f"TrajNet(trajcontrol=True): batch['control_cond'] must be [B, T, {module.control_cond_dim}]")
     e = get_engine(module, B, T, x_t.device)
-    key = (_tensor_key(cond), _tensor_key(control), B)
-    if e.cond_key != key:
+    # object identity + version (never data_ptr: freed addresses are recycled by the caching allocator)
+    same = (e.cond_ref is cond and e.cond_version == cond._version and e.cond_B == B and e.control_ref is control and
+            (control is None or e.control_version == control._version))
+    if not same:
         if _fingerprint(module) != module._engine_fingerprint:  # parameters changed since the weights were packed
             module._engine = None
             e = get_engine(module, B, T, x_t.device)
         e.set_cond(_f32c(cond), _f32c(control) if control is not None else None)
-        e.cond_key = key
+        e.cond_ref, e.cond_version, e.cond_B = cond, cond._version, B
+        e.control_ref, e.control_version = control, (control._version if control is not None else -1)
     ts = time.to(device=x_t.device, dtype=torch.int64).contiguous()
     return e.forward(_f32c(x_t), ts)

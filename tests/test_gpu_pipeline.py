@@ -1,0 +1,163 @@
+"""GPU: the full multi-round inference (BASELINE config 4: TrajNet -> glue -> PoseNet with in-loop SMPL-X guidance, rounds >= 2
+through TrajControl) replayed through rohm_b200.pipeline against the golden produced by the unmodified reference
+(tests/golden/pipeline.npz, tools/gen_golden.py:gen_pipeline), plus the guided tail of the sampler at the benchmark size."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import NoiseTape, TOL, golden
+from oracle import diffusion_oracle as do
+from oracle import pipeline_oracle
+from rohm_b200 import diffusion, pipeline, synthetic
+from rohm_b200.body_model import BodyModel
+from rohm_b200.posenet import PoseNet
+from rohm_b200.trajnet import TrajNet
+
+pytestmark = pytest.mark.gpu
+
+POSE_RESPACING = "12" + ",0" * 19  # tools/gen_golden.py
+
+
+def _models(dev, ds_pose, ds_traj):
+    mp = PoseNet(dataset=ds_pose, body_feat_dim=294, latent_dim=512, ff_size=1024, num_layers=8, num_heads=4, device=dev,
+                 traj_feat_dim=22)
+    sd_p = {k: v.cpu() for k, v in synthetic.synth_state_dict(mp, 1).items()}
+    mp.load_state_dict(sd_p)
+    mk = lambda c: TrajNet(time_dim=32, mid_dim=512, cond_dim=13, traj_feat_dim=13, trajcontrol=c, device=dev,
+                           dataset=ds_traj, repr_abs_only=True)
+    mt, mc = mk(False), mk(True)
+    sd_t, sd_c = synthetic.synth_state_dict(mt, 2), synthetic.synth_state_dict(mc, 4)
+    mt.load_state_dict(sd_t)
+    mc.load_state_dict(sd_c)
+    return mp.to(dev).eval(), mt.to(dev).eval(), mc.to(dev).eval(), sd_p, sd_t, sd_c
+
+
+def _diffusions(dev, traj_steps, pose_steps=1000, pose_respacing=POSE_RESPACING):
+    a = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
+    mk = diffusion.create_gaussian_diffusion
+    dp = mk(a, diffusion, diffusion.SpacedDiffusionPoseNet, pose_steps, pose_respacing, dev)
+    dt = mk(a, diffusion, diffusion.SpacedDiffusionTrajNet, traj_steps, '', dev)
+    dc = mk(a, diffusion, diffusion.SpacedDiffusionTrajNet, traj_steps, '', dev)
+    return dp, dt, dc
+
+
+def test_full_pipeline_replays_reference_golden(cuda_device):
+    dev = cuda_device
+    g = golden("pipeline.npz")
+    B, tn, pn, rounds, s_in, s_pose, s_traj = [int(v) for v in g["meta"]]
+    ds_pose = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    ds_traj = synthetic.make_dataset('traj', seed=3, realistic_std=True)
+    mp, mt, mc, *_ = _models(dev, ds_pose, ds_traj)
+    body = BodyModel.create('', device=dev, seed=0)
+    dp, dt, dc = _diffusions(dev, tn)
+    tape_p, tape_t = NoiseTape(s_pose, dev), NoiseTape(s_traj, dev)
+    dp._randn, dp._randn_like = tape_p.randn, tape_p.randn_like
+    for d in (dt, dc):  # the reference's two TrajNet diffusion objects share one module-level RNG stream
+        d._randn, d._randn_like = tape_t.randn, tape_t.randn_like
+    pose, traj = synthetic.pipeline_batches(B, s_in, ds_pose, device=dev)
+    args = pipeline.make_args(sample_iter=rounds, mask_scheme='lower')
+    seen = []
+
+    def on_round(it, val_traj, traj_full, cond, val_pose):
+        seen.append({k: v.detach().cpu() for k, v in (("val_traj", val_traj), ("traj_full", traj_full), ("cond", cond),
+                                                      ("val_pose", val_pose))})
+        # stage-wise comparison: the next round is conditioned on the reference's PoseNet output (the guided chain is
+        # chaotic at 2 clips: a 1e-6 perturbation reaches O(1) within three steps -- see the golden generator)
+        return torch.from_numpy(g[f"r{it}_val_pose"]).to(dev)
+
+    out_pose, out_traj, traj_noisy = pipeline.run_rounds(args, mp, mt, mc, dp, dt, dc, ds_pose, ds_traj, body, pose, traj,
+                                                         on_round=on_round)
+    assert out_pose.shape == (B, 294, 1, 143) and out_traj.shape == (B, 144, 13) and traj_noisy.shape == (B, 144, 22)
+    for it in range(rounds):
+        err = {k: float((seen[it][k] - torch.from_numpy(g[f"r{it}_{k}"])).abs().max()) for k in seen[it]}
+        print(f"pipeline round {it}: max |cuda - reference| {err}")
+        assert err["val_traj"] < TOL and err["traj_full"] < TOL and err["cond"] < TOL, (it, err)
+    # teacher-forced guided PoseNet steps from the reference's recorded states
+    t_rows = dp._t_rows(B, dev)
+    for it in range(rounds):
+        tape = NoiseTape(s_pose, dev)
+        for _ in range(it * (pn + 1) + 1):
+            tape.randn(B, 294, 1, 143)  # earlier rounds' draws and this round's x_T
+        noises = {i: tape.randn(B, 294, 1, 143) for i in range(pn - 1, -1, -1)}
+        batch = {'cond': torch.from_numpy(g[f"r{it}_cond"]).to(dev)}
+        for i, nxt in ((6, f"r{it}_xt5"), (1, f"r{it}_xt0"), (0, f"r{it}_val_pose")):
+            dp._randn_like = lambda x, _n=noises[i]: _n
+            o = dp.p_sample_with_grad(mp, batch, torch.from_numpy(g[f"r{it}_xt{i}"]).to(dev), t_rows[i], clip_denoised=False,
+                                      grad_type='amass', _step_index=i)
+            ref = torch.from_numpy(g[nxt])
+            err = float((o['sample'].cpu() - ref).abs().max())
+            rel = err / float(ref.abs().max())
+            print(f"round {it} guided step i={i}: teacher-forced max err {err:.3e} (|x| {float(ref.abs().max()):.1f}, rel {rel:.2e})")
+            if i == 0:
+                assert err < TOL, (it, i, err)       # final output = PoseNet(x_1): absolute 1e-4
+            else:
+                assert rel < 1e-3, (it, i, err, rel)  # |x| ~ 1e3 mid-chain: relative bound
+
+
+def test_pipeline_flag_variants_run(cuda_device):
+    """infill_traj + 'full' occlusion, non-noisy conditioning, early_stop: shapes and batch side effects of the driver."""
+    dev = cuda_device
+    ds_pose = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    ds_traj = synthetic.make_dataset('traj', seed=3, realistic_std=True)
+    mp, mt, mc, *_ = _models(dev, ds_pose, ds_traj)
+    body = BodyModel.create('', device=dev, seed=0)
+    dp, dt, dc = _diffusions(dev, 4, pose_steps=1000, pose_respacing="3" + ",0" * 19)
+    for kw in (dict(infill_traj=True, mask_scheme='full', traj_mask_ratio=0.1),
+               dict(input_noise=False, mask_scheme='upper', iter2_cond_noisy_traj=False, iter2_cond_noisy_pose=False),
+               dict(mask_scheme='full', iter2_cond_noisy_pose=False)):
+        torch.manual_seed(0)
+        pose, traj = synthetic.pipeline_batches(2, 5, ds_pose, device=dev)
+        args = pipeline.make_args(sample_iter=2, **kw)
+        vp, vt, tn = pipeline.run_rounds(args, mp, mt, mc, dp, dt, dc, ds_pose, ds_traj, body, pose, traj)
+        assert vp.shape == (2, 294, 1, 143) and vt.shape == (2, 144, 13) and bool(torch.isfinite(vp).all())
+        assert pose['motion_repr_clean'].shape == (2, 294, 1, 143) and pose['cond'].shape == (2, 294, 1, 143)
+        assert traj['control_cond'].shape == (2, 144, 272)
+        rec = pipeline.reconstruct_outputs(args, ds_pose, body, pose, vp, tn, return_verts=True)
+        assert rec['smpl_verts_rec'].shape == (2, 143, 10475, 3) and rec['rec_ric_data_rec_from_abs_traj'].shape == (2, 143, 22, 3)
+        payload = pipeline.result_dict(args, [rec])
+        assert payload['motion_repr_rec_list'].shape == (2, 143, 294)
+        assert ('rec_ric_data_noisy_list' in payload) == bool(args.input_noise)
+
+
+def test_guided_tail_at_benchmark_size(cuda_device):
+    """Guided tail of the PoseNet sampler at the benchmark size: 32 clips x 143 frames, respaced steps t = 50 .. 0 of the
+    1000-step schedule, in-loop skating guidance on every step, CUDA path vs the CPU oracle fed the same noise.
+    Free-running and teacher-forced errors are printed (committed under profiles/); only what is well-posed is asserted:
+    every teacher-forced step and the unguided chain."""
+    dev = cuda_device
+    B, T = 32, 143
+    ds = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    mp, _, _, sd_p, _, _ = _models(dev, ds, synthetic.make_dataset('traj', seed=3, realistic_std=True))
+    body_o = synthetic.smplx_like_model(0)
+    a = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
+    d = diffusion.create_gaussian_diffusion(a, diffusion, diffusion.SpacedDiffusionPoseNet, 1000, '', dev)
+    tables, tmap = do.create_diffusion('cosine', 1000, '')
+    init = synthetic.plausible_motion(B, T, 21, ds)
+    cond = init.clone()
+    tape = NoiseTape(22)
+    first = 50
+    x = do.q_sample(tables, first, init, tape.randn(B, 294, 1, T))
+    mean_p, std_p = torch.from_numpy(ds.Mean), torch.from_numpy(ds.Std)
+    t_rows = d._t_rows(B, dev)
+    batch = {'cond': cond.to(dev)}
+    x_free = x.to(dev)
+    worst_tf, worst_free, lines = 0.0, 0.0, []
+    for i in range(first, -1, -1):
+        nz = tape.randn(B, 294, 1, T)
+        x_next, _ = pipeline_oracle.posenet_guided_step(tables, tmap, i, x, cond, sd_p, mean_p, std_p, body_o, nz)
+        d._randn_like = lambda t_, _n=nz.to(dev): _n
+        o_tf = d.p_sample_with_grad(mp, batch, x.to(dev), t_rows[i], clip_denoised=False, grad_type='amass', _step_index=i)
+        o_fr = d.p_sample_with_grad(mp, batch, x_free, t_rows[i], clip_denoised=False, grad_type='amass', _step_index=i)
+        x_free = o_fr['sample']
+        e_tf = float((o_tf['sample'].cpu() - x_next).abs().max())
+        e_fr = float((x_free.cpu() - x_next).abs().max())
+        mag = float(x_next.abs().max())
+        lines.append(f"t={i:2d} |x|={mag:8.2f} teacher-forced {e_tf:.3e} free-running {e_fr:.3e}")
+        worst_tf, worst_free = max(worst_tf, e_tf / max(1.0, mag)), max(worst_free, e_fr)
+        x = x_next
+    print("guided tail 32x143, t=50..0 (CUDA vs CPU oracle):\n" + "\n".join(lines))
+    print(f"guided tail summary: worst teacher-forced error / max(1,|x|) = {worst_tf:.3e}; final free-running error = "
+          f"{float((x_free.cpu() - x).abs().max()):.3e}; worst free-running = {worst_free:.3e}")
+    assert worst_tf < 1e-3

@@ -259,3 +259,99 @@ def test_q_sample_matches_oracle(cuda_device):
     y = d.q_sample(xs.to(cuda_device), t, nz.to(cuda_device)).cpu()
     for b, i in enumerate([0, 400, 999]):
         assert torch.equal(y[b], do.q_sample(tables, i, xs[b], nz[b]))
+
+
+def test_recycled_condition_address_is_not_mistaken_for_the_cached_one(posenet, cuda_device):
+    """Regression (round-1 advisor finding): the driver frees and rebuilds batch['cond'] per batch; the caching allocator
+    hands the new tensor the old address with the same version count.  The step-invariant embedding must follow the tensor
+    OBJECT, and every sampling loop must re-embed its condition."""
+    m, sd = posenet
+    B, T = 2, 16
+    x = torch.randn(B, 294, 1, T, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    ts = torch.tensor([10, 500], device=cuda_device)
+    outs, ptrs = [], []
+    for k in range(4):
+        cond = synthetic.posenet_batch(B, T, 40 + k)['cond'].to(cuda_device)  # fresh tensor, previous one freed below
+        cond[:, :, :, 0] = 0.0                                                # same number of in-place edits each time
+        ptrs.append((cond.data_ptr(), cond._version))
+        outs.append(m({'x_t': x, 'cond': cond}, ts).cpu())
+        ref = posenet_oracle.posenet_forward(sd, x.cpu(), cond.cpu(), ts.cpu())
+        assert float((outs[-1] - ref).abs().max()) < TOL, k
+        del cond
+    assert len(set(ptrs)) < 4, "allocator did not recycle the address: the scenario was not exercised"
+    for k in range(1, 4):
+        assert float((outs[k] - outs[k - 1]).abs().max()) > 1e-3
+    # and through the sampler: two loops, same-shaped conditions rebuilt in between
+    d = _diff(1000, 'ddim3', cuda_device)
+    finals = []
+    for k in range(2):
+        cond = synthetic.posenet_batch(B, T, 60 + k)['cond'].to(cuda_device)
+        tape = NoiseTape(5, cuda_device)
+        d._randn, d._randn_like = tape.randn, tape.randn_like
+        finals.append(d.p_sample_loop(m, {'cond': cond}, [B, 294, 1, T], clip_denoised=False).cpu())
+        del cond
+    assert float((finals[0] - finals[1]).abs().max()) > 1e-3
+
+
+def test_out_of_range_timestep_poisons_the_output(posenet, cuda_device):
+    """The reference raises on pe[t] with a bad t; the kernel cannot raise, so it must not return a plausible embedding."""
+    m, _ = posenet
+    B, T = 2, 8
+    cond = synthetic.posenet_batch(B, T, 9)['cond'].to(cuda_device)
+    x = torch.randn(B, 294, 1, T, device=cuda_device)
+    y = m({'x_t': x, 'cond': cond}, torch.tensor([5, 5000], device=cuda_device))
+    assert bool(torch.isfinite(y[0]).all()) and bool(torch.isnan(y[1, 22:]).all())
+    with pytest.raises(Exception):
+        m({'x_t': x, 'cond': cond}, torch.tensor([5.0, 6.0], device=cuda_device))
+
+
+def test_eval_losses_default_compute_loss_and_guards(posenet, cuda_device):
+    """eval_losses with its default compute_loss=True (test_posenet.py:178) returns the reference's loss dictionary; DDIM
+    respacing with guidance / early_stop is rejected BEFORE sampling."""
+    m, _ = posenet
+    B, T = 2, 16
+    d = _diff(1000, 'ddim4', cuda_device)
+    clean = synthetic.plausible_motion(B, T, 4, m.dataset).to(cuda_device)
+    batch = {'cond': clean.clone(), 'motion_repr_clean': clean}
+    loss, out = d.eval_losses(model=m, batch=batch, shape=[B, 294, 1, T], progress=False, clip_denoised=False,
+                              cond_fn_with_grad=False)
+    assert out.shape == (B, 294, 1, T) and 'loss' in loss and 'loss_foot_skating_from_smpl' in loss and len(loss) == 15
+    calls = []
+    real = m.forward
+    m.forward = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    with pytest.raises(Exception):
+        d.eval_losses(model=m, batch=batch, shape=[B, 294, 1, T], timestep_respacing='ddim4', cond_fn_with_grad=True,
+                      grad_type='amass', compute_loss=False)
+    with pytest.raises(Exception):
+        d.eval_losses(model=m, batch=batch, shape=[B, 294, 1, T], timestep_respacing='ddim4', early_stop=True,
+                      compute_loss=False)
+    m.forward = real
+    assert not calls, "the guard must fire before any denoiser step"
+
+
+def test_prox_guidance_schedule_runs_both_terms(posenet, cuda_device):
+    """grad_type='prox' (test_prox_egobody.py:316-323): 2-D reprojection guidance (3e5) then skating guidance (1e5) on
+    step indices <= 100."""
+    m, _ = posenet
+    B, T = 2, 12
+    dev = cuda_device
+    ds = m.dataset
+    ds.cam_R, ds.cam_t = torch.tensor([[1., 0, 0], [0, 0, 1], [0, -1, 0]], device=dev), torch.tensor([[0., -4, 1]], device=dev)
+    d = _diff(1000, "3" + ",0" * 19, dev)
+    init = synthetic.plausible_motion(B, T, 4, ds).to(dev)
+    g = torch.Generator().manual_seed(1)
+    batch = {'cond': init.clone(), 'transf_matrix': torch.eye(4, device=dev).repeat(B, 1, 1),
+             'focal_length': torch.tensor([[1000., 1000.]], device=dev).repeat(B, 1),
+             'camera_center': torch.tensor([[900., 500.]], device=dev).repeat(B, 1),
+             'keypoints_2d': torch.cat([900 + 100 * torch.randn(B, T + 2, 22, 2, generator=g),
+                                        torch.ones(B, T + 2, 22, 1)], dim=-1).to(dev)}
+    used = []
+    r2d, rsk = m.guide_2d_projection_with_smpl, m.guide_skating_with_smpl
+    m.guide_2d_projection_with_smpl = lambda *a, **k: (used.append('2d'), r2d(*a, **k))[1]
+    m.guide_skating_with_smpl = lambda *a, **k: (used.append('sk'), rsk(*a, **k))[1]
+    torch.manual_seed(0)
+    _, out = d.eval_losses(model=m, batch=batch, shape=[B, 294, 1, T], progress=False, clip_denoised=False,
+                           cond_fn_with_grad=True, grad_type='prox', compute_loss=False)
+    del m.guide_2d_projection_with_smpl, m.guide_skating_with_smpl
+    assert used == ['2d', 'sk'] * 3 and bool(torch.isfinite(out).all())
+    delattr(ds, 'cam_R'), delattr(ds, 'cam_t')

@@ -145,3 +145,40 @@ def test_control_chain_properties_at_config3_size(nets, cuda_device):
     ref = trajnet_oracle.trajnet_forward(sd, x_in, batch['cond'][:2].cpu(), torch.zeros(2, dtype=torch.long),
                                          batch['control_cond'][:2].cpu())
     assert float((outs[0]['sample'][:2].cpu() - ref).abs().max()) < TOL
+
+
+def test_recycled_condition_addresses_are_not_mistaken_for_the_cached_ones(nets, cuda_device):
+    """Regression (round-1 advisor finding): cond / control_cond rebuilt per batch can reuse the freed tensors' addresses and
+    version counts; the cached condition pyramid must follow the tensor objects."""
+    m, sd = nets[True]
+    B, T = 2, 32
+    x = torch.randn(B, T, 13, generator=torch.Generator().manual_seed(1))
+    ts = torch.tensor([3, 40])
+    outs, ptrs = [], []
+    for k in range(4):
+        b = {kk: v.to(cuda_device) for kk, v in synthetic.trajnet_batch(B, T, 70 + k, control=True).items()}
+        b['x_t'] = x.to(cuda_device)
+        ptrs.append((b['cond'].data_ptr(), b['control_cond'].data_ptr()))
+        y = m(b, ts.to(cuda_device)).cpu()
+        ref = trajnet_oracle.trajnet_forward(sd, x, b['cond'].cpu(), ts, control_cond=b['control_cond'].cpu())
+        assert float((y - ref).abs().max()) < TOL, k
+        outs.append(y)
+        del b
+    assert len(set(ptrs)) < 4, "allocator did not recycle the addresses: the scenario was not exercised"
+    for k in range(1, 4):
+        assert float((outs[k] - outs[k - 1]).abs().max()) > 1e-3
+
+
+def test_eval_losses_default_compute_loss(nets, cuda_device):
+    """eval_losses with its default compute_loss=True (test_trajnet.py:154) returns the reference's loss dictionary."""
+    from rohm_b200.body_model import BodyModel
+    m, _ = nets[False]
+    B, T = 2, 32
+    a = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
+    d = diffusion.create_gaussian_diffusion(a, diffusion, diffusion.SpacedDiffusionTrajNet, 5, '', cuda_device)
+    b = {k: v.to(cuda_device) for k, v in synthetic.trajnet_batch(B, T, 5).items()}
+    m.device = cuda_device
+    loss, out = d.eval_losses(model=m, batch=b, shape=[B, T, 13], progress=False, clip_denoised=False,
+                              cond_fn_with_grad=True, smplx_model=BodyModel.create('', device=cuda_device))
+    assert out.shape == (B, T, 13) and 'loss' in loss and float(loss['loss_root_pos_global_from_rel_traj']) == 0.0
+    assert all(bool(torch.isfinite(v)) for v in loss.values())

@@ -166,3 +166,67 @@ def test_precision_modes_env_and_header_agree(monkeypatch):
     monkeypatch.setenv("ROHM_B200_PRECISION", "bf16")
     with pytest.raises(_lib.RohmB200Error):
         _precision_from_env()
+
+
+def test_body_model_create_refuses_a_missing_model_file(tmp_path):
+    """A non-empty body_model_path without smplx/SMPLX_NEUTRAL.npz must raise (round-1 finding: it silently built the
+    synthetic body); the synthetic model is an explicit opt-in."""
+    from rohm_b200._lib import RohmB200Error
+    from rohm_b200.body_model import BodyModel
+    with pytest.raises(RohmB200Error):
+        BodyModel.create(str(tmp_path / "no_such_dir"))
+    assert BodyModel.create('').v_template.shape == (10475, 3)
+    assert BodyModel.create(str(tmp_path), synthetic_ok=True).posedirs.shape == (486, 10475 * 3)
+    # official layout: <path>/smplx/SMPLX_NEUTRAL.npz
+    m = synthetic.smplx_like_model(1, num_verts=64)
+    os.makedirs(tmp_path / "smplx")
+    sd = np.zeros((64, 3, 400), np.float32)
+    sd[:, :, :10], sd[:, :, 300:310] = m["shapedirs"][:, :, :10].numpy(), m["shapedirs"][:, :, 10:].numpy()
+    kt = np.stack([np.array([2 ** 32 - 1] + m["parents"][1:], dtype=np.int64), np.arange(55)])
+    np.savez(tmp_path / "smplx" / "SMPLX_NEUTRAL.npz", v_template=m["v_template"].numpy(), shapedirs=sd,
+             posedirs=m["posedirs"].numpy().T.reshape(64, 3, 486), J_regressor=m["J_regressor"].numpy(),
+             weights=m["lbs_weights"].numpy(), kintree_table=kt)
+    b = BodyModel.create(str(tmp_path))
+    assert torch.equal(b.posedirs, m["posedirs"]) and torch.equal(b.shapedirs, m["shapedirs"])
+    assert b.parents.tolist() == m["parents"]
+
+
+def test_posenet_adopts_smplx_buffers_of_a_reference_checkpoint():
+    """A reference checkpoint stores the whole smplx module under smplx_model.* (more buffers than RoHM's calls read);
+    strict loading must succeed and the body tensors must be taken from the checkpoint."""
+    from rohm_b200.posenet import PoseNet
+    ds = synthetic.make_dataset('pose')
+    m = PoseNet(dataset=ds, body_feat_dim=294, latent_dim=512, ff_size=1024, num_layers=8, num_heads=4, device=None,
+                traj_feat_dim=22)
+    sd = synthetic.synth_state_dict(m, 1)
+    body = synthetic.smplx_like_model(7)
+    sd = {k: v for k, v in sd.items() if not k.startswith("smplx_model.")}
+    sd.update({"smplx_model.v_template": body["v_template"], "smplx_model.shapedirs": body["shapedirs"][:, :, :10],
+               "smplx_model.expr_dirs": body["shapedirs"][:, :, 10:], "smplx_model.posedirs": body["posedirs"],
+               "smplx_model.J_regressor": body["J_regressor"], "smplx_model.lbs_weights": body["lbs_weights"],
+               "smplx_model.parents": torch.tensor([-1] + body["parents"][1:]),
+               "smplx_model.faces_tensor": torch.zeros(20908, 3, dtype=torch.long),
+               "smplx_model.global_orient": torch.zeros(1, 3), "smplx_model.pose_mean": torch.zeros(165)})
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.smplx_model.v_template, body["v_template"])
+    assert torch.equal(m.smplx_model.shapedirs, body["shapedirs"])
+    # own-format state dicts still round-trip
+    m.load_state_dict(m.state_dict(), strict=True)
+
+
+def test_sampler_guards_fire_before_any_denoiser_call():
+    """DDIM respacing with guidance / early-stop and a timestep map beyond the positional table are rejected up front."""
+    from rohm_b200._lib import RohmB200Error
+
+    class Boom:
+        def parameters(self):
+            raise AssertionError("the sampler touched the model before validating its arguments")
+
+        def __call__(self, *a, **k):
+            raise AssertionError("denoiser called")
+
+    d = _make('cosine', 1000, 'ddim10')
+    for kw in (dict(cond_fn_with_grad=True, grad_type='amass'), dict(early_stop=True)):
+        with pytest.raises(RohmB200Error):
+            d.eval_losses(model=Boom(), batch={}, shape=[1, 294, 1, 8], timestep_respacing='ddim10', compute_loss=False, **kw)

@@ -57,9 +57,10 @@ def import_reference():
     import data_loaders.motion_representation as mr
     import data_loaders.common.quaternion as quat
     import utils.konia_transform as kt
+    import utils.other_utils as ou
     sys.path.pop(0)
     return types.SimpleNamespace(gdp=gdp, gdt=gdt, respace=respace, model_util=model_util, posenet=ref_posenet,
-                                 trajnet=ref_trajnet, mr=mr, quat=quat, kt=kt)
+                                 trajnet=ref_trajnet, mr=mr, quat=quat, kt=kt, ou=ou)
 
 
 TABLES = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "alphas_cumprod_next", "sqrt_alphas_cumprod",
@@ -272,11 +273,218 @@ def gen_kinematics(ref):
     print("kinematics.npz  grad absmax", float(grad.abs().max()))
 
 
+def _rep_dict(full):
+    rep, cur = {}, 0
+    for name in ko.REPR_LIST:
+        rep[name] = full[..., cur:cur + ko.REPR_DIM_DICT[name]]
+        cur += ko.REPR_DIM_DICT[name]
+    return rep
+
+
+def gen_glue(ref):
+    """Driver-side functions around the loops: get_repr_smplx (trajectory block), 'joint_rel_traj' recovery, the two
+    compute_losses_with_smpl dictionaries and the 2-D reprojection guidance gradient (reference autograd)."""
+    out = {}
+    body = _StubBody()
+    ds = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    # (a) get_repr_smplx on SMPL-X joints of a plausible motion, 2 clips x 24 frames (+ a clip that faces -y at one frame so
+    #     the NaN repair of motion_representation.py:212-215 is exercised)
+    x = synthetic.plausible_motion(2, 24, 61, ds)
+    full = x[:, :, 0].permute(0, 2, 1) * torch.from_numpy(ds.Std) + torch.from_numpy(ds.Mean)
+    rep = _rep_dict(full)
+    joints = ref.mr.recover_from_repr_smpl(rep, recover_mode='smplx_params', smplx_model=body).numpy()
+    traj = []
+    for i in range(2):
+        go = ref.kt.rotation_matrix_to_angle_axis(ref.quat.rot6d_to_rotmat(rep['smplx_rot_6d'][i]))
+        bp = ref.kt.rotation_matrix_to_angle_axis(ref.quat.rot6d_to_rotmat(rep['smplx_body_pose_6d'][i].reshape(-1, 6)))
+        params = {'transl': rep['smplx_trans'][i].numpy(), 'global_orient': go.numpy(),
+                  'body_pose': bp.reshape(-1, 63).numpy(), 'betas': rep['smplx_betas'][i].numpy()}
+        d = ref.mr.get_repr_smplx(positions=joints[i], smplx_params_dict=params, feet_vel_thre=5e-5)
+        traj.append(np.concatenate([d[k] for k in ko.REPR_LIST], axis=-1)[:, 0:22])
+    out["repr_x"] = x.numpy()
+    out["repr_joints"] = joints
+    out["repr_traj22"] = np.asarray(traj)
+    out["repr_meta"] = np.array([2, 24, 61, 3])
+    # NaN repair: hips/shoulders arranged so that the forward direction is exactly -y at frame 5
+    pos = joints[0].copy()
+    pos[5, 1], pos[5, 2], pos[5, 17], pos[5, 16] = [0, 0, 0], [1, 0, 0], [0, 0, 0], [1, 0, 0]
+    go0 = ref.kt.rotation_matrix_to_angle_axis(ref.quat.rot6d_to_rotmat(rep['smplx_rot_6d'][0])).numpy()
+    params = {'transl': rep['smplx_trans'][0].numpy(), 'global_orient': go0,
+              'body_pose': np.zeros((24, 63), np.float32), 'betas': rep['smplx_betas'][0].numpy()}
+    d = ref.mr.get_repr_smplx(positions=pos, smplx_params_dict=params, feet_vel_thre=5e-5)
+    out["nan_positions"], out["nan_go"] = pos, go0
+    out["nan_traj22"] = np.concatenate([d[k] for k in ko.REPR_LIST], axis=-1)[:, 0:22]
+    # (b) joint_rel_traj recovery
+    out["rel_traj_joints"] = ref.mr.recover_from_repr_smpl(rep, recover_mode='joint_rel_traj', smplx_model=body).numpy()
+    # (c) evaluation loss dictionaries
+    mp, _ = build_ref_posenet(ref, seed=1)
+    mp.dataset, mp.device = ds, 'cpu'
+    g = torch.Generator().manual_seed(62)
+    rec = x + 0.05 * torch.randn(x.shape, generator=g)
+    ld = mp.compute_losses_with_smpl({'motion_repr_clean': x}, rec, smplx_model=body, epoch=0)
+    out["pose_loss_names"] = np.array(list(ld.keys()))
+    out["pose_loss_values"] = np.array([float(v) for v in ld.values()], dtype=np.float64)
+    out["pose_loss_rec"] = rec.numpy()
+    dst = synthetic.make_dataset('traj', seed=3, realistic_std=True)
+    mt, _ = build_ref_trajnet(ref, seed=2, control=False)
+    mt.dataset, mt.device = dst, 'cpu'
+    clean_cl = x[:, :, 0].permute(0, 2, 1).contiguous()
+    traj_rec = torch.cat([clean_cl[..., 0:1], clean_cl[..., 2:4], clean_cl[..., 6:7], clean_cl[..., 7:13],
+                          clean_cl[..., 16:19]], dim=-1) + 0.05 * torch.randn(2, 24, 13, generator=g)
+    ld = mt.compute_losses_with_smpl({'motion_repr_clean': clean_cl}, traj_rec, smplx_model=body)
+    out["traj_loss_names"] = np.array(list(ld.keys()))
+    out["traj_loss_values"] = np.array([float(v) for v in ld.values()], dtype=np.float64)
+    out["traj_loss_rec"] = traj_rec.numpy()
+    # (d) 2-D reprojection guidance (autograd through the reference code + stub body)
+    B, T = 2, 24
+    cam2world = torch.eye(4)
+    ang = 0.3
+    cam2world[:3, :3] = torch.tensor([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]).float() @ \
+        torch.tensor([[1., 0, 0], [0, 0, 1], [0, -1, 0]])
+    cam2world[:3, 3] = torch.tensor([0.3, -4.0, 1.2])
+    ds.cam_R, ds.cam_t = cam2world[:3, :3].reshape(3, 3).float(), cam2world[:3, 3].reshape(1, 3).float()
+    tm = torch.eye(4).repeat(B, 1, 1)
+    for b in range(B):
+        a = 0.4 * (b + 1)
+        tm[b, :3, :3] = torch.tensor([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]).float()
+        tm[b, :3, 3] = torch.tensor([0.1 * b, -0.2, 0.05])
+    batch = {'x_t': x, 'transf_matrix': tm.float(), 'focal_length': torch.tensor([[1060.0, 1058.0]]).repeat(B, 1),
+             'camera_center': torch.tensor([[951.0, 536.0]]).repeat(B, 1)}
+    kp = torch.zeros(B, T + 2, 22, 3)
+    kp[..., 0] = 951.0 + 300.0 * torch.randn(B, T + 2, 22, generator=g)
+    kp[..., 1] = 536.0 + 200.0 * torch.randn(B, T + 2, 22, generator=g)
+    kp[..., 2] = (torch.rand(B, T + 2, 22, generator=g) > 0.3).float() * torch.rand(B, T + 2, 22, generator=g)
+    batch['keypoints_2d'] = kp
+    gr = mp.guide_2d_projection_with_smpl(batch, {'pred_xstart': x}, None, compute_grad='x_0')
+    out["proj_grad"] = gr.detach().numpy()
+    out["proj_cam_R"], out["proj_cam_t"] = ds.cam_R.numpy(), ds.cam_t.numpy()
+    out["proj_transf"], out["proj_focal"], out["proj_center"] = tm.numpy(), batch['focal_length'].numpy(), batch['camera_center'].numpy()
+    out["proj_kp"] = kp.numpy()
+    np.savez_compressed(os.path.join(OUT, "glue.npz"), **out)
+    print("glue.npz  proj grad absmax", float(gr.abs().max()), " nan-repair traj finite:", bool(np.isfinite(out["nan_traj22"]).all()))
+
+
+POSE_RESPACING = "12" + ",0" * 19
+POSE_RECORDED_STEPS = (6, 5, 1, 0)
+
+
+def gen_pipeline(ref):
+    """BASELINE config 4 in miniature, driven through the UNMODIFIED reference: the call sequence of
+    test_amass_full.py:231-384 (TrajNet -> host glue -> PoseNet with in-loop skating guidance, 2 rounds, round 2 through
+    TrajControl) on 2 clips x 144 frames with 10-step TrajNet and 12-step PoseNet schedules (every PoseNet step guided)."""
+    get_repr_smplx = ref.mr.get_repr_smplx
+    out = {}
+    B, Tn_steps, Pn_steps, rounds = 2, 10, 12, 2
+    ds_pose = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    ds_traj = synthetic.make_dataset('traj', seed=3, realistic_std=True)
+    body = _StubBody()
+    mp, _ = build_ref_posenet(ref, seed=1)
+    mp.dataset, mp.device = ds_pose, 'cpu'
+    mt, _ = build_ref_trajnet(ref, seed=2, control=False)
+    mc, _ = build_ref_trajnet(ref, seed=4, control=True)
+    args = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
+    mk = ref.model_util.create_gaussian_diffusion
+    # PoseNet: the last 50 steps of the 1000-step schedule thinned to 12 (respacing "12,0,...,0" over 20 sections of 50),
+    # i.e. the regime the guidance weights were tuned for (posterior variance ~1e-3..1e-5); every step index is <= 50, so
+    # every step is guided
+    dp = mk(args, gd=ref.gdp, return_class=ref.respace.SpacedDiffusionPoseNet, num_diffusion_timesteps=1000,
+            timestep_respacing=POSE_RESPACING, device='cpu')
+    dt = mk(args, gd=ref.gdt, return_class=ref.respace.SpacedDiffusionTrajNet, num_diffusion_timesteps=Tn_steps, device='cpu')
+    dc = mk(args, gd=ref.gdt, return_class=ref.respace.SpacedDiffusionTrajNet, num_diffusion_timesteps=Tn_steps, device='cpu')
+    pose, traj = synthetic.pipeline_batches(B, 71, ds_pose)
+    tfd, pfd = ds_traj.traj_feat_dim, ds_traj.pose_feat_dim
+    val_pose = None
+    with _patched_th(ref.gdp, 72), _patched_th(ref.gdt, 73):
+        for it in range(rounds):
+            shape = list(traj['motion_repr_clean'][:, :, 0:tfd].shape)
+            if it == 0:
+                _, val_traj = dt.eval_losses(model=mt, batch=traj, shape=shape, progress=False, clip_denoised=False,
+                                             timestep_respacing='', cond_fn_with_grad=True, compute_loss=False, smplx_model=body)
+            else:
+                traj['control_cond'] = torch.zeros([shape[0], shape[1], pfd])
+                traj['control_cond'][:, 0:-1] = val_pose[:, :, 0].permute(0, 2, 1)[:, :, -pfd:]
+                traj['control_cond'][:, -1] = traj['control_cond'][:, -2].clone()
+                _, val_traj = dc.eval_losses(model=mc, batch=traj, shape=shape, progress=False, clip_denoised=False,
+                                             timestep_respacing='', cond_fn_with_grad=True, compute_loss=False, smplx_model=body)
+            comp = traj['motion_repr_clean'].clone()
+            comp[..., 0], comp[..., 2:4], comp[..., 6] = val_traj[..., 0], val_traj[..., 1:3], val_traj[..., 3]
+            comp[..., 7:13], comp[..., 16:19] = val_traj[..., 4:10], val_traj[..., 10:13]
+            if it == 0:
+                traj['motion_repr_noisy'] = comp
+            full = comp.detach().numpy() * ds_traj.Std + ds_traj.Mean
+            rep = _rep_dict(torch.from_numpy(full))
+            joints, _ = ref.mr.recover_from_repr_smpl(rep, recover_mode='smplx_params', smplx_model=_VertsBody(body), return_verts=True)
+            joints = joints.detach().numpy()
+            rows = []
+            for i in range(B):
+                go = ref.kt.rotation_matrix_to_angle_axis(ref.quat.rot6d_to_rotmat(rep['smplx_rot_6d'][i]))
+                bp = ref.kt.rotation_matrix_to_angle_axis(ref.quat.rot6d_to_rotmat(rep['smplx_body_pose_6d'][i].reshape(-1, 6)))
+                d = get_repr_smplx(positions=joints[i], smplx_params_dict={
+                    'transl': rep['smplx_trans'][i].numpy(), 'global_orient': go.numpy(),
+                    'body_pose': bp.reshape(-1, 63).numpy(), 'betas': rep['smplx_betas'][i].numpy()}, feet_vel_thre=5e-5)
+                row = np.concatenate([d[k] for k in ko.REPR_LIST], axis=-1)
+                rows.append(((row - ds_pose.Mean) / ds_pose.Std)[:, 0:22])
+            traj_full = torch.tensor(np.asarray(rows))
+            if it == 0:
+                pose['motion_repr_noisy'] = pose['motion_repr_noisy'][:, 0:-1]
+                pose['motion_repr_clean'] = pose['motion_repr_clean'][:, 0:-1]
+            pose['cond'] = pose['motion_repr_noisy'].clone()  # input_noise, iter2_cond_noisy_pose
+            pose['cond'][:, :, 0:22] = traj_full
+            ids = np.asarray([1, 2, 4, 5, 7, 8, 10, 11])      # mask_scheme 'lower', applied in every round
+            for k in range(3):
+                pose['cond'][:, :, 22 + ids * 3 + k] = 0.
+                pose['cond'][:, :, 22 + 66 + ids * 3 + k] = 0.
+            for k in range(6):
+                pose['cond'][:, :, 22 + 132 + (ids - 1) * 6 + k] = 0.
+            pose['cond'][:, :, -4:] = 0.
+            pose['cond'] = torch.permute(pose['cond'], (0, 2, 1)).unsqueeze(-2)
+            if it == 0:
+                pose['motion_repr_clean'] = torch.permute(pose['motion_repr_clean'], (0, 2, 1)).unsqueeze(-2)
+            # The guided chain is chaotic at this batch size (3e6-weighted gradient of a hard-masked mean over only 2 clips:
+            # |x_t| reaches 1e3 and a 1e-6 perturbation grows to O(1) within three steps), so the states entering steps
+            # 6, 5, 1 and 0 are recorded for teacher-forced comparison of single guided steps and of the final output.
+            seen = {}
+            orig = dp.p_sample_with_grad
+
+            def recording(model, batch, x, t, **kw):
+                seen[int(t[0])] = x.detach().clone()
+                return orig(model, batch, x, t, **kw)
+
+            dp.p_sample_with_grad = recording
+            _, val_pose = dp.eval_losses(model=mp, batch=pose, shape=list(pose['motion_repr_clean'].shape), progress=False,
+                                         clip_denoised=False, timestep_respacing='', cond_fn_with_grad=True, early_stop=False,
+                                         compute_loss=False, grad_type='amass', smplx_model=body)
+            dp.p_sample_with_grad = orig
+            for i in POSE_RECORDED_STEPS:
+                out[f"r{it}_xt{i}"] = seen[i].numpy()
+            out[f"r{it}_val_traj"] = val_traj.detach().numpy()
+            out[f"r{it}_traj_full"] = traj_full.numpy().astype(np.float32)
+            out[f"r{it}_cond"] = pose['cond'].detach().numpy()
+            out[f"r{it}_val_pose"] = val_pose.detach().numpy()
+            print(f"pipeline round {it}: |val_traj| {float(val_traj.abs().max()):.3f} |val_pose| {float(val_pose.abs().max()):.3f}")
+    out["meta"] = np.array([B, Tn_steps, Pn_steps, rounds, 71, 72, 73])
+    np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
+    print("pipeline.npz")
+
+
+class _VertsBody(nn.Module):
+    """The driver asks for vertices (return_verts=True) and discards them; hand back a placeholder of the right shape."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, **kw):
+        o = self.inner(**kw)
+        o.vertices = torch.zeros(o.joints.shape[0], 10475, 3)
+        return o
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = import_reference()
-    which = sys.argv[1:] or ["schedules", "posenet", "trajnet", "sampling", "kinematics"]
+    which = sys.argv[1:] or ["schedules", "posenet", "trajnet", "sampling", "kinematics", "glue", "pipeline"]
     for w in which:
         {"schedules": gen_schedules, "posenet": gen_posenet, "trajnet": gen_trajnet, "sampling": gen_sampling,
-         "kinematics": gen_kinematics}[w](ref)
+         "kinematics": gen_kinematics, "glue": gen_glue, "pipeline": gen_pipeline}[w](ref)
