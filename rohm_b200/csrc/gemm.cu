@@ -95,6 +95,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
 struct EpiParams {
   const float* bias;
   const float* residual;
+  const float2* a_stats;
+  const float* a_corr;
+  const float2* res_stats;
+  const float* res_gamma;
+  const float* res_beta;
+  float2* stats_out;
+  float ln_eps;
   float* out;
   void* out_hi;
   void* out_lo;
@@ -145,10 +152,53 @@ __device__ __forceinline__ void gn_partial_sums(const float (&v)[32], const EpiP
   }
 }
 
+// (mean, rstd) of a 512-wide row from its 8 partial (mean_i, M2_i) over 64 columns each (Chan et al. pairwise combination);
+// row8: 64 contiguous bytes in global memory, written by the previous kernel.
+__device__ __forceinline__ float2 combine_row_stats(const float2* row8, float eps) {
+  const float4* q4 = reinterpret_cast<const float4*>(row8);
+  float4 t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = __ldcg(q4 + i);
+  const float mean = ((t[0].x + t[0].z) + (t[1].x + t[1].z) + (t[2].x + t[2].z) + (t[3].x + t[3].z)) * 0.125f;
+  float m2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d0 = t[i].x - mean, d1 = t[i].z - mean;
+    m2 += fmaf(64.0f * d0, d0, t[i].y) + fmaf(64.0f * d1, d1, t[i].w);
+  }
+  return make_float2(mean, rsqrtf(m2 * (1.0f / 512.0f) + eps));
+}
+
+// One 32 x 32 chunk (row per lane) as an fp16 hi/lo pair: registers -> two SWIZZLE_64B planes of the warp's staging tile
+// (hi at +0, lo at +2048; chunk c of row r at slot c ^ ((r >> 1) & 3)) -> two TMA bulk stores.
+__device__ __forceinline__ void stage_pair_chunk(const float (&v)[32], uint8_t* tb, int lane, const CUtensorMap* st_hi,
+                                                 const CUtensorMap* st_lo, int col0, int row0) {
+  if (lane == 0) ptx::bulk_wait_read_all();  // an earlier bulk store may still be reading the tile
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint2 h0, l0, h1, l1;
+    ptx::split_f16x4(make_float4(v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3]), h0, l0);
+    ptx::split_f16x4(make_float4(v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]), h1, l1);
+    const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(tb + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint4*>(tb + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  }
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_2d(st_hi, tb, col0, row0);
+    ptx::tma_store_2d(st_lo, tb + 2048, col0, row0);
+    ptx::bulk_commit();
+  }
+}
+
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
 // (N-tile index fastest, so CTAs running concurrently share the same A rows in L2).
 // Epilogue variants: 0 = bias + residual + fp32 / hi-lo stores (the PoseNet linears), 1 = the same + exact GELU (FFN1),
-// 2 = everything (other activations, padded-clip row masks, GroupNorm partial sums: TrajNet).  Separate instantiations keep the hot variants' code small (the full
+// 2 = everything (other activations, padded-clip row masks, GroupNorm partial sums: TrajNet), 3 = bias + residual pair +
+// LayerNorm with the row statistics exchanged between the four column-tile CTAs of a row stripe (PoseNet out-proj / FFN2,
+// see GemmParams::ln_gamma).  Separate instantiations keep the hot variants' code small (the full
 // epilogue is ~7000 SASS instructions, most of them predicated-off activation code when unused).
 template <int BLOCK_N, int PASSES, int EPI, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
@@ -164,7 +214,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   // Epilogue parameters are copied from the (3 KB, tensor-map dominated) kernel parameter block into shared memory
   // once: reading them late from the constant bank cost ~0.7 us per first touch (measured with %globaltimer stamps).
   __shared__ EpiParams epi_s;
-  __shared__ __align__(16) float bias_s[Cfg::kAccStages][BLOCK_N];
+  // per-column vectors of the current tile (single-buffered, see the staging block of the epilogue; 227 KB are in use, every
+  // 512 bytes count): bias; LayerNorm folding: c_n of a consumer GEMM, or (EPI 3) gamma | beta of the residual's LayerNorm
+  __shared__ __align__(16) float bias_s[BLOCK_N];
+  __shared__ __align__(16) float corr_s[BLOCK_N];
+  __shared__ __align__(16) float beta_s[EPI == 3 ? BLOCK_N : 4];
+  __shared__ uint64_t res_bar[EPI == 3 ? kEpiWarps : 1];  // EPI 3: one transaction barrier per epilogue warp (residual tile loads)
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -195,6 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps);
     }
+    if (EPI == 3)
+      for (int i = 0; i < kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -209,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     epi_s.acc_scale = p.acc_scale == 0.0f ? 1.0f : p.acc_scale;
     epi_s.tma_store = p.tma_store;
     epi_s.bias_per_row = p.bias_per_row;
+    epi_s.a_stats = p.a_stats, epi_s.a_corr = p.a_corr, epi_s.res_stats = p.res_stats, epi_s.res_gamma = p.res_gamma;
+    epi_s.res_beta = p.res_beta, epi_s.stats_out = p.stats_out, epi_s.ln_eps = p.ln_eps;
     if (p.tma_store) {
       ptx::prefetch_tmap(&p.st_out);
       ptx::prefetch_tmap(&p.st_hi);
@@ -332,11 +391,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       const int64_t orow = static_cast<int64_t>(m) * e.out_row_mul + e.out_row_add;
       const float bias_row = (e.bias != nullptr && e.bias_per_row && row_ok) ? __ldg(e.bias + m) : 0.0f;
 
-      // stage this tile's bias slice (and warm the residual lines) while the MMA warp is still accumulating
+      // stage this tile's per-column vectors while the MMA warp is still accumulating.  Single-buffered: the first barrier
+      // keeps the writers off the vectors until every epilogue thread has finished the previous tile.
       {
         const int i = (warp_idx - 2) * 32 + lane;
-        if (e.bias != nullptr && i < BLOCK_N)
-          bias_s[acc_stage][i] = (!e.bias_per_row && n0 + i < e.N) ? __ldg(e.bias + n0 + i) : 0.0f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
+        if (i < BLOCK_N) {
+          const bool col_ok = n0 + i < e.N;
+          bias_s[i] = (e.bias != nullptr && !e.bias_per_row && col_ok) ? __ldg(e.bias + n0 + i) : 0.0f;
+          if (EPI == 3) {
+            corr_s[i] = e.res_stats != nullptr ? __ldg(e.res_gamma + n0 + i) : 1.0f;
+            beta_s[i] = e.res_stats != nullptr ? __ldg(e.res_beta + n0 + i) : 0.0f;
+          } else {
+            corr_s[i] = (e.a_stats != nullptr && col_ok) ? __ldg(e.a_corr + n0 + i) : 0.0f;
+          }
+        }
         if (e.residual != nullptr && row_ok) {
           const float* r = e.residual + orow * e.ldr + n0 + half * 32;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
@@ -344,9 +413,116 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
       }
+      // LayerNorm folding, consumer side: (mean, rstd) of this thread's A row, fetched while the accumulator is still filling
+      float a_mean = 0.0f, a_rstd = 1.0f;
+      if (EPI != 3 && LEAN && e.a_stats != nullptr && row_ok) {
+        const float2 mr = combine_row_stats(e.a_stats + static_cast<int64_t>(m) * 8, e.ln_eps);
+        a_mean = mr.x, a_rstd = mr.y;
+      }
+      // LayerNorm folding, producer side: the residual tile (this thread: one row, 2 x 32 columns) arrives through TMA into
+      // the warp's staging tile -- with 225 KB of shared memory in use there is no L1, and per-thread 16-byte loads were
+      // measured to slow the operand stream by 40 % -- and is passed through the previous LayerNorm on the fly.
+      float lnv[EPI == 3 ? 2 : 1][EPI == 3 ? 32 : 1];
+      if constexpr (EPI == 3) {
+        float r_mean = 0.0f, r_rstd = 1.0f;
+        if (e.res_stats != nullptr && row_ok) {
+          const float2 mr = combine_row_stats(e.res_stats + static_cast<int64_t>(m) * 8, e.ln_eps);
+          r_mean = mr.x, r_rstd = mr.y;
+        }
+        uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+        uint64_t* rb = &res_bar[warp_idx - 2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c0 = half * 32 + 64 * h2;
+          if (lane == 0) {
+            ptx::bulk_wait_read_all();  // this warp's stores of the previous tile have finished reading the staging tile
+            ptx::mbar_expect_tx(rb, 4096);
+            ptx::tma_load_2d(tb, &p.st_hi, rb, n0 + c0, m0 + q * 32);
+            ptx::tma_load_2d(tb + 2048, &p.st_lo, rb, n0 + c0, m0 + q * 32);
+          }
+          ptx::mbar_wait(rb, static_cast<uint32_t>((2 * tcount + h2) & 1));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+            const uint4 hq = *reinterpret_cast<const uint4*>(tb + off);
+            const uint4 lq = *reinterpret_cast<const uint4*>(tb + 2048 + off);
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+            const uint32_t lw[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+              const int j = 8 * c + 2 * k;
+              lnv[h2][j] = fmaf(((fh.x + fl.x) - r_mean) * r_rstd, corr_s[c0 + j], beta_s[c0 + j]);
+              lnv[h2][j + 1] = fmaf(((fh.y + fl.y) - r_mean) * r_rstd, corr_s[c0 + j + 1], beta_s[c0 + j + 1]);
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy reads above, async-proxy writes (next load / the stores) below
+          __syncwarp();
+        }
+      }
       ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 5);
       ptx::tc_fence_after_sync();
+
+      if constexpr (EPI == 3) {
+        // ===== u = LN_prev(residual) + acc * 2^-s + bias, written in place as an fp16 pair + per-row partial statistics =====
+        static_assert(BLOCK_N == 128 && PASSES == 3 && KIND == kKindF16, "LayerNorm-folding producer: fp16 pairs, 128-wide tiles");
+        const int tile_n = tile_idx % tiles_n;
+        float (&v)[2][32] = lnv;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c0 = half * 32 + 64 * h2;
+          uint32_t raw[32], raw2[32];
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
+                                 (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+          ptx::tmem_ld_32x32(taddr, raw);
+          ptx::tmem_ld_32x32(taddr + BLOCK_N, raw2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
+            v[h2][j] += fmaf(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]), e.acc_scale, b4.x);
+            v[h2][j + 1] += fmaf(__uint_as_float(raw[j + 1]) + __uint_as_float(raw2[j + 1]), e.acc_scale, b4.y);
+            v[h2][j + 2] += fmaf(__uint_as_float(raw[j + 2]) + __uint_as_float(raw2[j + 2]), e.acc_scale, b4.z);
+            v[h2][j + 3] += fmaf(__uint_as_float(raw[j + 3]) + __uint_as_float(raw2[j + 3]), e.acc_scale, b4.w);
+          }
+        }
+        if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 8);
+        // the accumulator is drained: hand it back so that the MMA warp can start the next tile
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+        // partial row statistics over this thread's 64 columns for the consumers of LN(u)
+        float s1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s1 += v[0][j] + v[1][j];
+        const float mean_i = s1 * (1.0f / 64.0f);
+        float m2_i = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d0 = v[0][j] - mean_i, d1 = v[1][j] - mean_i;
+          m2_i = fmaf(d0, d0, fmaf(d1, d1, m2_i));
+        }
+        if (row_ok) e.stats_out[static_cast<int64_t>(m) * 8 + tile_n * 2 + half] = make_float2(mean_i, m2_i);
+        if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 9);
+        uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+        const bool group_full = (m0 + q * 32 + 32 <= e.M);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int nb = n0 + half * 32 + 64 * h2;
+          if (group_full) {
+            stage_pair_chunk(v[h2], tb, lane, &p.st_hi, &p.st_lo, nb, m0 + q * 32);
+          } else if (row_ok) {  // ragged last row group: per-thread stores
+            __half* oh = static_cast<__half*>(e.out_hi) + static_cast<int64_t>(m) * e.lds + nb;
+            __half* ol = static_cast<__half*>(e.out_lo) + static_cast<int64_t>(m) * e.lds + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ptx::split_f16(v[h2][j], oh[j], ol[j]);
+          }
+        }
+        if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 6);
+        continue;
+      }
 
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
@@ -371,10 +547,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= e.acc_scale;
           }
+          if (LEAN && e.a_stats != nullptr) {  // LayerNorm folding: out = rstd (acc - mean c_n) + d_n
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(&corr_s[c0 + j]);
+              v[j] = a_rstd * fmaf(-a_mean, c4.x, v[j]), v[j + 1] = a_rstd * fmaf(-a_mean, c4.y, v[j + 1]);
+              v[j + 2] = a_rstd * fmaf(-a_mean, c4.z, v[j + 2]), v[j + 3] = a_rstd * fmaf(-a_mean, c4.w, v[j + 3]);
+            }
+          }
           if (e.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[acc_stage][c0 + j]);
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
               v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
             }
             if (e.bias_per_row) {
@@ -467,9 +651,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (nb >= e.N) continue;  // warp-uniform
 
         if (row_ok) {
+          if (LEAN && e.a_stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = a_rstd * fmaf(-a_mean, corr_s[c0 + j], v[j]);
+          }
           if (e.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_s[acc_stage][c0 + j];  // smem broadcast; zero beyond N
+            for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];  // smem broadcast; zero beyond N
             if (e.bias_per_row) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += bias_row;
@@ -647,8 +835,13 @@ static cudaError_t set_attr() {
   e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            TileCfg<BLOCK_N, PASSES>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 2, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 2, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  if constexpr (BLOCK_N == 128 && PASSES == 3 && KIND == kKindF16)
+    e = cudaFuncSetAttribute(gemm_tile_kernel<BLOCK_N, PASSES, 3, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TileCfg<BLOCK_N, PASSES>::kSmemBytes);
+  return e;
 }
 
 template <int BLOCK_N, int PASSES, int KIND>
@@ -658,6 +851,19 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   auto kern = (plain && p.act == kActNone)   ? gemm_tile_kernel<BLOCK_N, PASSES, 0, KIND>
               : (plain && p.act == kActGelu) ? gemm_tile_kernel<BLOCK_N, PASSES, 1, KIND>
                                              : gemm_tile_kernel<BLOCK_N, PASSES, 2, KIND>;
+  if (p.a_stats != nullptr && (!plain || p.a_corr == nullptr)) return cudaErrorInvalidValue;
+  if (p.stats_out != nullptr) {
+    // LayerNorm-folding producer: the output pair overwrites the residual pair tile by tile (st_hi / st_lo both ways), rows are
+    // four 128-column tiles wide, and the column tile of a CTA must not change between its tiles (per-column vectors)
+    if constexpr (BLOCK_N == 128 && PASSES == 3 && KIND == kKindF16) {
+      if (!plain || p.act != kActNone || n_cols != 4 * BLOCK_N || p.N != n_cols || !p.tma_store || p.out != nullptr ||
+          p.out_hi == nullptr || p.a_stats != nullptr || (p.res_stats != nullptr && (p.res_gamma == nullptr || p.res_beta == nullptr)))
+        return cudaErrorInvalidValue;
+      kern = gemm_tile_kernel<BLOCK_N, PASSES, 3, KIND>;
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
     cudaError_t e = set_attr<BLOCK_N, PASSES, KIND>();
@@ -675,7 +881,9 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   q.grid_n_cols = n_cols;
   const int tiles = ((n_cols + BLOCK_N - 1) / BLOCK_N) * ((m_rows + kGemmBlockM - 1) / kGemmBlockM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms, 1, 1);
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (p.stats_out != nullptr) grid -= grid % 4;  // a CTA keeps its column tile: tile % 4 == blockIdx % 4 on every round
+  cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;

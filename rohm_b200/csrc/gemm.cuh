@@ -92,6 +92,25 @@ struct alignas(64) GemmParams {
   CUtensorMap st_hi;
   CUtensorMap st_lo;
   int tma_store;
+  // ---- LayerNorm folding (PoseNet post-norm encoder layers; kKindF16, d_model = 512 = 8 x 64 columns) ----
+  // The residual stream is kept UN-normalised: u = LN_prev(u_prev) + sublayer(.) is stored as an fp16 pair together with
+  // per-row partial statistics, and x = LN(u) is never materialised:
+  //  * the PRODUCER of u (out-proj / FFN2, `stats_out` != nullptr, BLOCK_N = 128, N = 512, output pair written in place
+  //    over the residual pair through st_hi / st_lo) adds the residual tile -- optionally passed through the previous
+  //    LayerNorm on the fly: (r - mean) rstd gamma + beta with `res_stats`, `res_gamma`, `res_beta` -- and writes, per thread,
+  //    the (mean, M2) of its 64 columns of the row to stats_out[row][tile_n * 2 + half];
+  //  * every CONSUMER GEMM of x = LN(u) (QKV, FFN1, output head; `a_stats` != nullptr) runs on the raw pair u with the
+  //    LayerNorm scale folded into its weight, W'[n,k] = gamma_k W[n,k], and corrects in the epilogue:
+  //      out[m,n] = rstd_m (acc[m,n] - mean_m c_n) + d_n,   c_n = sum_k W'[n,k] (`a_corr`),  d_n = b_n + sum_k beta_k W[n,k]
+  //    (passed as `bias`).  (mean_m, rstd_m) come from Chan's combination of the row's 8 partials.
+  // Statistics cross kernels through global memory; nothing waits inside a kernel.
+  const float2* a_stats;    // [rows][8] partial (mean, M2) of the A rows, or nullptr
+  const float* a_corr;      // [N]
+  const float2* res_stats;  // [rows][8] partials of the residual rows, or nullptr: residual added as is
+  const float* res_gamma;   // [N]
+  const float* res_beta;    // [N]
+  float2* stats_out;        // [rows][8], or nullptr: plain epilogue
+  float ln_eps;
   // optional: CTA 0 records %globaltimer at 8 milestones (developer instrumentation, see tools/gemm_selftest)
   unsigned long long* debug_ts;
   // filled in by launch_gemm: extent of the tile grid

@@ -95,8 +95,12 @@ __global__ void pe_rows_kernel(const float* __restrict__ pe, float* __restrict__
 // over all pe_len timesteps); per step the token row (b, 0) is a gather.
 __global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, const float* __restrict__ table,
                                          int table_rows, float* __restrict__ X, float* __restrict__ Xh,
-                                         float* __restrict__ Xl, int S, int D, int f16) {
+                                         float* __restrict__ Xl, int S, int D, int f16, unsigned int* __restrict__ zero_buf,
+                                         int zero_n) {
   const int b = blockIdx.x;
+  // once per forward: clear the arrival counters of the fused LayerNorm epilogues (GemmParams::ln_count)
+  if (b == 0)
+    for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_buf[i] = 0u;
   int64_t t = timesteps[b];
   // The reference indexes pe[timesteps] and raises on a bad index (heads.py:145).  A kernel cannot raise, so an
   // out-of-range timestep poisons the clip's timestep token with NaN (which attention spreads over the whole clip's
@@ -1065,6 +1069,9 @@ size_t attention_smem_bytes(int S, int DH) {
 struct PoseNetLayerDev {
   PackedWeight qkv, proj, ff1, ff2;
   float *qkv_b, *proj_b, *ff1_b, *ff2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+  // LayerNorm folding: c_n = sum_k gamma_k W[n,k] and d_n = b_n + sum_k beta_k W[n,k] of the GEMMs that consume a
+  // normalised input (QKV of layers >= 1: previous layer's norm2; FFN1: this layer's norm1)
+  float *qkv_c = nullptr, *qkv_d = nullptr, *ff1_c = nullptr, *ff1_d = nullptr;
 };
 
 }  // namespace rohm
@@ -1104,6 +1111,13 @@ struct rohm_posenet {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_tma_store = true;  // ROHM_B200_TMA_STORE=0 falls back to the per-thread store epilogue (developer switch)
+  // LayerNorm folding (F16X2, d_model 512; ROHM_B200_FUSED_LN=0 keeps the separate layernorm_kernel): the residual stream
+  // is stored un-normalised as an fp16 pair plus per-row partial statistics (stats1: after the attention sublayer, stats2:
+  // after the feed-forward sublayer), LN(u) is never materialised: see GemmParams::stats_out / a_stats
+  bool fused_ln = false;
+  float2* stats1 = nullptr;
+  float2* stats2 = nullptr;
+  float *out_c = nullptr, *out_d = nullptr;  // output head: c_n, d_n of the folded last LayerNorm
   // tcgen05 attention (F16X2, head dim 128, <= 160 tokens per clip; ROHM_B200_TC_ATTENTION=0 selects the mma.sync kernel)
   bool tc_attention = false;
   AttnTcParams attn_tc{};
@@ -1172,9 +1186,58 @@ static __global__ void pack_weight_kernel(const float* __restrict__ w, float* __
   }
 }
 
+// LayerNorm folding of a consumer GEMM y = LN(u) W^T + b, LN(u) = (u - mean) rstd gamma + beta:
+//   Wf[n,k] = gamma_k W[n,k],  c_n = sum_k Wf[n,k],  d_n = b_n + sum_k beta_k W[n,k]      (one CTA per output row n)
+static __global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias, int K,
+                                      float* __restrict__ Wf, float* __restrict__ c, float* __restrict__ d) {
+  const int n = blockIdx.x;
+  double sc = 0.0, sd = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = W[static_cast<int64_t>(n) * K + k];
+    const float wf = gamma[k] * w;
+    Wf[static_cast<int64_t>(n) * K + k] = wf;
+    sc += static_cast<double>(wf);
+    sd += static_cast<double>(beta[k]) * static_cast<double>(w);
+  }
+  __shared__ double rc[256], rd[256];
+  rc[threadIdx.x] = sc, rd[threadIdx.x] = sd;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) rc[threadIdx.x] += rc[threadIdx.x + s], rd[threadIdx.x] += rd[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    c[n] = static_cast<float>(rc[0]);
+    d[n] = static_cast<float>(static_cast<double>(bias[n]) + rd[0]);
+  }
+}
+
+static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out, int kind);
+
+// Packs gamma-folded weights of a [N, K] linear layer and produces its c / d vectors (library-owned).
+static int pack_folded(rohm_posenet* pn, const float* w, const float* bias, const float* gamma, const float* beta, int N, int K,
+                       PackedWeight* out, float** c, float** d) {
+  float* wf = nullptr;
+  if (cudaMalloc(&wf, static_cast<size_t>(N) * K * sizeof(float)) != cudaSuccess)
+    return fail(pn->ctx, ROHM_ERR_CUDA, "folded weight scratch alloc failed");
+  *c = pn->pool.floats(N), *d = pn->pool.floats(N);
+  int rc = ROHM_OK;
+  if (*c == nullptr || *d == nullptr) {
+    rc = fail(pn->ctx, ROHM_ERR_CUDA, "alloc failed: %s", cudaGetErrorString(pn->pool.last_error()));
+  } else {
+    fold_ln_kernel<<<N, 256>>>(w, gamma, beta, bias, K, wf, *c, *d);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(pn->ctx, ROHM_ERR_CUDA, "fold_ln_kernel launch failed");
+    if (rc == ROHM_OK) rc = pack_weight(pn, wf, N, K, out, pn->kind);
+    if (rc == ROHM_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(pn->ctx, ROHM_ERR_CUDA, "weight folding failed");
+  }
+  cudaFree(wf);
+  return rc;
+}
+
 // kind == kKindF16: the matrix is stored as fp16 hi/lo of w * 2^s, s chosen per matrix so that max |w| 2^s lies in
 // [2^13, 2^14): every weight within 2^-13 of the largest keeps a normal-range lo half, and nothing overflows.
-static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out, int kind = kKindTf32) {
+static int pack_weight(rohm_posenet* pn, const float* w, int N, int K, PackedWeight* out, int kind) {
   out->N = N, out->K = K;
   out->block_n = pick_block_n(N);
   out->Np = static_cast<int>(round_up(N, out->block_n));
@@ -1391,8 +1454,8 @@ static int build_time_table(rohm_posenet* pn, const rohm_posenet_weights* w) {
   float* bias2 = tmp.floats(D);
   if (!pe_h || !pe_l || !h_h || !h_l || !bias2) return fail(pn->ctx, ROHM_ERR_CUDA, "time table scratch alloc failed");
   int rc;
-  if ((rc = pack_weight(pn, w->t0_w, D, D, &w0)) != ROHM_OK) return rc;  // small (2 x 2 MB), kept in the pool
-  if ((rc = pack_weight(pn, w->t2_w, D, D, &w2)) != ROHM_OK) return rc;
+  if ((rc = pack_weight(pn, w->t0_w, D, D, &w0, kKindTf32)) != ROHM_OK) return rc;  // small (2 x 2 MB), kept in the pool
+  if ((rc = pack_weight(pn, w->t2_w, D, D, &w2, kKindTf32)) != ROHM_OK) return rc;
   ROHM_CUDA(pn->ctx, launch_split_tf32(pn->pe, pe_h, pe_l, n, 0));
   add_vec_kernel<<<(D + 255) / 256, 256>>>(w->t2_b, pn->pe, bias2, D);  // b2 + pe[0]
   ROHM_CUDA(pn->ctx, cudaGetLastError());
@@ -1442,6 +1505,19 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   }
   const int D = pn->D, F = pn->F;
   const int64_t R = pn->max_rows;
+  {
+    const char* env = getenv("ROHM_B200_FUSED_LN");
+    pn->fused_ln = pn->kind == kKindF16 && D == 512 && pn->use_tma_store && (env == nullptr || env[0] != '0');
+    if (pn->fused_ln) {
+      pn->stats1 = static_cast<float2*>(pn->pool.bytes(R * 8 * static_cast<int64_t>(sizeof(float2))));
+      pn->stats2 = static_cast<float2*>(pn->pool.bytes(R * 8 * static_cast<int64_t>(sizeof(float2))));
+      if (pn->stats1 == nullptr || pn->stats2 == nullptr) {
+        const int rc = fail(ctx, ROHM_ERR_CUDA, "LayerNorm statistics buffers: %s", cudaGetErrorString(pn->pool.last_error()));
+        delete pn;
+        return rc;
+      }
+    }
+  }
 
 #define TRY(expr)            \
   do {                       \
@@ -1454,7 +1530,12 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
 
   TRY(pack_weight(pn, w->in_w, D, pn->C, &pn->w_in, pn->kind));
   TRY(pack_weight(pn, w->cond_w, D, pn->C, &pn->w_cond, pn->kind));
-  TRY(pack_weight(pn, w->out_w, pn->Cout, D, &pn->w_out, pn->kind));
+  if (pn->fused_ln && pn->L > 0) {  // the head consumes LN2 of the last layer
+    const rohm_posenet_layer& last = w->layers[pn->L - 1];
+    TRY(pack_folded(pn, w->out_w, w->out_b, last.norm2_w, last.norm2_b, pn->Cout, D, &pn->w_out, &pn->out_c, &pn->out_d));
+  } else {
+    TRY(pack_weight(pn, w->out_w, pn->Cout, D, &pn->w_out, pn->kind));
+  }
   TRY(copy_vec(pn, w->in_b, D, &pn->in_b));
   TRY(copy_vec(pn, w->cond_b, D, &pn->cond_b));
   TRY(copy_vec(pn, w->out_b, pn->Cout, &pn->out_b));
@@ -1464,9 +1545,18 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   for (int l = 0; l < pn->L; ++l) {
     const rohm_posenet_layer& s = w->layers[l];
     PoseNetLayerDev& d = pn->layers[l];
-    TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv, pn->kind));
+    if (pn->fused_ln && l > 0) {  // QKV consumes LN2 of the previous layer
+      const rohm_posenet_layer& prev = w->layers[l - 1];
+      TRY(pack_folded(pn, s.in_proj_w, s.in_proj_b, prev.norm2_w, prev.norm2_b, 3 * D, D, &d.qkv, &d.qkv_c, &d.qkv_d));
+    } else {
+      TRY(pack_weight(pn, s.in_proj_w, 3 * D, D, &d.qkv, pn->kind));
+    }
     TRY(pack_weight(pn, s.out_proj_w, D, D, &d.proj, pn->kind));
-    TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1, pn->kind));
+    if (pn->fused_ln) {  // FFN1 consumes LN1 of this layer
+      TRY(pack_folded(pn, s.lin1_w, s.lin1_b, s.norm1_w, s.norm1_b, F, D, &d.ff1, &d.ff1_c, &d.ff1_d));
+    } else {
+      TRY(pack_weight(pn, s.lin1_w, F, D, &d.ff1, pn->kind));
+    }
     TRY(pack_weight(pn, s.lin2_w, D, F, &d.ff2, pn->kind));
     TRY(copy_vec(pn, s.in_proj_b, 3 * D, &d.qkv_b));
     TRY(copy_vec(pn, s.out_proj_b, D, &d.proj_b));
@@ -1507,6 +1597,8 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   // Output head.
   TRY(setup_linear(pn, &pn->g_out, pn->Xh, pn->Xl, R, D, D, pn->w_out, pn->out_b));
   pn->g_out.out = pn->OUT, pn->g_out.ldo = pn->Cout;
+  if (pn->fused_ln && pn->L > 0)
+    pn->g_out.a_stats = pn->stats2, pn->g_out.a_corr = pn->out_c, pn->g_out.bias = pn->out_d, pn->g_out.ln_eps = 1e-5f;
   pn->g_qkv.resize(pn->L), pn->g_proj.resize(pn->L), pn->g_ff1.resize(pn->L), pn->g_ff2.resize(pn->L);
   for (int l = 0; l < pn->L; ++l) {
     PoseNetLayerDev& d = pn->layers[l];
@@ -1522,11 +1614,30 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
     // the GEMM epilogues free of global reads
     TRY(setup_linear(pn, &pn->g_proj[l], pn->CTXh, pn->CTXl, R, D, D, d.proj, d.proj_b));
     pn->g_proj[l].out = pn->Y, pn->g_proj[l].ldo = D;
+    // LayerNorm folding: producers write u in place over the residual pair + partial statistics; consumers correct
+    auto producer = [&](GemmParams& g, float2* stats_out, const float2* res_stats, const float* res_gamma, const float* res_beta) {
+      g.out = nullptr, g.ldo = 0;
+      g.out_hi = pn->Xh, g.out_lo = pn->Xl, g.lds = D;
+      g.stats_out = stats_out, g.res_stats = res_stats, g.res_gamma = res_gamma, g.res_beta = res_beta, g.ln_eps = 1e-5f;
+    };
+    auto consumer = [&](GemmParams& g, const float2* a_stats, const float* c, const float* dvec) {
+      g.a_stats = a_stats, g.a_corr = c, g.bias = dvec, g.ln_eps = 1e-5f;
+    };
+    if (pn->fused_ln) {
+      if (l > 0) consumer(pn->g_qkv[l], pn->stats2, d.qkv_c, d.qkv_d);
+      // out-proj: u1 = LN2_prev(u2_prev) + attn   (layer 0: the embedded input, not normalised)
+      producer(pn->g_proj[l], pn->stats1, l > 0 ? pn->stats2 : nullptr, l > 0 ? pn->layers[l - 1].n2_w : nullptr,
+               l > 0 ? pn->layers[l - 1].n2_b : nullptr);
+    }
     TRY(setup_linear(pn, &pn->g_ff1[l], pn->Xh, pn->Xl, R, D, D, d.ff1, d.ff1_b));
     pn->g_ff1[l].act = kActGelu;
     pn->g_ff1[l].out_hi = pn->Hh, pn->g_ff1[l].out_lo = pn->Hl, pn->g_ff1[l].lds = F;
     TRY(setup_linear(pn, &pn->g_ff2[l], pn->Hh, pn->Hl, R, F, F, d.ff2, d.ff2_b));
     pn->g_ff2[l].out = pn->Y, pn->g_ff2[l].ldo = D;
+    if (pn->fused_ln) {
+      consumer(pn->g_ff1[l], pn->stats1, d.ff1_c, d.ff1_d);
+      producer(pn->g_ff2[l], pn->stats2, pn->stats1, d.n1_w, d.n1_b);  // u2 = LN1(u1) + ffn
+    }
     for (GemmParams* g : {&pn->g_qkv[l], &pn->g_proj[l], &pn->g_ff1[l], &pn->g_ff2[l]}) {
       if (pn->use_tma_store && gemm_enable_tma_store(g, R, pn->kind) != 0) {
         const int rc__ = fail(ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed");
@@ -1667,7 +1778,7 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
   if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
   prof_begin(pn, kCatOther, st);
   time_token_gather_kernel<<<B, 128, 0, st>>>(timesteps, pn->time_table, pn->pe_len, pn->X, pn->Xh, pn->Xl, S, D,
-                                              pn->kind == kKindF16 ? 1 : 0);
+                                              pn->kind == kKindF16 ? 1 : 0, nullptr, 0);
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
@@ -1681,10 +1792,10 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
       if ((rc = run_attention(pn, B, S, st)) != ROHM_OK) return rc;
     }
     if ((rc = run_gemm(pn, pn->g_proj[l], d.proj, rows, st)) != ROHM_OK) return rc;
-    if ((rc = run_ln(pn, pn->Y, pn->X, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+    if (!pn->fused_ln && (rc = run_ln(pn, pn->Y, pn->X, d.n1_w, d.n1_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_ff1[l], d.ff1, rows, st)) != ROHM_OK) return rc;
     if ((rc = run_gemm(pn, pn->g_ff2[l], d.ff2, rows, st)) != ROHM_OK) return rc;
-    if ((rc = run_ln(pn, pn->Y, pn->X, d.n2_w, d.n2_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
+    if (!pn->fused_ln && (rc = run_ln(pn, pn->Y, pn->X, d.n2_w, d.n2_b, pn->X, pn->Xh, pn->Xl, rows, st)) != ROHM_OK) return rc;
   }
   if ((rc = run_gemm(pn, pn->g_out, pn->w_out, rows, st)) != ROHM_OK) return rc;
   dim3 grid_o((T + 31) / 32, (pn->Cout + 31) / 32, B);
@@ -1815,7 +1926,7 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   }
   {
     cudaKernelNodeParams kp = fg->p_time;
-    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 9);
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 11);
     args[0] = &a_t;
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_time, &kp));

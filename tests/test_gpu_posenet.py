@@ -300,7 +300,11 @@ def test_out_of_range_timestep_poisons_the_output(posenet, cuda_device):
     cond = synthetic.posenet_batch(B, T, 9)['cond'].to(cuda_device)
     x = torch.randn(B, 294, 1, T, device=cuda_device)
     y = m({'x_t': x, 'cond': cond}, torch.tensor([5, 5000], device=cuda_device))
-    assert bool(torch.isfinite(y[0]).all()) and bool(torch.isnan(y[1, 22:]).all())
+    # (clips that share an attention key tile with the poisoned one may turn NaN too -- 0 x NaN in the masked key columns --
+    # which is still "the call failed", as the reference's IndexError is for the whole batch)
+    assert bool(torch.isnan(y[1, 22:]).all())
+    ok = m({'x_t': x, 'cond': cond}, torch.tensor([5, 4999], device=cuda_device))
+    assert bool(torch.isfinite(ok).all())
     with pytest.raises(Exception):
         m({'x_t': x, 'cond': cond}, torch.tensor([5.0, 6.0], device=cuda_device))
 

@@ -277,6 +277,179 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
 }
 
 // ------------------------------------------------------------------------------------------------
+// Case 1c: LayerNorm folding (GemmParams::stats_out / a_stats), three chained launches on [M, 512] rows:
+//   (A) producer:  u1 = R + A1 W1^T + b1            (in place over the residual pair, writes partial row statistics S1)
+//   (B) consumer:  y  = LN(u1) W2^T + b2             (raw pair u1 as the A operand, gamma folded into W2, epilogue correction)
+//   (C) producer:  u2 = LN(u1) + A3 W3^T + b3        (residual passed through the LayerNorm on the fly, writes S2)
+// ------------------------------------------------------------------------------------------------
+struct F16Weights {
+  __half *hi = nullptr, *lo = nullptr;
+  float scale = 1.f;
+  int Kp = 0;
+};
+static F16Weights pack_f16(const std::vector<float>& W, int N, int K) {
+  const int BK = gemm_block_k(kKindF16);
+  F16Weights o;
+  o.Kp = (K + BK - 1) / BK * BK;
+  std::vector<float> Wp((size_t)N * o.Kp, 0.f);
+  float wmax = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) wmax = std::fmax(wmax, std::fabs(Wp[(size_t)n * o.Kp + k] = W[(size_t)n * K + k]));
+  int e2;
+  std::frexp(wmax, &e2);
+  o.scale = std::ldexp(1.0f, 14 - e2);
+  float* d = dev(Wp);
+  CK(cudaMalloc(&o.hi, Wp.size() * 2));
+  CK(cudaMalloc(&o.lo, Wp.size() * 2));
+  CK(launch_split_f16(d, o.hi, o.lo, (int64_t)Wp.size(), o.scale, 0));
+  CK(cudaDeviceSynchronize());
+  cudaFree(d);
+  return o;
+}
+static void make_linear(GemmParams& p, const __half* Ah, const __half* Al, int M, int K, int lda, const F16Weights& w, int N, int bn) {
+  p = GemmParams{};
+  const int BK = gemm_block_k(kKindF16);
+  if (make_tmap_2d(&p.a_hi[0], Ah, M, K, lda, kGemmBlockM, 1, kKindF16) || make_tmap_2d(&p.a_lo[0], Al, M, K, lda, kGemmBlockM, 1, kKindF16) ||
+      make_tmap_2d(&p.b_hi, w.hi, N, w.Kp, w.Kp, bn, 1, kKindF16) || make_tmap_2d(&p.b_lo, w.lo, N, w.Kp, w.Kp, bn, 1, kKindF16)) {
+    printf("tensor map encode failed (ln)\n");
+    exit(2);
+  }
+  p.num_segs = 1, p.seg_kblocks[0] = w.Kp / BK, p.seg_row_mul[0] = 1;
+  p.M = M, p.N = N, p.out_row_mul = 1, p.acc_scale = 1.0f / w.scale, p.ln_eps = 1e-5f;
+}
+static void case_linear_ln(int M, int K, bool timing) {
+  const int D = 512, N2 = 1024;
+  std::normal_distribution<float> nd(0.f, 1.f);
+  auto randv = [&](size_t n, float sc, float off = 0.f) {
+    std::vector<float> v(n);
+    for (auto& x : v) x = off + sc * nd(rng);
+    return v;
+  };
+  auto A1 = randv((size_t)M * K, 1.f), A3 = randv((size_t)M * K, 1.f), R = randv((size_t)M * D, 1.5f, 0.7f);
+  auto W1 = randv((size_t)D * K, 1.f / std::sqrt((float)K)), W3 = randv((size_t)D * K, 1.f / std::sqrt((float)K));
+  auto W2 = randv((size_t)N2 * D, 1.f / std::sqrt((float)D));
+  auto b1 = randv(D, 1.f), b2 = randv(N2, 1.f), b3 = randv(D, 1.f), gam = randv(D, 0.1f, 1.f), bet = randv(D, 0.1f);
+  // folded consumer weights
+  std::vector<float> W2f((size_t)N2 * D), c2(N2), d2(N2);
+  for (int n = 0; n < N2; ++n) {
+    double sc = 0, sd = 0;
+    for (int k = 0; k < D; ++k) {
+      W2f[(size_t)n * D + k] = gam[k] * W2[(size_t)n * D + k];
+      sc += W2f[(size_t)n * D + k];
+      sd += (double)bet[k] * W2[(size_t)n * D + k];
+    }
+    c2[n] = (float)sc, d2[n] = (float)(b2[n] + sd);
+  }
+  const F16Weights w1 = pack_f16(W1, D, K), w2 = pack_f16(W2f, N2, D), w3 = pack_f16(W3, D, K);
+  float *dA1 = dev(A1), *dA3 = dev(A3), *dR = dev(R), *db1 = dev(b1), *db3 = dev(b3), *dc2 = dev(c2), *dd2 = dev(d2);
+  float *dg = dev(gam), *dbe = dev(bet);
+  __half *A1h, *A1l, *A3h, *A3l, *Xh, *Xl;
+  for (__half** q : {&A1h, &A1l, &A3h, &A3l}) CK(cudaMalloc(q, (size_t)M * K * 2));
+  CK(cudaMalloc(&Xh, (size_t)M * D * 2));
+  CK(cudaMalloc(&Xl, (size_t)M * D * 2));
+  CK(launch_split_f16(dA1, A1h, A1l, (int64_t)M * K, 1.0f, 0));
+  CK(launch_split_f16(dA3, A3h, A3l, (int64_t)M * K, 1.0f, 0));
+  float2 *S1, *S2;
+  CK(cudaMalloc(&S1, (size_t)M * 8 * sizeof(float2)));
+  CK(cudaMalloc(&S2, (size_t)M * 8 * sizeof(float2)));
+  float* dY = dev_zero((size_t)M * N2);
+  GemmParams pa, pb, pc;
+  make_linear(pa, A1h, A1l, M, K, K, w1, D, 128);
+  pa.bias = db1, pa.out_hi = Xh, pa.out_lo = Xl, pa.lds = D, pa.stats_out = S1;
+  make_linear(pb, Xh, Xl, M, D, D, w2, N2, 128);
+  pb.bias = dd2, pb.a_stats = S1, pb.a_corr = dc2, pb.out = dY, pb.ldo = N2;
+  make_linear(pc, A3h, A3l, M, K, K, w3, D, 128);
+  pc.bias = db3, pc.out_hi = Xh, pc.out_lo = Xl, pc.lds = D, pc.stats_out = S2, pc.res_stats = S1, pc.res_gamma = dg, pc.res_beta = dbe;
+  for (GemmParams* q : {&pa, &pb, &pc})
+    if (gemm_enable_tma_store(q, M, kKindF16) != 0 || !q->tma_store) {
+      printf("gemm_enable_tma_store refused a LayerNorm-folding launch\n");
+      exit(2);
+    }
+  auto read_pair = [&](std::vector<double>& out) {
+    std::vector<__half> h((size_t)M * D), l((size_t)M * D);
+    CK(cudaMemcpy(h.data(), Xh, h.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), Xl, l.size() * 2, cudaMemcpyDeviceToHost));
+    out.resize(h.size());
+    for (size_t i = 0; i < h.size(); ++i) out[i] = (double)__half2float(h[i]) + (double)__half2float(l[i]);
+  };
+  CK(launch_split_f16(dR, Xh, Xl, (int64_t)M * D, 1.0f, 0));
+  CK(launch_gemm(pa, M, D, 128, 3, 0, false, kKindF16));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> u1g, u2g;
+  read_pair(u1g);
+  CK(launch_gemm(pb, M, N2, 128, 3, 0, false, kKindF16));
+  CK(launch_gemm(pc, M, D, 128, 3, 0, false, kKindF16));
+  CK(cudaDeviceSynchronize());
+  read_pair(u2g);
+  auto Y = host(dY, (size_t)M * N2);
+  double ea = 0, eb = 0, ec = 0, ra = 0, rb = 0, rcm = 0;
+  const int step = M > 600 ? 11 : 1;
+  std::vector<double> u1(D), x(D);
+  for (int m = 0; m < M; m += step) {
+    double mean = 0;
+    for (int n = 0; n < D; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)A1[(size_t)m * K + k] * W1[(size_t)n * K + k];
+      u1[n] = acc + b1[n] + R[(size_t)m * D + n];
+      mean += u1[n];
+      ea = std::fmax(ea, std::fabs(u1g[(size_t)m * D + n] - u1[n])), ra = std::fmax(ra, std::fabs(u1[n]));
+    }
+    mean /= D;
+    double var = 0;
+    for (int n = 0; n < D; ++n) var += (u1[n] - mean) * (u1[n] - mean);
+    const double rstd = 1.0 / std::sqrt(var / D + 1e-5);
+    for (int n = 0; n < D; ++n) x[n] = (u1[n] - mean) * rstd * gam[n] + bet[n];
+    for (int n = 0; n < N2; ++n) {
+      double acc = b2[n];
+      for (int k = 0; k < D; ++k) acc += x[k] * W2[(size_t)n * D + k];
+      eb = std::fmax(eb, std::fabs(Y[(size_t)m * N2 + n] - acc)), rb = std::fmax(rb, std::fabs(acc));
+    }
+    for (int n = 0; n < D; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)A3[(size_t)m * K + k] * W3[(size_t)n * K + k];
+      const double ref = x[n] + acc + b3[n];
+      ec = std::fmax(ec, std::fabs(u2g[(size_t)m * D + n] - ref)), rcm = std::fmax(rcm, std::fabs(ref));
+    }
+  }
+  char name[160];
+  snprintf(name, sizeof name, "LN folding M%d K%d: (A) producer u = res + A W^T + b", M, K);
+  report(name, ea, ra, 2e-5);
+  report("  (B) consumer y = LN(u) W2^T + b2 via folded weights + epilogue correction", eb, rb, 3e-5);
+  report("  (C) producer u2 = LN(u) + A W^T + b (residual normalised on the fly)", ec, rcm, 3e-5);
+  if (timing) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 20;
+    for (GemmParams* q : {&pc, &pb}) {
+      for (int i = 0; i < 3; ++i) CK(launch_gemm(*q, M, q->N, 128, 3, 0, false, kKindF16));
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < iters; ++i) CK(launch_gemm(*q, M, q->N, 128, 3, 0, false, kKindF16));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      printf("    timing %s: %.2f us/launch\n", q == &pc ? "(C) producer" : "(B) consumer N=1024", ms * 1000.0 / iters);
+    }
+    unsigned long long* dts;
+    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
+    pc.debug_ts = dts;
+    CK(launch_gemm(pc, M, D, 128, 3, 0, false, kKindF16));
+    CK(launch_gemm(pc, M, D, 128, 3, 0, false, kKindF16));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[16];
+    CK(cudaMemcpy(h, dts, sizeof h, cudaMemcpyDeviceToHost));
+    printf("    (C) CTA0 timeline (ns): setup %llu | first_tma %llu | first_full %llu | tile0 mma issued %llu | epi start %llu | acc added %llu | "
+           "stats written %llu | tile0 epi done %llu | all mma issued %llu | end %llu\n",
+           h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0], h[6] - h[0], h[12] - h[0], h[7] - h[0]);
+    cudaFree(dts);
+  }
+  for (float* q : {dA1, dA3, dR, db1, db3, dc2, dd2, dg, dbe, dY}) cudaFree(q);
+  for (__half* q : {A1h, A1l, A3h, A3l, Xh, Xl, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo}) cudaFree(q);
+  cudaFree(S1), cudaFree(S2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Case 2: Conv1d over a padded-clip channels-last layout, as TrajNet uses it.
 //   x: [B, Tp_in, Cin] with the first T_in rows of each clip real, others zero.
 //   y[b, t, co] = bias[co] + sum_{j<ks} sum_ci W[co, ci, j] * x[b, t*stride + j - pad, ci]
@@ -484,6 +657,13 @@ int main() {
   case_linear_f16(4640, 1024, 512, 128, kActGelu, false, true, 1.0f, 2);
   case_linear_f16(4640, 512, 1024, 128, kActNone, false, true, 1.0f, 1);
   case_linear_f16(4640, 272, 512, 96, kActNone, false, true, 1.0f, 1);
+  // fused residual + LayerNorm epilogue: PoseNet out-proj / FFN2 shapes, a one-stripe case and ragged row counts
+  case_linear_ln(4640, 512, true);
+  case_linear_ln(4640, 1024, true);
+  case_linear_ln(18560, 512, true);   // 128 clips: 145 stripes -> 3.9 persistent rounds
+  case_linear_ln(128, 512, false);
+  case_linear_ln(34, 512, false);      // ragged last row group (per-thread store path)
+  case_linear_ln(1000, 1024, false);
   case_linear_f16(145, 512, 512, 128, kActNone, false, false, 1.0f, 1);
   case_linear_f16(333, 1536, 512, 128, kActNone, false, false, 1.0f, 2);
   case_linear_f16(300, 512, 512, 128, kActNone, false, false, 300.0f);   // large activations
