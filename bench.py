@@ -564,6 +564,14 @@ def posenet_roofline(w, peaks, ms_per_step, model=None, B=None, T=None):
             cat_n[k] = n[k]
     out = torch.empty_like(x)
     graph_ms = _event_ms(lambda: engine.forward(x, ts, out), 50)  # the forward as it runs in the loop (CUDA graph, warm L2)
+    # the whole sampler step as it runs in the loop (forward + in-kernel-noise update, one graph launch), device and host side
+    coef_row = torch.zeros(8, device=w.dev)
+    step_graph_ms = _event_ms(lambda: engine.sample_step(x, ts, coef_row), 50)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        engine.sample_step(x, ts, coef_row)
+    host_us = (time.perf_counter() - t0) / 50 * 1e6  # enqueue cost (the GPU runs behind): must stay below the device time
+    torch.cuda.synchronize()
     flops = gemm_flops_per_forward(B, T + 1)
     gemm_s = cat_ms["gemm"] / 1000.0
     achieved = flops / gemm_s / 1e12 if gemm_s > 0 else None
@@ -588,7 +596,7 @@ def posenet_roofline(w, peaks, ms_per_step, model=None, B=None, T=None):
         "tensor_pipe_frac_note": "issued tensor work (3 products per algorithmic flop) / peak of that operand type",
         "share_of_forward": {k: cat_ms[k] / max(sum(cat_ms.values()), 1e-9) for k in cat_ms},
         "forward_ms_by_kernel_class": cat_ms, "launches_by_kernel_class": cat_n,
-        "forward_graph_ms": graph_ms,
+        "forward_graph_ms": graph_ms, "step_graph_ms": step_graph_ms, "host_enqueue_us_per_step": host_us,
         "achieved_from_graph_share": achieved_graph, "frac_from_graph_share": achieved_graph / peaks["bf16_tflops"],
         # GEMMs + attention (QK^T and PV: 4 S^2 D per clip and layer) over the whole forward graph
         "whole_forward_tflops": (flops + B * 8 * 4.0 * (T + 1) * (T + 1) * 512) / (graph_ms / 1000.0) / 1e12,

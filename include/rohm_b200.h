@@ -70,6 +70,16 @@ ROHM_API int rohm_ddpm_step(rohm_ctx* ctx, const float* x0, const float* x_t, co
                             const float* grad1, int n_grads, float* out, int64_t n_clips, int64_t clip_elems,
                             const float* coef, int64_t coef_clip_stride, void* stream);
 
+/* rohm_ddpm_step with the noise = th.randn_like(x) (:426, :458) drawn INSIDE the kernel: Philox4_32_10(seed, offset) consumed
+ * exactly as torch's CUDA normal_ kernel consumes it for a tensor of n_clips*clip_elems fp32 elements on this device, so
+ * with (seed, offset) = the state of torch's CUDA generator the result is bit-identical to
+ * rohm_ddpm_step(..., noise = torch.randn_like(x), ...).  *offset_increment (host, optional) receives the amount the caller
+ * must advance the generator's offset by afterwards (what torch itself would have added). */
+ROHM_API int rohm_ddpm_step_philox(rohm_ctx* ctx, const float* x0, const float* x_t, const float* grad0, const float* grad1,
+                                   int n_grads, float* out, int64_t n_clips, int64_t clip_elems, const float* coef,
+                                   int64_t coef_clip_stride, uint64_t seed, uint64_t offset, uint64_t* offset_increment,
+                                   void* stream);
+
 /* q_sample :192-210:  out = sqrt_ac*x_start + sqrt_1m_ac*noise. */
 ROHM_API int rohm_q_sample(rohm_ctx* ctx, const float* x_start, const float* noise, float* out, int64_t n, float sqrt_ac,
                   float sqrt_one_minus_ac, void* stream);
@@ -137,6 +147,14 @@ ROHM_API int rohm_posenet_set_cond(rohm_posenet* pn, const float* cond, int B, i
  * out: [B, in_feats, 1, T] with channels [0, traj_feats) copied from the cond given to set_cond. */
 ROHM_API int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
                          void* stream);
+
+/* One whole ancestral step of the PoseNet sampler (p_mean_variance :236-280 + p_sample :388-434) as ONE graph launch:
+ * x0_out = PoseNet(x_t, timesteps) followed by x_next = c1 x0 + c2 x_t + sigma N(0, I) with the noise drawn in the update
+ * kernel exactly as torch.randn_like(x_t) would draw it from (seed, offset) (see rohm_ddpm_step_philox).  coef_row: device
+ * row {c1, c2, sigma, ...} of this step (shared by all clips).  *offset_increment: what to advance the generator by. */
+ROHM_API int rohm_posenet_sample_step(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* x0_out,
+                                      float* x_next, const float* coef_row, uint64_t seed, uint64_t offset,
+                                      uint64_t* offset_increment, int B, int T, void* stream);
 
 /* Same as rohm_posenet_forward but with CUDA events recorded on `stream` around every kernel launch; synchronises the
  * stream and returns, per category {0: tensor-core GEMM, 1: attention, 2: LayerNorm, 3: pack/unpack/time-token}, the

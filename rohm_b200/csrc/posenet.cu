@@ -1102,10 +1102,11 @@ struct rohm_posenet {
   // memory (pack: x_t, time-token gather: timesteps, unpack: out) get their pointers patched before every replay.
   struct FwdGraph {
     int B = 0, T = 0;
+    bool with_step = false;  // forward + Philox-fused ancestral update (rohm_posenet_sample_step)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t n_pack = nullptr, n_time = nullptr, n_unpack = nullptr;
-    cudaKernelNodeParams p_pack{}, p_time{}, p_unpack{};
+    cudaGraphNode_t n_pack = nullptr, n_time = nullptr, n_unpack = nullptr, n_step = nullptr;
+    cudaKernelNodeParams p_pack{}, p_time{}, p_unpack{}, p_step{};
   };
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
@@ -1839,8 +1840,16 @@ extern "C" int rohm_posenet_profile(rohm_posenet* pn, const float* x_t, const in
   return ROHM_OK;
 }
 
+struct StepArgs {  // the ancestral update appended to the forward (rohm_posenet_sample_step)
+  float* x_next;
+  const float* coef_row;
+  unsigned long long seed, offset;
+  int64_t G;
+  int iters;
+};
+
 static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
-                               cudaStream_t st, rohm_posenet::FwdGraph* fg) {
+                               cudaStream_t st, rohm_posenet::FwdGraph* fg, const StepArgs* step = nullptr) {
   rohm_ctx* ctx = pn->ctx;
   rohm::DeviceGuard device_guard__(ctx);
   // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
@@ -1851,6 +1860,13 @@ static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t
   cudaStream_t cs = pn->capture_stream;
   ROHM_CUDA(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   int rc = forward_launches(pn, x_t, timesteps, out, B, T, cs);
+  if (rc == ROHM_OK && step != nullptr) {
+    const int64_t clip_elems = static_cast<int64_t>(pn->C) * T;
+    if (launch_ddpm_step_philox(out, x_t, step->x_next, clip_elems * B, clip_elems, step->coef_row, step->seed, step->offset,
+                                step->G, step->iters, cs) != cudaSuccess)
+      rc = fail(ctx, ROHM_ERR_CUDA, "ddpm step launch failed during capture");
+    pn->launches++;
+  }
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(cs, &graph);
   if (rc != ROHM_OK) {
@@ -1862,7 +1878,7 @@ static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t
   ROHM_CUDA(ctx, cudaGraphGetNodes(graph, nullptr, &n));
   std::vector<cudaGraphNode_t> nodes(n);
   ROHM_CUDA(ctx, cudaGraphGetNodes(graph, nodes.data(), &n));
-  fg->B = B, fg->T = T, fg->graph = graph;
+  fg->B = B, fg->T = T, fg->graph = graph, fg->with_step = step != nullptr;
   for (cudaGraphNode_t node : nodes) {
     cudaGraphNodeType ty;
     ROHM_CUDA(ctx, cudaGraphNodeGetType(node, &ty));
@@ -1872,8 +1888,9 @@ static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t
     if (kp.func == reinterpret_cast<void*>(pack_tokens_kernel)) fg->n_pack = node, fg->p_pack = kp;
     else if (kp.func == reinterpret_cast<void*>(time_token_gather_kernel)) fg->n_time = node, fg->p_time = kp;
     else if (kp.func == reinterpret_cast<void*>(unpack_tokens_kernel)) fg->n_unpack = node, fg->p_unpack = kp;
+    else if (kp.func == const_cast<void*>(ddpm_step_philox_kernel_address())) fg->n_step = node, fg->p_step = kp;
   }
-  if (!fg->n_pack || !fg->n_time || !fg->n_unpack) {
+  if (!fg->n_pack || !fg->n_time || !fg->n_unpack || (step != nullptr && !fg->n_step)) {
     cudaGraphDestroy(graph);
     fg->graph = nullptr;
     return fail(ctx, ROHM_ERR_CUDA, "forward graph: could not locate the boundary kernel nodes");
@@ -1882,8 +1899,8 @@ static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t
   return ROHM_OK;
 }
 
-extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
-                                    int T, void* stream) {
+static int forward_or_step(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B, int T,
+                           void* stream, const StepArgs* step) {
   if (pn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = pn->ctx;
   rohm::DeviceGuard device_guard__(ctx);
@@ -1895,15 +1912,23 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   ROHM_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
-  if (!pn->use_graph || pn->profiling || cap != cudaStreamCaptureStatusNone)
-    return forward_launches(pn, x_t, timesteps, out, B, T, st);
+  if (!pn->use_graph || pn->profiling || cap != cudaStreamCaptureStatusNone) {
+    int rc = forward_launches(pn, x_t, timesteps, out, B, T, st);
+    if (rc == ROHM_OK && step != nullptr) {
+      const int64_t clip_elems = static_cast<int64_t>(pn->C) * T;
+      ROHM_CUDA(ctx, launch_ddpm_step_philox(out, x_t, step->x_next, clip_elems * B, clip_elems, step->coef_row, step->seed,
+                                             step->offset, step->G, step->iters, st));
+      pn->launches++;
+    }
+    return rc;
+  }
 
   rohm_posenet::FwdGraph* fg = nullptr;
   for (auto& g : pn->graphs)
-    if (g.B == B && g.T == T) fg = &g;
+    if (g.B == B && g.T == T && g.with_step == (step != nullptr)) fg = &g;
   if (fg == nullptr) {
     rohm_posenet::FwdGraph ng;
-    int rc = build_forward_graph(pn, x_t, timesteps, out, B, T, st, &ng);
+    int rc = build_forward_graph(pn, x_t, timesteps, out, B, T, st, &ng, step);
     if (rc != ROHM_OK) return rc;
     if (pn->graphs.size() >= 8) {  // bounded cache
       if (pn->graphs.front().exec) cudaGraphExecDestroy(pn->graphs.front().exec);
@@ -1938,8 +1963,38 @@ extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const in
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_unpack, &kp));
   }
+  if (step != nullptr) {  // x0, x_t, out, coef row, Philox seed / offset of this step
+    cudaKernelNodeParams kp = fg->p_step;
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 14);
+    const void* a_x0 = out;
+    void* a_next = step->x_next;
+    const void* a_coef = step->coef_row;
+    unsigned long long a_seed = step->seed, a_off = step->offset;
+    args[0] = &a_x0, args[1] = &a_x, args[5] = &a_next, args[8] = &a_coef, args[10] = &a_seed, args[11] = &a_off;
+    kp.kernelParams = args.data();
+    ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_step, &kp));
+  }
   ROHM_CUDA(ctx, cudaGraphLaunch(fg->exec, st));
   return ROHM_OK;
+}
+
+extern "C" int rohm_posenet_forward(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* out, int B,
+                                    int T, void* stream) {
+  return forward_or_step(pn, x_t, timesteps, out, B, T, stream, nullptr);
+}
+
+extern "C" int rohm_posenet_sample_step(rohm_posenet* pn, const float* x_t, const int64_t* timesteps, float* x0_out,
+                                        float* x_next, const float* coef_row, uint64_t seed, uint64_t offset,
+                                        uint64_t* offset_increment, int B, int T, void* stream) {
+  if (pn == nullptr) return ROHM_ERR_INVALID;
+  if (x_next == nullptr || coef_row == nullptr)
+    return fail(pn->ctx, ROHM_ERR_INVALID, "rohm_posenet_sample_step: null pointer");
+  StepArgs sa{x_next, coef_row, seed, offset, 0, 0};
+  unsigned long long inc = 0;
+  int rc = ddpm_step_philox_policy(pn->ctx, static_cast<int64_t>(pn->C) * T * B, &sa.G, &sa.iters, &inc);
+  if (rc != ROHM_OK) return rc;
+  if (offset_increment != nullptr) *offset_increment = inc;
+  return forward_or_step(pn, x_t, timesteps, x0_out, B, T, stream, &sa);
 }
 
 extern "C" int rohm_posenet_set_option(rohm_posenet* pn, int option, int value) {

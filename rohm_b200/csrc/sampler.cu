@@ -2,6 +2,8 @@
 // 128-bit vectorised, grid sized as a multiple of the SM count, every product/sum individually rounded so the
 // result is bit-identical to the reference's chain of separate elementwise ops
 // (diffusion/gaussian_diffusion_posenet.py:212-234, 426-434, 461-479, 192-210, 696-715).
+#include <curand_kernel.h>
+
 #include "common.h"
 
 namespace rohm {
@@ -80,6 +82,38 @@ __global__ void __launch_bounds__(kThreads) ddim_step_kernel(const float* __rest
   }
 }
 
+// The same update with the Gaussian noise drawn inside the kernel, bit-identical to what `torch.randn_like(x)` would have
+// produced from the same generator state (ATen distribution_elementwise_grid_stride_kernel with curand_normal4, unroll 4):
+// virtual thread `vidx` of torch's grid (G = grid * 256 threads) owns elements vidx + G * j; its j-th normal is component
+// j % 4 of its (j / 4)-th curand_normal4 call on Philox4_32_10(seed, subsequence = vidx, offset).  One real thread per
+// virtual thread, so the launch reads x0 / x_t and writes x_{t-1} once and the noise never touches memory.
+__global__ void __launch_bounds__(kThreads) ddpm_step_philox_kernel(const float* __restrict__ x0, const float* x_t,
+                                                                    const float* __restrict__ g0,
+                                                                    const float* __restrict__ g1, int n_grads, float* out,
+                                                                    int64_t numel, int64_t clip_elems,
+                                                                    const float* __restrict__ coef, int64_t coef_stride,
+                                                                    unsigned long long seed, unsigned long long offset,
+                                                                    int64_t G, int iters) {
+  const int64_t vidx = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (vidx >= G) return;
+  curandStatePhilox4_32_10_t state;
+  curand_init(seed, static_cast<unsigned long long>(vidx), offset, &state);
+  for (int k = 0; k < iters; ++k) {
+    const float4 nz = curand_normal4(&state);
+    const float z[4] = {nz.x, nz.y, nz.z, nz.w};
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int64_t li = vidx + G * (4 * k + ii);
+      if (li < numel) {
+        const int64_t clip = li / clip_elems;
+        const float* cf = coef + clip * coef_stride;
+        out[li] = ddpm_one(x0[li], x_t[li], z[ii], n_grads > 0 ? g0[li] : 0.f, n_grads > 1 ? g1[li] : 0.f, n_grads, cf[0],
+                           cf[1], cf[2], cf[3], cf[4]);
+      }
+    }
+  }
+}
+
 int grid_for(const rohm_ctx* ctx, int64_t work_items) {
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   int64_t blocks = (work_items + kThreads - 1) / kThreads;
@@ -125,6 +159,61 @@ extern "C" int rohm_ddpm_step(rohm_ctx* ctx, const float* x0, const float* x_t, 
   ROHM_CUDA(ctx, cudaGetLastError());
   return ROHM_OK;
 }
+
+// Launch geometry of torch's normal_ kernel for `numel` fp32 elements on this device (ATen calc_execution_policy):
+// G = virtual threads, iters = curand_normal4 calls per thread, *increment = what the generator's offset advances by.
+static int torch_normal_policy(rohm_ctx* ctx, int64_t numel, int64_t* G, int* iters, unsigned long long* increment) {
+  int threads_per_sm = 0;
+  ROHM_CUDA(ctx, cudaDeviceGetAttribute(&threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, ctx->device));
+  const int64_t blocks_per_sm = threads_per_sm / 256;
+  int64_t grid = (numel + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * blocks_per_sm;
+  if (grid > cap) grid = cap;
+  *G = grid * 256;
+  *iters = static_cast<int>((numel - 1) / (*G * 4) + 1);
+  *increment = static_cast<unsigned long long>(*iters) * 4ull;
+  return ROHM_OK;
+}
+
+extern "C" int rohm_ddpm_step_philox(rohm_ctx* ctx, const float* x0, const float* x_t, const float* grad0, const float* grad1,
+                                     int n_grads, float* out, int64_t n_clips, int64_t clip_elems, const float* coef,
+                                     int64_t coef_clip_stride, uint64_t seed, uint64_t offset, uint64_t* offset_increment,
+                                     void* stream) {
+  if (ctx == nullptr) return ROHM_ERR_INVALID;
+  rohm::DeviceGuard device_guard__(ctx);
+  if (n_clips < 0 || clip_elems < 0 || x0 == nullptr || x_t == nullptr || out == nullptr || coef == nullptr || n_grads < 0 ||
+      n_grads > 2 || (n_grads > 0 && grad0 == nullptr) || (n_grads > 1 && grad1 == nullptr))
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_ddpm_step_philox: bad arguments");
+  const int64_t numel = n_clips * clip_elems;
+  if (offset_increment != nullptr) *offset_increment = 0;
+  if (numel == 0) return ROHM_OK;
+  int64_t G = 0;
+  int iters = 0;
+  unsigned long long inc = 0;
+  int rc = torch_normal_policy(ctx, numel, &G, &iters, &inc);
+  if (rc != ROHM_OK) return rc;
+  if (offset_increment != nullptr) *offset_increment = inc;
+  ddpm_step_philox_kernel<<<static_cast<unsigned>(G / kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x0, x_t, grad0, grad1, n_grads, out, numel, clip_elems, coef, coef_clip_stride, seed, offset, G, iters);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  return ROHM_OK;
+}
+
+// For the denoiser engines that append the update to their forward graph (posenet.cu): the kernel's address (to find its
+// graph node) and a launch with explicit geometry.
+namespace rohm {
+const void* ddpm_step_philox_kernel_address() { return reinterpret_cast<const void*>(ddpm_step_philox_kernel); }
+int ddpm_step_philox_policy(rohm_ctx* ctx, int64_t numel, int64_t* G, int* iters, unsigned long long* increment) {
+  return torch_normal_policy(ctx, numel, G, iters, increment);
+}
+cudaError_t launch_ddpm_step_philox(const float* x0, const float* x_t, float* out, int64_t numel, int64_t clip_elems,
+                                    const float* coef, unsigned long long seed, unsigned long long offset, int64_t G, int iters,
+                                    cudaStream_t st) {
+  ddpm_step_philox_kernel<<<static_cast<unsigned>(G / kThreads), kThreads, 0, st>>>(
+      x0, x_t, nullptr, nullptr, 0, out, numel, clip_elems, coef, static_cast<int64_t>(0), seed, offset, G, iters);
+  return cudaGetLastError();
+}
+}  // namespace rohm
 
 extern "C" int rohm_q_sample(rohm_ctx* ctx, const float* x_start, const float* noise, float* out, int64_t n,
                              float sqrt_ac, float sqrt_one_minus_ac, void* stream) {

@@ -24,6 +24,11 @@ import torch as th
 from . import ops, schedule
 from ._lib import RohmB200Error
 
+import os
+
+# ROHM_B200_FUSED_STEP=0: keep the explicit torch.randn_like + gather + update launches (developer / A-B switch)
+_FUSED_STEP = os.environ.get("ROHM_B200_FUSED_STEP", "1") != "0"
+
 get_named_beta_schedule = schedule.get_named_beta_schedule
 betas_for_alpha_bar = schedule.betas_for_alpha_bar
 space_timesteps = schedule.space_timesteps
@@ -222,17 +227,56 @@ class _GaussianDiffusion:
         batch['x_t'] = x
         return x, model(batch, self._scale_timesteps(t), **(model_kwargs or {}))
 
+    def _wrap_model(self, model):
+        return model  # the respaced subclasses wrap the denoiser so that it sees original timesteps
+
+    # ------------------------------------------------------------------ fused step (one launch per step)
+    def _noise_in_kernel(self, x):
+        """The noise may be drawn inside the update kernel when it comes from torch's own CUDA generator (bit-identical
+        stream, see ops.ddpm_step_philox); an injected noise source (tests, sharded parity noise) keeps the explicit tensor."""
+        return self._randn_like is th.randn_like and x.is_cuda and _FUSED_STEP
+
+    def _coef_row(self, t, step_index):
+        """The step's coefficient row: a view of the per-device table when the (batch-uniform) step index is known to the
+        host, else a gather by the per-clip indices."""
+        if step_index is not None:
+            return self._dev(t.device)["coef"][int(step_index)]
+        return self._coef_for(t)
+
+    def _fused_posenet_step(self, model, batch, x, t, step_index, model_kwargs):
+        """PoseNet, unguided step, noise from torch's generator, no model kwargs: forward + update as ONE graph launch."""
+        if not (self._POSENET and step_index is not None and not model_kwargs and self._noise_in_kernel(x)):
+            return None
+        model = self._wrap_model(model)  # respaced schedules: step index -> original timestep
+        inner = model.model if isinstance(model, _WrappedModel) else model
+        prep = getattr(inner, "prepare_cond", None)
+        if prep is None or x.dim() != 4 or self.rescale_timesteps or t.is_floating_point():
+            return None
+        x = x if (x.is_contiguous() and x.dtype == th.float32) else x.contiguous().float()
+        batch['x_t'] = x
+        ts = model.map_timesteps(t) if isinstance(model, _WrappedModel) else t
+        e = prep(batch['cond'])
+        x0, nxt = e.sample_step(x, ts.to(th.int64).contiguous(), self._coef_row(t, step_index))
+        return {"sample": nxt, "pred_xstart": x0, "x_t": x}
+
     def p_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
-                 const_noise=False):
+                 const_noise=False, _step_index=None):
         """x_{t-1} = coef1[t] x0 + coef2[t] x_t + (t != 0) exp(0.5 logvar[t]) noise, x0 = model(batch | x_t, t).
         Returns {'sample', 'pred_xstart', 'x_t'}."""
+        if cond_fn is None and not const_noise:
+            fused = self._fused_posenet_step(model, batch, x, t, _step_index, model_kwargs)
+            if fused is not None:
+                return fused
         x, x0 = self._denoise(model, batch, x, t, model_kwargs)
+        if cond_fn is None and not const_noise and self._noise_in_kernel(x):
+            return {"sample": ops.ddpm_step_philox(x0, x, self._coef_row(t, _step_index)), "pred_xstart": x0, "x_t": x}
         noise = self._randn_like(x)
         if const_noise:
             noise = noise[[0]].repeat(x.shape[0], *([1] * (x.dim() - 1)))
-        coef = self._coef_for(t)
+        coef = self._coef_row(t, _step_index)
         if cond_fn is not None and not self._POSENET:
             # TrajNet variant only (reference _trajnet.py:433-436): mean <- condition_mean(cond_fn, ...)
+            coef = self._coef_for(t)
             rows = coef.clone()
             rows[:, 2:] = 0
             mean = ops.ddpm_step(x0, x, x0, rows)
@@ -250,9 +294,19 @@ class _GaussianDiffusion:
                            model_kwargs=None, const_noise=False, _step_index=None):
         """PoseNet: p_sample plus the hard-coded test-time guidance schedule; TrajNet: identical to p_sample without
         const_noise / cond_fn (the reference's TrajNet variant contains no guidance)."""
+        step = None if _step_index is None else int(_step_index)
+        guided_now = (self._POSENET and grad_type in _GUIDANCE and
+                      (step is None or any(step <= last for _, _, last in _GUIDANCE[grad_type])))
+        if not guided_now:
+            fused = self._fused_posenet_step(model, batch, x, t, _step_index, model_kwargs)
+            if fused is not None:
+                return fused
         x, x0 = self._denoise(model, batch, x, t, model_kwargs)
-        noise = self._randn_like(x)
-        coef = self._coef_for(t)
+        in_kernel = self._noise_in_kernel(x)
+        noise = None if in_kernel else self._randn_like(x)
+        coef = self._coef_row(t, _step_index)
+        if coef.dim() == 1:
+            coef = coef.unsqueeze(0).expand(x.shape[0], -1)  # guidance scales are written per clip below
         grads = []
         if self._POSENET and grad_type in _GUIDANCE:
             step = int(t[0]) if _step_index is None else _step_index  # the reference syncs on t[0] every step
@@ -276,7 +330,11 @@ class _GaussianDiffusion:
                     coef[:, 3 + k] = w * var  # fp32 product weight * variance[t], as the reference forms it
         elif grad_type is not None and self._POSENET:
             pass  # unknown grad_type: the reference silently applies no guidance
-        sample = ops.ddpm_step(x0, x, noise, coef, grads=tuple(grads))
+        coef = coef.contiguous()
+        if in_kernel:
+            sample = ops.ddpm_step_philox(x0, x, coef, grads=tuple(grads))
+        else:
+            sample = ops.ddpm_step(x0, x, noise, coef, grads=tuple(grads))
         return {"sample": sample, "pred_xstart": x0, "x_t": x}
 
     # ------------------------------------------------------------------ loops
@@ -363,10 +421,10 @@ class _GaussianDiffusion:
                     else:
                         out = self.p_sample_with_grad(model, batch, img, t, clip_denoised=clip_denoised,
                                                       denoised_fn=denoised_fn, cond_fn=cond_fn,
-                                                      model_kwargs=model_kwargs, const_noise=const_noise)
+                                                      model_kwargs=model_kwargs, const_noise=const_noise, _step_index=i)
                 else:
                     out = self.p_sample(model, batch, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                        cond_fn=cond_fn, model_kwargs=model_kwargs, const_noise=const_noise)
+                                        cond_fn=cond_fn, model_kwargs=model_kwargs, const_noise=const_noise, _step_index=i)
                 yield out
                 img = out["sample"]
 
@@ -466,9 +524,10 @@ class GaussianDiffusionTrajNet(_GaussianDiffusion):
     _POSENET = False
 
     def p_sample_with_grad(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None,
-                           model_kwargs=None, const_noise=False):
+                           model_kwargs=None, const_noise=False, _step_index=None):
         return super().p_sample_with_grad(model, batch, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                          cond_fn=cond_fn, grad_type=None, model_kwargs=model_kwargs)
+                                          cond_fn=cond_fn, grad_type=None, model_kwargs=model_kwargs,
+                                          _step_index=_step_index)
 
     def p_sample_loop(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
@@ -518,8 +577,15 @@ class _WrappedModel:
             self._maps[key] = m
         return m
 
+    def map_timesteps(self, ts):
+        """Original timesteps of a batch of step indices (what __call__ hands to the denoiser); the identity map of an
+        un-respaced schedule needs no gather."""
+        if self.timestep_map == list(range(len(self.timestep_map))):
+            return ts
+        return self._map(ts)[ts]
+
     def __call__(self, x, ts, **kwargs):
-        new_ts = self._map(ts)[ts]
+        new_ts = self.map_timesteps(ts)
         if self.rescale_timesteps:
             new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
         return self.model(x, new_ts, **kwargs)

@@ -60,6 +60,47 @@ def ddpm_step(x0, x_t, noise, coef, grads=(), out=None):
     return out
 
 
+def cuda_generator_state(device):
+    """(generator, seed, offset) of torch's default CUDA generator of `device`: what torch.randn_like would consume next."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    return gen, int(gen.initial_seed()), int(gen.get_offset())
+
+
+def ddpm_step_philox(x0, x_t, coef, grads=(), out=None):
+    """ddpm_step with noise = torch.randn_like(x_t) drawn inside the kernel from torch's CUDA generator (same values, same
+    generator advance as the explicit call), saving the noise tensor's launch and its HBM round trip."""
+    for n, t in (("x0", x0), ("x_t", x_t), ("coef", coef)):
+        _require_cuda(n, t)
+    if x0.shape != x_t.shape:
+        raise RohmB200Error("ddpm_step_philox: x0 and x_t must have the same shape")
+    for g in grads:
+        _require_cuda("grad", g)
+        if g.shape != x0.shape:
+            raise RohmB200Error("ddpm_step_philox: grad shape mismatch")
+    B = x0.shape[0]
+    clip_elems = x0.numel() // max(B, 1)
+    if coef.dim() == 1:
+        stride = 0
+        if coef.numel() < _lib.DDPM_COEFS:
+            raise RohmB200Error("ddpm_step_philox: coef row must hold 8 floats")
+    else:
+        if coef.shape != (B, _lib.DDPM_COEFS):
+            raise RohmB200Error(f"ddpm_step_philox: per-clip coef must be [{B}, 8]")
+        stride = _lib.DDPM_COEFS
+    if out is None:
+        out = torch.empty_like(x0)
+    lib, c = _lib.load(), _lib.ctx(x0.device.index)
+    gen, seed, offset = cuda_generator_state(x0.device)
+    inc = C.c_uint64(0)
+    g0 = grads[0] if len(grads) > 0 else None
+    g1 = grads[1] if len(grads) > 1 else None
+    rc = lib.rohm_ddpm_step_philox(c, _ptr(x0), _ptr(x_t), _ptr(g0), _ptr(g1), len(grads), _ptr(out), B, clip_elems,
+                                   _ptr(coef), stride, seed, offset, C.byref(inc), _stream(x0.device))
+    _lib.check(rc, c)
+    gen.set_offset(offset + int(inc.value))
+    return out
+
+
 def q_sample(x_start, noise, sqrt_ac, sqrt_one_minus_ac):
     _require_cuda("x_start", x_start)
     _require_cuda("noise", noise)

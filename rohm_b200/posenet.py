@@ -114,6 +114,21 @@ class PoseNetEngine:
         _lib.check(rc, self.ctx)
         return out
 
+    def sample_step(self, x_t, timesteps, coef_row):
+        """One whole ancestral step as one graph launch (rohm_posenet_sample_step): -> (pred_xstart, x_{t-1}); the noise is
+        what torch.randn_like(x_t) would have drawn (torch's CUDA generator is advanced accordingly)."""
+        from .ops import cuda_generator_state
+        B, _, _, T = x_t.shape
+        x0, nxt = torch.empty_like(x_t), torch.empty_like(x_t)
+        gen, seed, offset = cuda_generator_state(x_t.device)
+        inc = C.c_uint64(0)
+        rc = self.lib.rohm_posenet_sample_step(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(timesteps.data_ptr()),
+                                               C.c_void_p(x0.data_ptr()), C.c_void_p(nxt.data_ptr()),
+                                               C.c_void_p(coef_row.data_ptr()), seed, offset, C.byref(inc), B, T, self._stream())
+        _lib.check(rc, self.ctx)
+        gen.set_offset(offset + int(inc.value))
+        return x0, nxt
+
     def profile(self, x_t, timesteps):
         """One forward with per-kernel CUDA-event timing -> ({category: ms}, {category: launches})."""
         B, _, _, T = x_t.shape

@@ -359,3 +359,59 @@ def test_prox_guidance_schedule_runs_both_terms(posenet, cuda_device):
     del m.guide_2d_projection_with_smpl, m.guide_skating_with_smpl
     assert used == ['2d', 'sk'] * 3 and bool(torch.isfinite(out).all())
     delattr(ds, 'cam_R'), delattr(ds, 'cam_t')
+
+
+def test_in_kernel_noise_is_torchs_own_stream(cuda_device):
+    """rohm_ddpm_step_philox draws what torch.randn_like would have drawn (same values, same generator advance), for sizes
+    below / at / above one pass of torch's grid (148 SMs x 8 blocks x 256 threads x 4)."""
+    dev = cuda_device
+    gen = torch.cuda.default_generators[dev.index]
+    for shape in [(1, 7, 1, 3), (2, 294, 1, 16), (32, 294, 1, 144), (128, 294, 1, 144), (64, 144, 13)]:
+        torch.manual_seed(11)
+        x0, x = torch.randn(shape, device=dev), torch.randn(shape, device=dev)
+        coef = torch.rand(shape[0], 8, device=dev)
+        g1 = torch.randn(shape, device=dev)
+        off0 = gen.get_offset()
+        ref = ops.ddpm_step(x0, x, torch.randn_like(x), coef, grads=(g1,))
+        off_ref = gen.get_offset()
+        gen.set_offset(off0)
+        got = ops.ddpm_step_philox(x0, x, coef, grads=(g1,))
+        assert gen.get_offset() == off_ref, shape
+        assert torch.equal(got, ref), shape
+        after_a = torch.randn(5, device=dev)
+        gen.set_offset(off_ref)
+        assert torch.equal(after_a, torch.randn(5, device=dev))
+
+
+def test_fused_sample_step_equals_the_unfused_chain(posenet, cuda_device, monkeypatch):
+    """One graph launch per step (forward + in-kernel-noise update) == forward, torch.randn_like, gather, update: bit for bit,
+    for an un-respaced and a respaced schedule, and torch's generator ends in the same state."""
+    m, _ = posenet
+    B, T = 2, 16
+    cond = synthetic.posenet_batch(B, T, 5)['cond'].to(cuda_device)
+    gen = torch.cuda.default_generators[cuda_device.index]
+    for steps, resp in ((1000, 'ddim6'), (6, '')):
+        d = _diff(steps, resp, cuda_device)
+        outs, offs = [], []
+        for fused in (True, False):
+            monkeypatch.setattr(diffusion, "_FUSED_STEP", fused)
+            torch.manual_seed(123)
+            outs.append(d.p_sample_loop(m, {'cond': cond}, [B, 294, 1, T], clip_denoised=False))
+            offs.append(gen.get_offset())
+        assert torch.equal(outs[0], outs[1]) and offs[0] == offs[1], (steps, resp)
+    # guided tail (explicit forward + guidance + in-kernel noise) against the explicit-noise path
+    ds = synthetic.make_dataset('pose', seed=3, realistic_std=True)
+    old = m.dataset
+    m.dataset = ds
+    try:
+        d = _diff(1000, "4" + ",0" * 19, cuda_device)
+        init = synthetic.plausible_motion(B, T, 4, ds).to(cuda_device)
+        outs = []
+        for fused in (True, False):
+            monkeypatch.setattr(diffusion, "_FUSED_STEP", fused)
+            torch.manual_seed(5)
+            outs.append(d.p_sample_loop(m, {'cond': init}, [B, 294, 1, T], clip_denoised=False, cond_fn_with_grad=True,
+                                        grad_type='amass'))
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        m.dataset = old
