@@ -18,6 +18,7 @@
 // Gram-Schmidt output only moves inside SO(3), so its Jacobian contribution is the identity: the VJP goes straight
 // from the joint rotation matrices to the 6-D inputs (differences to the reference's autograd: its eps clamps below
 // ~2e-3 rad and fp32 round-off of the round trip).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <new>
@@ -38,6 +39,7 @@ constexpr int kBetas = 10;
 constexpr int kPoseFeat = 189;  // (22 - 1) * 9 non-zero pose-corrective features (hands / jaw / eyes are identity)
 constexpr int kBlendK = 256;    // 189 pose features + 10 betas + 1 (template), zero-padded to whole K blocks (64 fp16 / 32 TF32)
 constexpr int kMaxBones = 8;    // compressed skinning weights per vertex
+constexpr int64_t kLbsChunk = 384;  // frames per (blend GEMM -> skinning) chunk: 384 x 31488 x 4 B = 48 MB of v_posed
 
 __constant__ int c_parents[kJ];
 
@@ -239,14 +241,14 @@ __global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __r
 // registers for all frames (re-reading them per frame was 5x the algorithmic traffic), the frames' 55 x 12 transform
 // tables are staged in shared memory.  HBM-bound: 12 B in + 12 B out per vertex and frame.
 constexpr int kSkinFrames = 16;
-__global__ void __launch_bounds__(256) skin_kernel(const float* __restrict__ vposed, int64_t vp_pitch,
-                                                   const float* __restrict__ A, const int* __restrict__ idx,
+// grid = (vertex blocks, Y): CTA (vb, y) keeps the (bone, weight) pairs of its 256 vertices in registers and walks the frame
+// blocks y, y + Y, ... of the chunk; Y is chosen by the host so that the grid is one full wave (5 CTAs of 42 KB per SM), which
+// removes the partial-wave tail that a (vertex blocks x frame blocks) grid has for most frame counts.
+__global__ void __launch_bounds__(256, 4) skin_kernel(const float* __restrict__ vposed, int64_t vp_pitch,
+                                                      const float* __restrict__ A, const int* __restrict__ idx,
                                                    const float* __restrict__ wt, int V, int64_t N,
                                                    float* __restrict__ verts) {
   __shared__ __align__(16) float sA[kSkinFrames][kJ * 12];
-  const int64_t n0 = static_cast<int64_t>(blockIdx.y) * kSkinFrames;
-  const int nf = static_cast<int>(min(static_cast<int64_t>(kSkinFrames), N - n0));
-  for (int i = threadIdx.x; i < nf * kJ * 12; i += blockDim.x) sA[i / (kJ * 12)][i % (kJ * 12)] = A[n0 * kJ * 12 + i];
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   int bi[kMaxBones];
   float bw[kMaxBones];
@@ -258,41 +260,52 @@ __global__ void __launch_bounds__(256) skin_kernel(const float* __restrict__ vpo
     bi[0] = i0.x, bi[1] = i0.y, bi[2] = i0.z, bi[3] = i0.w, bi[4] = i1.x, bi[5] = i1.y, bi[6] = i1.z, bi[7] = i1.w;
     bw[0] = w0.x, bw[1] = w0.y, bw[2] = w0.z, bw[3] = w0.w, bw[4] = w1.x, bw[5] = w1.y, bw[6] = w1.z, bw[7] = w1.w;
   }
-  __syncthreads();
-  if (v >= V) return;
-  // Four frames per iteration: all twelve streaming loads are issued before the first dependent use (the loop was bound by
-  // load latency, ncu: 12.6 stall cycles on long scoreboard per issued instruction with one frame in flight).
-  constexpr int kFramesInFlight = 4;
-  for (int f0 = 0; f0 < nf; f0 += kFramesInFlight) {
-    float px[kFramesInFlight], py[kFramesInFlight], pz[kFramesInFlight];
-#pragma unroll
-    for (int u = 0; u < kFramesInFlight; ++u) {
-      const int f = min(f0 + u, nf - 1);
-      const float* p = vposed + (n0 + f) * vp_pitch + static_cast<int64_t>(v) * 3;
-      px[u] = __ldcs(p), py[u] = __ldcs(p + 1), pz[u] = __ldcs(p + 2);  // read once: evict-first
+  const int64_t frame_blocks = (N + kSkinFrames - 1) / kSkinFrames;
+  for (int64_t fb = blockIdx.y; fb < frame_blocks; fb += gridDim.y) {
+    const int64_t n0 = fb * kSkinFrames;
+    const int nf = static_cast<int>(min(static_cast<int64_t>(kSkinFrames), N - n0));
+    __syncthreads();  // the previous frame block's transforms are no longer read
+    {
+      const float4* src = reinterpret_cast<const float4*>(A + n0 * kJ * 12);
+      float4* dst = reinterpret_cast<float4*>(&sA[0][0]);
+      for (int i = threadIdx.x; i < nf * kJ * 3; i += blockDim.x) dst[i] = src[i];
     }
+    __syncthreads();
+    if (v >= V) continue;
+    // Four frames per iteration: all streaming loads are issued before the first dependent use (the loop is bound by load
+    // latency: ncu showed 12.6 stall cycles on long scoreboard per issued instruction with one frame in flight).
+    constexpr int kFramesInFlight = 4;
+    for (int f0 = 0; f0 < nf; f0 += kFramesInFlight) {
+      float px[kFramesInFlight], py[kFramesInFlight], pz[kFramesInFlight];
 #pragma unroll
-    for (int u = 0; u < kFramesInFlight; ++u) {
-      const int f = f0 + u;
-      if (f >= nf) break;
-      float T[12];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) T[e] = 0.0f;
-#pragma unroll
-      for (int k = 0; k < kMaxBones; ++k) {
-        if (bw[k] != 0.0f) {
-          const float4* a = reinterpret_cast<const float4*>(sA[f] + bi[k] * 12);  // 3 x 128-bit smem loads per bone
-          const float4 r0 = a[0], r1 = a[1], r2 = a[2];
-          const float w = bw[k];
-          T[0] = fmaf(w, r0.x, T[0]), T[1] = fmaf(w, r0.y, T[1]), T[2] = fmaf(w, r0.z, T[2]), T[3] = fmaf(w, r0.w, T[3]);
-          T[4] = fmaf(w, r1.x, T[4]), T[5] = fmaf(w, r1.y, T[5]), T[6] = fmaf(w, r1.z, T[6]), T[7] = fmaf(w, r1.w, T[7]);
-          T[8] = fmaf(w, r2.x, T[8]), T[9] = fmaf(w, r2.y, T[9]), T[10] = fmaf(w, r2.z, T[10]), T[11] = fmaf(w, r2.w, T[11]);
-        }
+      for (int u = 0; u < kFramesInFlight; ++u) {
+        const int f = min(f0 + u, nf - 1);
+        const float* p = vposed + (n0 + f) * vp_pitch + static_cast<int64_t>(v) * 3;
+        px[u] = __ldcs(p), py[u] = __ldcs(p + 1), pz[u] = __ldcs(p + 2);  // read once: evict-first
       }
-      float* o = verts + ((n0 + f) * V + v) * 3;
-      __stcs(o, T[0] * px[u] + T[1] * py[u] + T[2] * pz[u] + T[3]);  // written once, never re-read by this library
-      __stcs(o + 1, T[4] * px[u] + T[5] * py[u] + T[6] * pz[u] + T[7]);
-      __stcs(o + 2, T[8] * px[u] + T[9] * py[u] + T[10] * pz[u] + T[11]);
+#pragma unroll
+      for (int u = 0; u < kFramesInFlight; ++u) {
+        const int f = f0 + u;
+        if (f >= nf) break;
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxBones; ++k) {
+          if (bw[k] != 0.0f) {
+            const float4* a = reinterpret_cast<const float4*>(sA[f] + bi[k] * 12);  // 3 x 128-bit smem loads per bone
+            const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+            const float w = bw[k];
+            T[0] = fmaf(w, r0.x, T[0]), T[1] = fmaf(w, r0.y, T[1]), T[2] = fmaf(w, r0.z, T[2]), T[3] = fmaf(w, r0.w, T[3]);
+            T[4] = fmaf(w, r1.x, T[4]), T[5] = fmaf(w, r1.y, T[5]), T[6] = fmaf(w, r1.z, T[6]), T[7] = fmaf(w, r1.w, T[7]);
+            T[8] = fmaf(w, r2.x, T[8]), T[9] = fmaf(w, r2.y, T[9]), T[10] = fmaf(w, r2.z, T[10]), T[11] = fmaf(w, r2.w, T[11]);
+          }
+        }
+        float* o = verts + ((n0 + f) * V + v) * 3;
+        __stcs(o, T[0] * px[u] + T[1] * py[u] + T[2] * pz[u] + T[3]);  // written once, never re-read by this library
+        __stcs(o + 1, T[4] * px[u] + T[5] * py[u] + T[6] * pz[u] + T[7]);
+        __stcs(o + 2, T[8] * px[u] + T[9] * py[u] + T[10] * pz[u] + T[11]);
+      }
     }
   }
 }
@@ -673,7 +686,14 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
   if (ok && with_vertices) {
     bd->A = bd->pool.floats(F * kJ * 12);
     bd->feat_h = bd->pool.floats(F * kBlendK), bd->feat_l = bd->pool.floats(F * kBlendK);
-    bd->vposed = bd->pool.floats(F * round_up(V * 3, 128));  // row pitch padded to the GEMM tile: vector stores
+    // v_posed lives only for one chunk of kLbsChunk frames (48 MB): the blend GEMM writes it and the skinning kernel reads it
+    // back while it is still in the 126 MB L2, so the 2 x 531 MB round trip of a whole-batch intermediate never reaches HBM
+    if (const char* env = getenv("ROHM_B200_LBS_CHUNK")) {  // developer switch: frames per chunk (multiple of 128)
+      const long v = atol(env);
+      if (v >= 128 && v % 128 == 0) bd->chunk = v;
+    }
+    bd->vposed_stride = std::min<int64_t>(F, bd->chunk) * round_up(V * 3, 128);
+    bd->vposed = bd->pool.floats(2 * bd->vposed_stride);
     bd->bone_idx = static_cast<int*>(bd->pool.bytes(static_cast<int64_t>(V) * kMaxBones * sizeof(int)));
     bd->bone_w = bd->pool.floats(static_cast<int64_t>(V) * kMaxBones);
     bd->lbs_w_copy = bd->pool.floats(static_cast<int64_t>(V) * kJ);
@@ -733,10 +753,22 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
     g.num_segs = 1, g.seg_kblocks[0] = kBlendK / gemm_block_k(bd->kind), g.seg_row_mul[0] = 1;
     g.acc_scale = 1.0f / bd->blend.scale;
     g.out = bd->vposed, g.ldo = bd->blend.Np, g.N = bd->blend.Np, g.out_row_mul = 1;  // padded columns are exact zeros
-    if (gemm_enable_tma_store(&g, F, bd->kind) != 0) {  // 32 x 32 fp32 chunks leave through TMA bulk stores
+    if (gemm_enable_tma_store(&g, std::min<int64_t>(F, bd->chunk), bd->kind) != 0 ||  // 32 x 32 fp32 chunks leave through TMA bulk stores
+        make_store_tmap(&bd->st_out_b, bd->vposed + bd->vposed_stride, std::min<int64_t>(F, bd->chunk), bd->blend.Np, bd->blend.Np,
+                        false) != 0) {
       delete bd;
       return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: store tensor map failed");
     }
+    bool ev_ok = cudaStreamCreateWithFlags(&bd->skin_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ev_ok; ++i)
+      ev_ok = cudaEventCreateWithFlags(&bd->gemm_done[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&bd->skin_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) {
+      delete bd;
+      return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: stream / event creation failed");
+    }
+    if (const char* env = getenv("ROHM_B200_LBS_OVERLAP"))
+      if (env[0] == '0') cudaStreamDestroy(bd->skin_stream), bd->skin_stream = nullptr;
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -770,16 +802,46 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
       verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr, bd->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(ctx, cudaGetLastError());
   if (verts) {
-    GemmParams g = bd->g_blend;
-    g.M = static_cast<int>(N);
-    ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 128, bd->passes, st, false, bd->kind));
-    dim3 grid((bd->V + 255) / 256, static_cast<unsigned>(N));
-    if (bd->sparse_ok)
-      skin_kernel<<<dim3((bd->V + 255) / 256, static_cast<unsigned>((N + kSkinFrames - 1) / kSkinFrames)), 256, 0, st>>>(
-          bd->vposed, bd->blend.Np, bd->A, bd->bone_idx, bd->bone_w, bd->V, N, vertices);
-    else
-      skin_dense_kernel<<<grid, 256, 0, st>>>(bd->vposed, bd->blend.Np, bd->A, bd->lbs_w_copy, bd->V, vertices);
-    ROHM_CUDA(ctx, cudaGetLastError());
+    // Pipeline over chunks of kLbsChunk frames: blend GEMM of chunk i on the caller's stream into v_posed buffer i % 2,
+    // skinning of chunk i on a second stream (HBM-bound next to the tensor-bound GEMM of chunk i + 1).
+    const int vblocks = (bd->V + 255) / 256;
+    int occ = 0;  // resident CTAs per SM (registers / the 42 KB of shared memory decide)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skin_kernel, 256, 0) != cudaSuccess || occ < 1) occ = 3;
+    const int skin_y = std::max(1, (ctx->sm_count > 0 ? ctx->sm_count : 148) * occ / vblocks);  // one full wave
+    const int64_t kChunk = bd->chunk;
+    const int64_t chunks = (N + kChunk - 1) / kChunk;
+    const bool overlap = bd->skin_stream != nullptr && chunks > 1;
+    cudaStream_t ss = overlap ? bd->skin_stream : st;
+    for (int64_t c = 0; c < chunks; ++c) {
+      const int64_t r0 = c * kChunk;
+      const int64_t n = std::min<int64_t>(kChunk, N - r0);
+      float* vp = bd->vposed + (overlap ? (c & 1) : 0) * bd->vposed_stride;
+      if (overlap && c >= 2) ROHM_CUDA(ctx, cudaStreamWaitEvent(st, bd->skin_done[c & 1], 0));  // buffer free again
+      GemmParams g = bd->g_blend;
+      g.M = static_cast<int>(n);
+      g.seg_row_shift[0] = static_cast<int>(r0);  // A rows of this chunk; output rows are chunk-local
+      if (overlap && (c & 1)) g.out = vp, g.st_out = bd->st_out_b, g.st_hi = bd->st_out_b, g.st_lo = bd->st_out_b;
+      ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(n), bd->blend.Np, 128, bd->passes, st, false, bd->kind));
+      if (overlap) {
+        ROHM_CUDA(ctx, cudaEventRecord(bd->gemm_done[c & 1], st));
+        ROHM_CUDA(ctx, cudaStreamWaitEvent(ss, bd->gemm_done[c & 1], 0));
+      }
+      const float* A = bd->A + r0 * kJ * 12;
+      float* vout = vertices + r0 * bd->V * 3;
+      if (bd->sparse_ok) {
+        const int64_t fblocks = (n + kSkinFrames - 1) / kSkinFrames;
+        skin_kernel<<<dim3(vblocks, static_cast<unsigned>(std::min<int64_t>(skin_y, fblocks))), 256, 0, ss>>>(
+            vp, bd->blend.Np, A, bd->bone_idx, bd->bone_w, bd->V, n, vout);
+      } else {
+        skin_dense_kernel<<<dim3(vblocks, static_cast<unsigned>(n)), 256, 0, ss>>>(vp, bd->blend.Np, A, bd->lbs_w_copy, bd->V, vout);
+      }
+      ROHM_CUDA(ctx, cudaGetLastError());
+      if (overlap) ROHM_CUDA(ctx, cudaEventRecord(bd->skin_done[c & 1], ss));
+    }
+    if (overlap) {  // join: the caller's stream continues after the last skinning kernels
+      ROHM_CUDA(ctx, cudaStreamWaitEvent(st, bd->skin_done[0], 0));
+      ROHM_CUDA(ctx, cudaStreamWaitEvent(st, bd->skin_done[1], 0));
+    }
   }
   return ROHM_OK;
 }

@@ -25,4 +25,19 @@ struct rohm_body {
   float* jwork = nullptr;          // [max_frames, 22, 3] scratch joints (glue)
   float* gwork = nullptr;          // [max_frames, 22, 3] scratch joint gradients (2-D guidance)
   rohm::GemmParams g_blend{};
+  // full LBS pipeline: v_posed double buffer (one chunk each), second stream for the skinning kernels
+  int64_t vposed_stride = 0;
+  // frames per chunk.  Measured on B200 (32 x 143 frames): chunking v_posed through L2 (384-frame chunks, with or without the
+  // second stream) is not faster than one pass (0.99 vs 0.85 ms): the skinning kernel is issue-bound, not HBM-bound.
+  int64_t chunk = 4608;
+  CUtensorMap st_out_b{};
+  cudaStream_t skin_stream = nullptr;
+  cudaEvent_t gemm_done[2] = {nullptr, nullptr}, skin_done[2] = {nullptr, nullptr};
+  ~rohm_body() {
+    if (skin_stream) cudaStreamDestroy(skin_stream);
+    for (int i = 0; i < 2; ++i) {
+      if (gemm_done[i]) cudaEventDestroy(gemm_done[i]);
+      if (skin_done[i]) cudaEventDestroy(skin_done[i]);
+    }
+  }
 };

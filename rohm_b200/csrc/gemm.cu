@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     if (PASSES == 3) ptx::prefetch_tmap(&p.b_lo);
     for (int i = 0; i < Cfg::kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], p.multicast_a ? 2 : 1);  // multicast: the slot is refilled by both CTAs of the pair
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (p.multicast_a) ptx::cluster_sync_all();  // the partner's barriers are initialised before anything is sent to them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -303,11 +304,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             if (it == 0) stamp(p, 2);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kElemK, row);
-            ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], kcol, n0);
-            if (PASSES == 3) {
-              ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kElemK, row);
+            if (PASSES == 3 && p.multicast_a) {
+              // my half of the stripe's A tile goes to both CTAs of the pair (the partner sends the other half)
+              const int half_rows = kGemmBlockM / 2;
+              const uint32_t rank = ptx::cluster_ctarank();
+              ptx::tma_load_2d_multicast(st + rank * (Cfg::kABytes / 2), &p.a_hi_half, &full_bar[stage], kb * kElemK,
+                                         row + static_cast<int>(rank) * half_rows, 0x3);
+              ptx::tma_load_2d_multicast(st + Cfg::kABytes + rank * (Cfg::kABytes / 2), &p.a_lo_half, &full_bar[stage],
+                                         kb * kElemK, row + static_cast<int>(rank) * half_rows, 0x3);
+              ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], kcol, n0);
               ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], kcol, n0);
+            } else {
+              ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kElemK, row);
+              ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[stage], kcol, n0);
+              if (PASSES == 3) {
+                ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kElemK, row);
+                ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[stage], kcol, n0);
+              }
             }
             if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
           }
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc(KIND == kKindF16 ? /*F16*/ 0 : /*TF32*/ 2, kGemmBlockM, BLOCK_N);
+      constexpr uint32_t idesc_wide = ptx::make_idesc(KIND == kKindF16 ? 0 : 2, kGemmBlockM, BLOCK_N <= 128 ? 2 * BLOCK_N : BLOCK_N);
       auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
         if (KIND == kKindF16) ptx::mma_f16_ss(d, a, b, id, accumulate);
         else ptx::mma_tf32_ss(d, a, b, id, accumulate);
@@ -345,7 +359,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
             // address field
             const uint64_t koff = static_cast<uint64_t>(k * 2);
             const uint32_t first = (ki > 0 || k > 0) ? 1u : 0u;
-            if (PASSES == 3) {
+            if (PASSES == 3 && BLOCK_N <= 128) {
+              // B_hi and B_lo are adjacent in the stage, and so are the two accumulators in TMEM: A_hi x [B_hi ; B_lo] is ONE
+              // instruction of twice the width (columns [0, BLOCK_N) = hi*hi, [BLOCK_N, 2 BLOCK_N) = hi*lo), which reads A_hi
+              // from shared memory once instead of twice.  The main loop is bound by the shared-memory port (TMA fill + operand
+              // reads, 128 B/clk), not by the tensor pipe: 20 KB instead of 24 KB of operand reads per k-step.
+              mma(acc, a_hi + koff, b_hi + koff, idesc_wide, first);
+              mma(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, 1u);
+            } else if (PASSES == 3) {
               mma(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, first);
               mma(acc + BLOCK_N, a_hi + koff, b_lo + koff, idesc, 1u);
               mma(acc, a_hi + koff, b_hi + koff, idesc, first);
@@ -353,7 +374,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
               mma(acc, a_hi + koff, b_hi + koff, idesc, first);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (multicast: in both CTAs of the pair, which both write into it)
+          if (p.multicast_a) ptx::mma_commit_multicast(&empty_bar[stage], 0x3);
+          else ptx::mma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
         }
         ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
@@ -776,6 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   }
 
   __syncthreads();
+  if (p.multicast_a) ptx::cluster_sync_all();  // neither CTA leaves while the other may still send to it
   if (warp_idx == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -883,15 +907,27 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   cudaLaunchConfig_t cfg{};
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.stats_out != nullptr) grid -= grid % 4;  // a CTA keeps its column tile: tile % 4 == blockIdx % 4 on every round
+  const int tiles_n_ = (n_cols + BLOCK_N - 1) / BLOCK_N;
+  if (q.multicast_a && (PASSES != 3 || q.num_segs != 1 || tiles_n_ % 2 != 0 || grid < 2)) q.multicast_a = 0;
+  if (q.multicast_a) grid -= grid % 2;  // pairs: tiles 2j, 2j+1 of a round are neighbouring column tiles of one stripe
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (q.multicast_a) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
@@ -931,6 +967,17 @@ static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, in
 
 int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half) {
   return encode_store_map(map, base, rows, cols, ld, half);
+}
+
+int gemm_enable_multicast(GemmParams* p, const void* a_hi, const void* a_lo, int64_t rows, int64_t cols, int64_t ld, int n_cols,
+                          int block_n, int kind) {
+  p->multicast_a = 0;
+  if (p->num_segs != 1 || p->seg_row_mul[0] != 1 || ((n_cols + block_n - 1) / block_n) % 2 != 0) return 0;
+  int rc = make_tmap_2d(&p->a_hi_half, a_hi, rows, cols, ld, kGemmBlockM / 2, 1, kind);
+  if (rc == 0) rc = make_tmap_2d(&p->a_lo_half, a_lo, rows, cols, ld, kGemmBlockM / 2, 1, kind);
+  if (rc != 0) return rc;
+  p->multicast_a = 1;
+  return 0;
 }
 
 int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind) {

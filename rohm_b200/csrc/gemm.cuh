@@ -111,6 +111,14 @@ struct alignas(64) GemmParams {
   const float* res_beta;    // [N]
   float2* stats_out;        // [rows][8], or nullptr: plain epilogue
   float ln_eps;
+  // A-operand multicast (`multicast_a`, set by gemm_enable_multicast): CTAs run as clusters of two that own neighbouring
+  // column tiles of the same 128-row stripe; each loads HALF of the stripe's A tile (64 rows, a_hi_half / a_lo_half) and
+  // multicasts it to both, so A crosses the L2 -> SM fabric once per pair.  Measured on B200 the main loop of these GEMMs is
+  // bound by that fabric (148 SMs x 64 KB per 0.51 us), not by the tensor pipe.  Requires one A segment, an even number
+  // of column tiles and PASSES == 3.
+  CUtensorMap a_hi_half;
+  CUtensorMap a_lo_half;
+  int multicast_a;
   // optional: CTA 0 records %globaltimer at 8 milestones (developer instrumentation, see tools/gemm_selftest)
   unsigned long long* debug_ts;
   // filled in by launch_gemm: extent of the tile grid
@@ -129,6 +137,11 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 // buffers) and sets p.tma_store when the launch is eligible (see GemmParams); otherwise clears it.  Returns 0 or a
 // CUresult.
 int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind);
+
+// Builds the half-tile maps of segment 0 (same base / extents as a_hi[0], a_lo[0]; 64-row boxes) and sets p->multicast_a when
+// the launch is eligible, else clears it.  Returns 0 or a CUresult.
+int gemm_enable_multicast(GemmParams* p, const void* a_hi, const void* a_lo, int64_t rows, int64_t cols, int64_t ld, int n_cols,
+                          int block_n, int kind);
 
 // Tensor map for 32 x 32-element TMA store boxes over a row-major [rows, cols] matrix with pitch ld: fp32 with
 // SWIZZLE_128B (128-byte box rows) or fp16 with SWIZZLE_64B (64-byte box rows).  Returns 0 or a CUresult.

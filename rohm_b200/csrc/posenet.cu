@@ -1112,6 +1112,10 @@ struct rohm_posenet {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_tma_store = true;  // ROHM_B200_TMA_STORE=0 falls back to the per-thread store epilogue (developer switch)
+  // A-operand TMA multicast across CTA pairs (GemmParams::multicast_a).  Measured on B200: no gain (the main loop is bound by
+  // the shared-memory port, not by the L2 -> SM fabric: 0.7705 ms per forward with, 0.7633 ms without), so it is off by
+  // default; ROHM_B200_MULTICAST=1 turns it on.
+  bool use_multicast = false;
   // LayerNorm folding (F16X2, d_model 512; ROHM_B200_FUSED_LN=0 keeps the separate layernorm_kernel): the residual stream
   // is stored un-normalised as an fp16 pair plus per-row partial statistics (stats1: after the attention sublayer, stats2:
   // after the feed-forward sublayer), LN(u) is never materialised: see GemmParams::stats_out / a_stats
@@ -1283,6 +1287,9 @@ static int setup_linear(rohm_posenet* pn, GemmParams* g, const float* a_hi, cons
   g->N = w.N;
   g->out_row_mul = 1;
   g->out_row_add = 0;
+  if (pn->use_multicast && w.kind == kKindF16 && pn->passes == 3 &&
+      gemm_enable_multicast(g, a_hi, a_lo, rows, K, lda, w.N, w.block_n, w.kind) != 0)
+    return fail(pn->ctx, ROHM_ERR_CUDA, "cuTensorMapEncodeTiled failed (multicast maps)");
   return ROHM_OK;
 }
 
@@ -1496,6 +1503,7 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
   pn->C = w->in_feats, pn->Cout = w->out_feats, pn->traj = w->traj_feats, pn->pe_len = w->pe_len;
   pn->kind = precision == ROHM_PRECISION_F16X2 ? kKindF16 : kKindTf32;
   if (const char* env = getenv("ROHM_B200_TMA_STORE")) pn->use_tma_store = env[0] != '0';
+  if (const char* env = getenv("ROHM_B200_MULTICAST")) pn->use_multicast = env[0] != '0';
   pn->passes = precision == ROHM_PRECISION_TF32 ? 1 : 3;
   pn->max_batch = max_batch, pn->max_frames = max_frames;
   pn->max_rows = static_cast<int64_t>(max_batch) * (max_frames + 1);

@@ -50,17 +50,14 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, float* __restrict_
 
 // Timestep path of TrajNet (trajnet.py:120-125, 189) and the per-block time projections (heads.py:34-38, 51-52):
 //   temb = W3 mish(W1 sinusoid(t) + b1) + b3;  tp[b, :] = Wcat mish(temb) + bcat   (all blocks' Linear(32,out) stacked)
-__global__ void __launch_bounds__(256) trajnet_time_kernel(const int64_t* __restrict__ time, int time_dim,
-                                                           const float* __restrict__ w1, const float* __restrict__ b1,
-                                                           const float* __restrict__ w3, const float* __restrict__ b3,
-                                                           const float* __restrict__ wcat, const float* __restrict__ bcat,
-                                                           int total_out, float* __restrict__ tp) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void trajnet_time_compute(float t, int b, int time_dim, const float* __restrict__ w1,
+                                                     const float* __restrict__ b1, const float* __restrict__ w3,
+                                                     const float* __restrict__ b3, const float* __restrict__ wcat,
+                                                     const float* __restrict__ bcat, int total_out, float* __restrict__ tp,
+                                                     float* sm) {
   float* e = sm;                  // [time_dim]
   float* h = e + time_dim;        // [4 * time_dim]
   float* m = h + 4 * time_dim;    // [time_dim]  mish(temb)
-  const int b = blockIdx.x;
-  const float t = static_cast<float>(time[b]);
   const int half = time_dim / 2;
   if (threadIdx.x < half) {
     const float f = expf(static_cast<float>(threadIdx.x) * -(logf(10000.0f) / static_cast<float>(half - 1)));
@@ -81,13 +78,33 @@ __global__ void __launch_bounds__(256) trajnet_time_kernel(const int64_t* __rest
     m[n] = mish_f(acc);
   }
   __syncthreads();
-  // the stacked projections are split over blockIdx.y (each CTA recomputes the small time MLP above): one CTA per clip
-  // left 84 of 148 SMs idle for 89 us
+  // the stacked projections are split over blockIdx.y (each CTA recomputes the small time MLP above)
   for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < total_out; n += blockDim.x * gridDim.y) {
     float acc = bcat[n];
     for (int k = 0; k < time_dim; ++k) acc = fmaf(wcat[n * time_dim + k], m[k], acc);
     tp[static_cast<int64_t>(b) * total_out + n] = acc;
   }
+}
+
+// Per step the embedding depends on the (integer) timestep only, so the whole path is tabulated at create time for
+// t in [0, table_rows) (the direct evaluation took 89 us per forward, latency-bound) and the per-forward kernel is a row
+// gather; timesteps outside the table are evaluated directly.  `table` == nullptr: always evaluate (used to build the table).
+__global__ void __launch_bounds__(256) trajnet_time_kernel(const int64_t* __restrict__ time, int time_dim,
+                                                           const float* __restrict__ w1, const float* __restrict__ b1,
+                                                           const float* __restrict__ w3, const float* __restrict__ b3,
+                                                           const float* __restrict__ wcat, const float* __restrict__ bcat,
+                                                           int total_out, float* __restrict__ tp,
+                                                           const float* __restrict__ table, int table_rows) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int64_t ti = time[b];
+  if (table != nullptr && ti >= 0 && ti < table_rows) {  // block-uniform
+    const float4* src = reinterpret_cast<const float4*>(table + ti * total_out);
+    float4* dst = reinterpret_cast<float4*>(tp + static_cast<int64_t>(b) * total_out);
+    for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < total_out / 4; n += blockDim.x * gridDim.y) dst[n] = src[n];
+    return;
+  }
+  trajnet_time_compute(static_cast<float>(ti), b, time_dim, w1, b1, w3, b3, wcat, bcat, total_out, tp, sm);
 }
 
 // out = Mish(GroupNorm(y)) [+ tp[b, c]] [+ r1] [+ r2] on real rows, 0 on pad rows.  4 channels per thread.
@@ -187,6 +204,7 @@ __global__ void pack_conv_segment_kernel(const float* __restrict__ w, float* __r
 }
 
 constexpr int kLevels = 5;
+constexpr int kTimeTableRows = 1024;  // timesteps whose time path is tabulated at create time (RoHM: 100 or 1000 steps)
 constexpr int kGroups = 8;
 
 struct Act {  // one activation tensor at pyramid level `level`
@@ -225,14 +243,25 @@ struct rohm_trajnet {
   std::map<std::string, std::pair<const float*, int64_t>> sd;  // caller's tensors, valid during create only
   // time path
   float *w1 = nullptr, *b1 = nullptr, *w3 = nullptr, *b3 = nullptr, *wcat = nullptr, *bcat = nullptr, *tp = nullptr;
+  float* time_table = nullptr;  // [kTimeTableRows, tp_total]: the stacked projections of every tabulated timestep
   int tp_total = 0;
   std::map<std::string, int> tp_off;  // block prefix -> offset in the stacked time projection
   // activations
   std::map<std::string, Act> acts;
   std::map<std::string, Conv> convs;
   std::map<std::string, std::pair<float*, float*>> norms;  // GroupNorm gamma/beta by conv-block prefix
-  float *scratchY = nullptr, *scratchRes = nullptr;
-  Act scratchA;
+  // RTB-internal scratch, one set per concurrently running branch (0: U-Net, 1: TrajControl)
+  float *scratchY[2] = {nullptr, nullptr}, *scratchRes[2] = {nullptr, nullptr};
+  Act scratchA[2];
+  // The forward is captured as a graph with parallel branches: the TrajControl branch next to the U-Net encoder, every
+  // block's 1x1 residual convolution next to its conv1 -> GroupNorm -> conv2 chain.  None of these GEMMs fills the 148 SMs
+  // (11 to 96 tiles), so running them side by side shortens the critical path at no cost.  ROHM_B200_TRAJ_PARALLEL=0: serial.
+  bool parallel = true;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // 0: TrajControl branch, 1 / 2: residual convolutions of branch 0 / 1
+  std::vector<cudaEvent_t> events;
+  size_t ev_next = 0;
+  cudaEvent_t time_ready = nullptr;     // recorded after the time kernel; each branch waits for it before its first GroupNorm
+  bool time_pending[2] = {false, false};
   double* stats_arena = nullptr;
   int64_t stats_used = 0, stats_cap = 0;
   int cond_B = -1;
@@ -250,6 +279,10 @@ struct rohm_trajnet {
   cudaStream_t capture_stream = nullptr;
   ~rohm_trajnet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
+    for (cudaStream_t q : side)
+      if (q) cudaStreamDestroy(q);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (time_ready) cudaEventDestroy(time_ready);
     for (auto& g : graphs) {
       if (g.exec) cudaGraphExecDestroy(g.exec);
       if (g.graph) cudaGraphDestroy(g.graph);
@@ -439,8 +472,9 @@ int make_rtb(rohm_trajnet* tn, const std::string& p, std::vector<const Act*> src
   for (auto* s : srcs) Cin += s->C;
   int rc;
   Act y;  // fp32 scratch view with this block's width
-  y.f32 = tn->scratchY, y.C = Cout, y.ld = Cout, y.level = level;
-  Act a1 = tn->scratchA;
+  const int br = p.rfind("controlnet.", 0) == 0 ? 1 : 0;
+  y.f32 = tn->scratchY[br], y.C = Cout, y.ld = Cout, y.level = level;
+  Act a1 = tn->scratchA[br];
   a1.C = Cout, a1.ld = Cout, a1.level = level;
   tn->acts[p + "#y"] = y;
   tn->acts[p + "#a1"] = a1;
@@ -450,7 +484,7 @@ int make_rtb(rohm_trajnet* tn, const std::string& p, std::vector<const Act*> src
   if ((rc = load_norm(tn, p + "blocks.1.", Cout)) != ROHM_OK) return rc;
   if (Cin != Cout) {
     Act r;
-    r.f32 = tn->scratchRes, r.C = Cout, r.ld = Cout, r.level = level;
+    r.f32 = tn->scratchRes[br], r.C = Cout, r.ld = Cout, r.level = level;
     tn->acts[p + "#res"] = r;
     if ((rc = make_conv(tn, p + "res", p + "residual_conv", srcs, Cout, 1, 1, 0, &tn->acts[p + "#res"], false)) != ROHM_OK) return rc;
   }
@@ -482,21 +516,46 @@ int run_gn(rohm_trajnet* tn, const std::string& conv_name, const std::string& no
 }
 
 // Executes a ResidualTemporalBlock: out = Mish(GN(conv2(Mish(GN(conv1(x))) + time))) + res(x) [+ extra]
+// fork: everything recorded on `from` so far happens-before what is launched on `to` afterwards (event record + wait; during
+// stream capture this adds a graph edge)
+int order_after(rohm_trajnet* tn, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return ROHM_OK;
+  if (tn->ev_next == tn->events.size()) {
+    cudaEvent_t e = nullptr;
+    ROHM_CUDA(tn->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    tn->events.push_back(e);
+  }
+  cudaEvent_t e = tn->events[tn->ev_next++];
+  ROHM_CUDA(tn->ctx, cudaEventRecord(e, from));
+  ROHM_CUDA(tn->ctx, cudaStreamWaitEvent(to, e, 0));
+  return ROHM_OK;
+}
+
 int run_rtb(rohm_trajnet* tn, const std::string& p, const float* identity_res, const Act* out, const float* extra, int B,
-            cudaStream_t st) {
+            cudaStream_t st, cudaStream_t side = nullptr, int branch = 0) {
   int rc;
   const Act& y = tn->acts[p + "#y"];
   const Act& a1 = tn->acts[p + "#a1"];
   const int C = y.C, level = y.level;
+  const bool has_res = tn->convs.count(p + "res") != 0;
+  if (side == nullptr) side = st;
+  if (has_res) {  // the 1x1 residual convolution only reads the block's input: run it next to the main chain
+    if ((rc = order_after(tn, st, side)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, p + "res", B, side)) != ROHM_OK) return rc;
+  }
   if ((rc = run_conv(tn, p + "c1", B, st)) != ROHM_OK) return rc;
   const float* tp = nullptr;
   auto t = tn->tp_off.find(p);
   if (t != tn->tp_off.end()) tp = tn->tp + t->second;
+  if (tp != nullptr && tn->time_pending[branch]) {  // first use of the time projections on this branch
+    ROHM_CUDA(tn->ctx, cudaStreamWaitEvent(st, tn->time_ready, 0));
+    tn->time_pending[branch] = false;
+  }
   if ((rc = run_gn(tn, p + "c1", p + "blocks.0.", y.f32, C, level, B, tp, nullptr, nullptr, &a1, st)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, p + "c2", B, st)) != ROHM_OK) return rc;
   const float* res = identity_res;
-  if (tn->convs.count(p + "res")) {
-    if ((rc = run_conv(tn, p + "res", B, st)) != ROHM_OK) return rc;
+  if (has_res) {
+    if ((rc = order_after(tn, side, st)) != ROHM_OK) return rc;
     res = tn->acts[p + "#res"].f32;
   }
   return run_gn(tn, p + "c2", p + "blocks.1.", y.f32, C, level, B, nullptr, res, extra, out, st);
@@ -547,13 +606,17 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
     const int widths[kLevels] = {m / 8, m / 4, m / 2, m, 2 * m};
     for (int l = 0; l < kLevels; ++l) max_elems = std::max<int64_t>(max_elems, rows_of(tn, l) * widths[l]);
   }
-  tn->scratchY = tn->pool.floats(max_elems);
-  tn->scratchRes = tn->pool.floats(max_elems);
-  tn->scratchA.hi = tn->pool.floats(max_elems);
-  tn->scratchA.lo = tn->pool.floats(max_elems);
+  for (int br = 0; br < 2; ++br) {
+    tn->scratchY[br] = tn->pool.floats(max_elems);
+    tn->scratchRes[br] = tn->pool.floats(max_elems);
+    tn->scratchA[br].hi = tn->pool.floats(max_elems);
+    tn->scratchA[br].lo = tn->pool.floats(max_elems);
+  }
+  if (const char* env = getenv("ROHM_B200_TRAJ_PARALLEL")) tn->parallel = env[0] != '0';
   tn->stats_cap = static_cast<int64_t>(64) * max_batch * kGroups * 2;
   tn->stats_arena = static_cast<double*>(tn->pool.bytes(tn->stats_cap * static_cast<int64_t>(sizeof(double))));
-  if (!tn->scratchY || !tn->scratchRes || !tn->scratchA.hi || !tn->scratchA.lo || !tn->stats_arena) {
+  if (!tn->scratchY[1] || !tn->scratchRes[1] || !tn->scratchA[1].hi || !tn->scratchA[1].lo || !tn->scratchY[0] ||
+      !tn->scratchRes[0] || !tn->scratchA[0].hi || !tn->scratchA[0].lo || !tn->stats_arena) {
     delete tn;
     return fail(ctx, ROHM_ERR_CUDA, "scratch alloc failed");
   }
@@ -638,6 +701,16 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
     if (rc != ROHM_OK) { delete tn; return rc; }
     tn->b3 = dev_copy(tn, p4, td, &rc);
     if (rc != ROHM_OK) { delete tn; return rc; }
+    // tabulate the whole time path for t = 0 .. kTimeTableRows-1 with the direct-evaluation branch of the kernel
+    tn->time_table = tn->pool.floats(static_cast<int64_t>(kTimeTableRows) * total);
+    std::vector<int64_t> ts(kTimeTableRows);
+    for (int i = 0; i < kTimeTableRows; ++i) ts[i] = i;
+    int64_t* d_ts = static_cast<int64_t*>(tn->pool.bytes(sizeof(int64_t) * kTimeTableRows));
+    if (!tn->time_table || !d_ts) { delete tn; return fail(ctx, ROHM_ERR_CUDA, "time table alloc failed"); }
+    cudaMemcpy(d_ts, ts.data(), sizeof(int64_t) * kTimeTableRows, cudaMemcpyHostToDevice);
+    trajnet_time_kernel<<<dim3(kTimeTableRows, 8), 256, sizeof(float) * 6 * td>>>(d_ts, td, tn->w1, tn->b1, tn->w3, tn->b3, tn->wcat,
+                                                                                tn->bcat, total, tn->time_table, nullptr, 0);
+    if (cudaDeviceSynchronize() != cudaSuccess) { delete tn; return fail(ctx, ROHM_ERR_CUDA, "time table build failed"); }
   }
 
   // ---- convolutions ----
@@ -674,7 +747,7 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
   TRY(make_rtb(tn, "diff_dec1.", {A("up1"), A("d1")}, 32, 0));
   {
     Act y;
-    y.f32 = tn->scratchY, y.C = 32, y.ld = 32, y.level = 0;
+    y.f32 = tn->scratchY[0], y.C = 32, y.ld = 32, y.level = 0;
     tn->acts["final#y"] = y;
     TRY(make_conv(tn, "final_c", "diff_final_conv.0.block.0", {A("u1")}, 32, 5, 1, 0, A("final#y"), true));
     TRY(load_norm(tn, "diff_final_conv.0.", 32));
@@ -766,27 +839,37 @@ static int trajnet_forward_launches(rohm_trajnet* tn, const float* x_t, const in
   if ((rc = trajnet_pack(tn, x_t, *A("xin"), B, st)) != ROHM_OK) return rc;
   const int td = tn->time_dim;
   trajnet_time_kernel<<<dim3(B, 8), 256, sizeof(float) * 6 * td, st>>>(time, td, tn->w1, tn->b1, tn->w3, tn->b3, tn->wcat, tn->bcat,
-                                                            tn->tp_total, tn->tp);
+                                                            tn->tp_total, tn->tp, tn->time_table, kTimeTableRows);
   ROHM_CUDA(ctx, cudaGetLastError());
   tn->launches++;
 
+  // Parallel branches (see rohm_trajnet::parallel): sC carries the TrajControl branch, r0 / r1 the residual 1x1 convolutions
+  // (and the odd phases of the transposed convolutions) of the U-Net / TrajControl blocks.
+  tn->ev_next = 0;
+  if (tn->parallel)
+    for (cudaStream_t& q : tn->side)
+      if (q == nullptr) ROHM_CUDA(ctx, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  cudaStream_t sC = (tn->parallel && tn->control) ? tn->side[0] : st;
+  cudaStream_t r0 = tn->parallel ? tn->side[1] : st;
+  cudaStream_t r1 = tn->parallel ? tn->side[2] : sC;
   if (tn->control) {
     const std::string c = "controlnet.";
-    if ((rc = run_rtb(tn, c + "control_enc1.", nullptr, A("k1"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kz1", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kd1", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_rtb(tn, c + "control_enc2.", A("ke1")->f32, A("k2"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kz2", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kd2", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_rtb(tn, c + "control_enc3.", A("ke2")->f32, A("k3"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kz3", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kd3", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_rtb(tn, c + "control_enc4.", A("ke3")->f32, A("k4"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kz4", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kd4", B, st)) != ROHM_OK) return rc;
-    if ((rc = run_rtb(tn, c + "control_mid_block1.", nullptr, A("km1"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_rtb(tn, c + "control_mid_block2.", A("km1")->f32, A("km2"), nullptr, B, st)) != ROHM_OK) return rc;
-    if ((rc = run_conv(tn, "kzm", B, st)) != ROHM_OK) return rc;
+    if ((rc = order_after(tn, st, sC)) != ROHM_OK) return rc;  // fork after pack + time
+    if ((rc = run_rtb(tn, c + "control_enc1.", nullptr, A("k1"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kz1", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kd1", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_rtb(tn, c + "control_enc2.", A("ke1")->f32, A("k2"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kz2", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kd2", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_rtb(tn, c + "control_enc3.", A("ke2")->f32, A("k3"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kz3", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kd3", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_rtb(tn, c + "control_enc4.", A("ke3")->f32, A("k4"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kz4", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kd4", B, sC)) != ROHM_OK) return rc;
+    if ((rc = run_rtb(tn, c + "control_mid_block1.", nullptr, A("km1"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_rtb(tn, c + "control_mid_block2.", A("km1")->f32, A("km2"), nullptr, B, sC, r1, 1)) != ROHM_OK) return rc;
+    if ((rc = run_conv(tn, "kzm", B, sC)) != ROHM_OK) return rc;
   }
   const float* z1 = tn->control ? A("z1")->f32 : nullptr;
   const float* z2 = tn->control ? A("z2")->f32 : nullptr;
@@ -794,28 +877,33 @@ static int trajnet_forward_launches(rohm_trajnet* tn, const float* x_t, const in
   const float* z4 = tn->control ? A("z4")->f32 : nullptr;
   const float* zm = tn->control ? A("zm")->f32 : nullptr;
 
-  if ((rc = run_rtb(tn, "diff_enc1.", nullptr, A("d1"), nullptr, B, st)) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_enc1.", nullptr, A("d1"), nullptr, B, st, r0, 0)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "diff_down1", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_enc2.", A("e1")->f32, A("d2"), nullptr, B, st)) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_enc2.", A("e1")->f32, A("d2"), nullptr, B, st, r0, 0)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "diff_down2", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_enc3.", A("e2")->f32, A("d3"), nullptr, B, st)) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_enc3.", A("e2")->f32, A("d3"), nullptr, B, st, r0, 0)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "diff_down3", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_enc4.", A("e3")->f32, A("d4"), nullptr, B, st)) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_enc4.", A("e3")->f32, A("d4"), nullptr, B, st, r0, 0)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "diff_down4", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_mid_block1.", nullptr, A("m1"), nullptr, B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_mid_block2.", A("m1")->f32, A("m2"), zm, B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up4e", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up4o", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_dec4.", nullptr, A("u4"), z4, B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up3e", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up3o", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_dec3.", nullptr, A("u3"), z3, B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up2e", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up2o", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_dec2.", nullptr, A("u2"), z2, B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up1e", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_conv(tn, "up1o", B, st)) != ROHM_OK) return rc;
-  if ((rc = run_rtb(tn, "diff_dec1.", nullptr, A("u1"), z1, B, st)) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_mid_block1.", nullptr, A("m1"), nullptr, B, st, r0, 0)) != ROHM_OK) return rc;
+  if (tn->control && (rc = order_after(tn, sC, st)) != ROHM_OK) return rc;  // join: the decoder adds the TrajControl residuals
+  if ((rc = run_rtb(tn, "diff_mid_block2.", A("m1")->f32, A("m2"), zm, B, st, r0, 0)) != ROHM_OK) return rc;
+  // ConvTranspose1d = two independent GEMMs (even / odd output frames) with row-interleaved stores
+  auto upsample = [&](const char* even, const char* odd) -> int {
+    int r;
+    if ((r = order_after(tn, st, r0)) != ROHM_OK) return r;
+    if ((r = run_conv(tn, odd, B, r0)) != ROHM_OK) return r;
+    if ((r = run_conv(tn, even, B, st)) != ROHM_OK) return r;
+    return order_after(tn, r0, st);
+  };
+  if ((rc = upsample("up4e", "up4o")) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_dec4.", nullptr, A("u4"), z4, B, st, r0, 0)) != ROHM_OK) return rc;
+  if ((rc = upsample("up3e", "up3o")) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_dec3.", nullptr, A("u3"), z3, B, st, r0, 0)) != ROHM_OK) return rc;
+  if ((rc = upsample("up2e", "up2o")) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_dec2.", nullptr, A("u2"), z2, B, st, r0, 0)) != ROHM_OK) return rc;
+  if ((rc = upsample("up1e", "up1o")) != ROHM_OK) return rc;
+  if ((rc = run_rtb(tn, "diff_dec1.", nullptr, A("u1"), z1, B, st, r0, 0)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "final_c", B, st)) != ROHM_OK) return rc;
   if ((rc = run_gn(tn, "final_c", "diff_final_conv.0.", A("final#y")->f32, 32, 0, B, nullptr, nullptr, nullptr, A("f1"), st)) != ROHM_OK) return rc;
   if ((rc = run_conv(tn, "final_o", B, st)) != ROHM_OK) return rc;
@@ -897,7 +985,7 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
   }
   {
     cudaKernelNodeParams kp = fg->p_time;
-    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 10);
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 12);
     args[0] = &a_t;
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_time, &kp));

@@ -161,6 +161,7 @@ static void case_linear(int M, int N, int K, int block_n, int act, bool with_res
 // middle of the fp16 range, accumulator scaled back in the epilogue.  a_scale stresses the fp16 range of the activations.
 // ------------------------------------------------------------------------------------------------
 #include <cuda_fp16.h>
+static bool g_multicast = false;  // A-operand multicast across CTA pairs (gemm_enable_multicast) in the fp16 cases below
 static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with_res, bool timing, float a_scale,
                             int tma_mode = 0) {
   const int BK = gemm_block_k(kKindF16);
@@ -214,6 +215,10 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
       exit(2);
     }
   }
+  if (g_multicast && gemm_enable_multicast(&p, Ah, Al, M, K, ldk, N, block_n, kKindF16) != 0) {
+    printf("gemm_enable_multicast failed\n");
+    exit(2);
+  }
   CK(cudaMemset(dCh, 0, (size_t)M * N * 2));
   CK(cudaMemset(dCl, 0, (size_t)M * N * 2));
   CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
@@ -239,8 +244,8 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
       if (split_out && tma_mode == 0) maxsplit = std::fmax(maxsplit, std::fabs(pair - got));
     }
   char name[160];
-  snprintf(name, sizeof name, "f16x2 linear M%d N%d K%d bn%d act%d a_scale %g%s", M, N, K, block_n, act, a_scale,
-           tma_mode == 1 ? " [TMA store fp32]" : tma_mode == 2 ? " [TMA store fp16 pair]" : "");
+  snprintf(name, sizeof name, "f16x2 linear M%d N%d K%d bn%d act%d a_scale %g%s%s", M, N, K, block_n, act, a_scale,
+           tma_mode == 1 ? " [TMA store fp32]" : tma_mode == 2 ? " [TMA store fp16 pair]" : "", p.multicast_a ? " [A multicast]" : "");
   report(name, maxerr, maxref, (tma_mode == 2 ? 2.5e-5 : 2e-5) * std::fmax(1.0f, a_scale));
   if (tma_mode == 0) report("  hi+lo == out (fp16 split epilogue)", maxsplit, maxref, 4e-6 * std::fmax(1.0, maxref));
   if (timing) {
@@ -316,6 +321,10 @@ static void make_linear(GemmParams& p, const __half* Ah, const __half* Al, int M
   }
   p.num_segs = 1, p.seg_kblocks[0] = w.Kp / BK, p.seg_row_mul[0] = 1;
   p.M = M, p.N = N, p.out_row_mul = 1, p.acc_scale = 1.0f / w.scale, p.ln_eps = 1e-5f;
+  if (g_multicast && gemm_enable_multicast(&p, Ah, Al, M, K, lda, N, bn, kKindF16) != 0) {
+    printf("gemm_enable_multicast failed (ln)\n");
+    exit(2);
+  }
 }
 static void case_linear_ln(int M, int K, bool timing) {
   const int D = 512, N2 = 1024;
@@ -657,6 +666,17 @@ int main() {
   case_linear_f16(4640, 1024, 512, 128, kActGelu, false, true, 1.0f, 2);
   case_linear_f16(4640, 512, 1024, 128, kActNone, false, true, 1.0f, 1);
   case_linear_f16(4640, 272, 512, 96, kActNone, false, true, 1.0f, 1);
+  // the PoseNet shapes again with the A operand multicast across CTA pairs
+  g_multicast = true;
+  case_linear_f16(4640, 1536, 512, 128, kActNone, false, true, 1.0f, 2);
+  case_linear_f16(4640, 1024, 512, 128, kActGelu, false, true, 1.0f, 2);
+  case_linear_f16(4640, 512, 1024, 128, kActNone, false, true, 1.0f, 1);
+  case_linear_f16(18560, 1536, 512, 128, kActNone, false, true, 1.0f, 2);
+  case_linear_f16(145, 512, 512, 128, kActNone, false, false, 1.0f, 1);
+  case_linear_f16(34, 1536, 512, 128, kActNone, false, false, 1.0f, 2);
+  case_linear_ln(4640, 512, true);
+  case_linear_ln(34, 1024, false);
+  g_multicast = false;
   // fused residual + LayerNorm epilogue: PoseNet out-proj / FFN2 shapes, a one-stripe case and ragged row counts
   case_linear_ln(4640, 512, true);
   case_linear_ln(4640, 1024, true);
