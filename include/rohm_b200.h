@@ -235,6 +235,15 @@ ROHM_API int rohm_body_from_repr_layout(rohm_body* bd, const float* x, int chann
 ROHM_API int rohm_skating_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
                                    float* grad, float* loss_out, void* stream);
 
+/* rohm_skating_guidance in two halves, for clip-sharded runs that reproduce the reference's BATCH-GLOBAL normalisers
+ * (posenet.py:230-233, 242-248): _sums computes this shard's {sum_abs, count_abs, sum_smpl, count_smpl} into sums_out (device
+ * float[4]; per-frame state stays in the handle), the caller all-reduces the four floats over the ranks, _backward produces
+ * this shard's gradient with the global sums.  _sums followed by _backward with the same sums == rohm_skating_guidance. */
+ROHM_API int rohm_skating_guidance_sums(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                        float* sums_out, void* stream);
+ROHM_API int rohm_skating_guidance_backward(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                            const float* sums, float* grad, void* stream);
+
 /* PoseNet.guide_2d_projection_with_smpl(compute_grad='x_0') (model/posenet.py:260-317, utils/other_utils.py:150-185):
  * grad [B,294,1,T] = d(-loss_2d)/d x0, loss_2d = mean over (clip, frame, 10 selected joints, 2) of
  * |perspective_projection(camera <- scene <- canonical joints) - keypoints| * confidence; channels [0,22) and the 4 contact

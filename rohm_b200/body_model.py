@@ -105,6 +105,23 @@ class BodyKernels:
         return (grad, loss) if want_loss else grad
 
 
+    def skating_guidance_global(self, x0, mean, std, reduce_sums):
+        """Skating guidance with batch-GLOBAL loss normalisers in a clip-sharded run: this shard's four loss sums are handed
+        to ``reduce_sums`` (an in-place all-reduce over the ranks: 4 floats, the one optional intra-step collective of the
+        path), then the gradient of this shard is formed with the reduced sums."""
+        B, _, _, T = x0.shape
+        sums = torch.empty(4, device=self.device)
+        rc = self.lib.rohm_skating_guidance_sums(self.handle, C.c_void_p(x0.data_ptr()), C.c_void_p(mean.data_ptr()),
+                                                 C.c_void_p(std.data_ptr()), B, T, C.c_void_p(sums.data_ptr()), self._stream())
+        _lib.check(rc, self.ctx)
+        reduce_sums(sums)
+        grad = torch.empty_like(x0)
+        rc = self.lib.rohm_skating_guidance_backward(self.handle, C.c_void_p(x0.data_ptr()), C.c_void_p(mean.data_ptr()),
+                                                     C.c_void_p(std.data_ptr()), B, T, C.c_void_p(sums.data_ptr()),
+                                                     C.c_void_p(grad.data_ptr()), self._stream())
+        _lib.check(rc, self.ctx)
+        return grad
+
     def projection_guidance(self, x0, mean, std, cam_affine, focal, center, keypoints_2d, want_loss=False):
         """d(-loss_2d)/dx0 of guide_2d_projection_with_smpl (reference posenet.py:260-317): x0 [B,294,1,T] normalised,
         cam_affine [B,3,4] canonical -> camera, focal / center [B,2], keypoints_2d [B,>=T,22,3]."""

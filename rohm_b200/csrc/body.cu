@@ -876,6 +876,47 @@ extern "C" int rohm_body_from_repr_layout(rohm_body* bd, const float* x, int cha
 // trajectory and contact channels zeroed.  If nothing skates the gradient is all zeros (the reference returns a
 // scalar 0 in that case; adding weight*variance*0 is the same update).  loss_out (device float[4], optional) receives
 // {sum_abs, count_abs, sum_smpl, count_smpl}.
+// The two halves of rohm_skating_guidance, for clip-sharded runs that want the reference's batch-global normalisers
+// (posenet.py:230-233, 242-248: loss = sum of masked speeds / number of masked (frame, foot) pairs over the WHOLE batch):
+//   rohm_skating_guidance_sums     forward kinematics of both recovery paths + masked loss sums of THIS shard -> sums[4]
+//                                  = {sum_abs, count_abs, sum_smpl, count_smpl} (device); per-frame state stays in the handle
+//   (caller: all-reduce the 4 floats over the ranks)
+//   rohm_skating_guidance_backward VJP with the given (global) sums -> grad of this shard
+extern "C" int rohm_skating_guidance_sums(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
+                                          float* sums_out, void* stream) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = bd->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
+  const int64_t N = static_cast<int64_t>(B) * T;
+  if (!x0 || !mean || !stdv || !sums_out || B <= 0 || T <= 0 || N > bd->max_frames)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_skating_guidance_sums: bad arguments (B*T=%lld, capacity %lld)",
+                static_cast<long long>(N), static_cast<long long>(bd->max_frames));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GuideWs ws{bd->foot, bd->gdir, sums_out};
+  ROHM_CUDA(ctx, cudaMemsetAsync(sums_out, 0, 4 * sizeof(float), st));
+  const unsigned blocks = static_cast<unsigned>((N + 127) / 128);
+  guide_forward_kernel<<<blocks, 128, 0, st>>>(x0, mean, stdv, bd->Jt, bd->Jd, B, T, ws);
+  guide_loss_kernel<<<blocks, 128, 0, st>>>(x0, mean, stdv, B, T, ws);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  return ROHM_OK;
+}
+
+extern "C" int rohm_skating_guidance_backward(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B,
+                                              int T, const float* sums, float* grad, void* stream) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  rohm_ctx* ctx = bd->ctx;
+  rohm::DeviceGuard device_guard__(ctx);
+  const int64_t N = static_cast<int64_t>(B) * T;
+  if (!x0 || !mean || !stdv || !sums || !grad || B <= 0 || T <= 0 || N > bd->max_frames)
+    return fail(ctx, ROHM_ERR_INVALID, "rohm_skating_guidance_backward: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GuideWs ws{bd->foot, bd->gdir, const_cast<float*>(sums)};
+  ROHM_CUDA(ctx, cudaMemsetAsync(grad, 0, sizeof(float) * N * kC, st));
+  guide_backward_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(x0, mean, stdv, bd->Jt, bd->Jd, B, T, ws, grad);
+  ROHM_CUDA(ctx, cudaGetLastError());
+  return ROHM_OK;
+}
+
 extern "C" int rohm_skating_guidance(rohm_body* bd, const float* x0, const float* mean, const float* stdv, int B, int T,
                                      float* grad, float* loss_out, void* stream) {
   if (bd == nullptr) return ROHM_ERR_INVALID;

@@ -127,6 +127,65 @@ def ddim_step(x0, x_t, noise, coefs):
 # ---------------------------------------------------------------------------------------------------------------
 # torch.library registration (torch.ops.rohm.*)
 # ---------------------------------------------------------------------------------------------------------------
+# Engine objects (PoseNetEngine / TrajNetEngine / BodyKernels: one C handle + workspace each) are addressed by an integer
+# key, so the denoiser and body-model entry points are ordinary tensor-in / tensor-out custom ops as well.
+_engines = {}
+
+
+def register_engine(engine):
+    import weakref
+    key = id(engine)
+    _engines[key] = weakref.ref(engine)  # weak: the registry must not keep a replaced engine (and its device memory) alive
+    return key
+
+
+def unregister_engine(key):
+    _engines.pop(key, None)
+
+
+def _engine(key):
+    ref = _engines.get(int(key))
+    e = ref() if ref is not None else None
+    if e is None:
+        raise RohmB200Error(f"torch.ops.rohm: unknown engine key {key} (engine destroyed?)")
+    return e
+
+
+try:
+    @torch.library.custom_op("rohm::posenet_forward", mutates_args=(), device_types="cuda")
+    def _posenet_forward_op(engine: int, x_t: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        return _engine(engine)._forward_impl(x_t, timesteps)
+
+    @_posenet_forward_op.register_fake
+    def _(engine, x_t, timesteps):
+        return torch.empty_like(x_t)
+
+    @torch.library.custom_op("rohm::trajnet_forward", mutates_args=(), device_types="cuda")
+    def _trajnet_forward_op(engine: int, x_t: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        return _engine(engine)._forward_impl(x_t, time)
+
+    @_trajnet_forward_op.register_fake
+    def _(engine, x_t, time):
+        return torch.empty_like(x_t)
+
+    @torch.library.custom_op("rohm::skating_guidance", mutates_args=(), device_types="cuda")
+    def _skating_guidance_op(engine: int, x0: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+        return _engine(engine).skating_guidance(x0, mean, std)
+
+    @_skating_guidance_op.register_fake
+    def _(engine, x0, mean, std):
+        return torch.empty_like(x0)
+
+    @torch.library.custom_op("rohm::ddpm_step_philox", mutates_args=(), device_types="cuda")
+    def _ddpm_step_philox_op(x0: torch.Tensor, x_t: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+        return ddpm_step_philox(x0, x_t, coef)
+
+    @_ddpm_step_philox_op.register_fake
+    def _(x0, x_t, coef):
+        return torch.empty_like(x0)
+except Exception:  # pragma: no cover
+    pass
+
 try:
     @torch.library.custom_op("rohm::ddpm_step", mutates_args=(), device_types="cuda")
     def _ddpm_step_op(x0: torch.Tensor, x_t: torch.Tensor, noise: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:

@@ -70,6 +70,19 @@ def gather_clips(local_out, n_clips, group=None):
     return torch.cat([buf[r * mx: r * mx + sizes[r]] for r in range(world)], dim=0)
 
 
+def global_guidance(model, group=None, enable=True):
+    """Guidance normalisers of a clip-sharded run.  Default contract (enable=False): each shard equals the reference run on
+    that sub-batch.  enable=True: the skating loss is normalised by the batch-wide counts as in an unsharded reference run --
+    one 4-float all-reduce per guided step (the only intra-step collective of the path; <= 51 of 1000 steps), which makes the
+    gathered result reproduce the single-GPU run on the whole batch."""
+    if not enable:
+        if hasattr(model, "guidance_sum_reducer"):
+            del model.guidance_sum_reducer
+        return model
+    model.guidance_sum_reducer = lambda sums: dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return model
+
+
 def sample_sharded(diffusion, model, batch, shape, parity_noise=True, group=None, **eval_kwargs):
     """eval_losses on this rank's shard + the final all-gather.  `batch` and `shape` describe the GLOBAL batch."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)

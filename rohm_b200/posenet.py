@@ -87,9 +87,16 @@ class PoseNetEngine:
         # allocator cannot hand its address to a different tensor while it is cached) plus its version counter
         self.cond_ref = None
         self.cond_version = -1
+        from . import ops
+        self.op_key = ops.register_engine(self)
 
     def __del__(self):
         h = getattr(self, "handle", None)
+        try:
+            from . import ops
+            ops.unregister_engine(getattr(self, "op_key", 0))
+        except Exception:
+            pass
         if h:
             try:
                 self.lib.rohm_posenet_destroy(h)
@@ -106,6 +113,12 @@ class PoseNetEngine:
         _lib.check(rc, self.ctx)
 
     def forward(self, x_t, timesteps, out=None):
+        """The denoiser call, through the custom op torch.ops.rohm.posenet_forward (an explicit `out` skips the op layer)."""
+        if out is None:
+            return torch.ops.rohm.posenet_forward(self.op_key, x_t, timesteps)
+        return self._forward_impl(x_t, timesteps, out)
+
+    def _forward_impl(self, x_t, timesteps, out=None):
         B, _, _, T = x_t.shape
         if out is None:
             out = torch.empty_like(x_t)
@@ -313,6 +326,11 @@ class PoseNet(nn.Module):
         B, _, _, T = x.shape
         mean, std = self._norm_stats(x.device)
         k = kernels_for(self.smplx_model, x.device, B * T, with_vertices=False)
+        reducer = getattr(self, "guidance_sum_reducer", None)
+        if reducer is not None:
+            # clip-sharded run reproducing the unsharded batch: the loss normalisers are batch-wide counts (reference
+            # posenet.py:230-233), so the four sums are all-reduced over the ranks (rohm_b200.parallel.global_guidance)
+            return k.skating_guidance_global(x, mean, std, reducer)
         return k.skating_guidance(x, mean, std)
 
     def _camera_affine(self, batch, device):

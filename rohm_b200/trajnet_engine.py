@@ -32,10 +32,17 @@ class TrajNetEngine:
         self.cond_ref, self.cond_version = None, -1
         self.control_ref, self.control_version = None, -1
         self.cond_B = -1
+        from . import ops
+        self.op_key = ops.register_engine(self)
         del sd
 
     def __del__(self):
         h = getattr(self, "handle", None)
+        try:
+            from . import ops
+            ops.unregister_engine(getattr(self, "op_key", 0))
+        except Exception:
+            pass
         if h:
             try:
                 self.lib.rohm_trajnet_destroy(h)
@@ -53,6 +60,10 @@ class TrajNetEngine:
         _lib.check(rc, self.ctx)
 
     def forward(self, x_t, time):
+        """The denoiser call, through the custom op torch.ops.rohm.trajnet_forward."""
+        return torch.ops.rohm.trajnet_forward(self.op_key, x_t, time)
+
+    def _forward_impl(self, x_t, time):
         out = torch.empty_like(x_t)
         rc = self.lib.rohm_trajnet_forward(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(time.data_ptr()),
                                            C.c_void_p(out.data_ptr()), x_t.shape[0], self._stream())

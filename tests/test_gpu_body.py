@@ -159,3 +159,35 @@ def test_full_lbs_throughput_shape(body, cuda_device):
     idx = torch.tensor([0, 1000, N - 1])
     j, v = ko.smplx_forward(model, go[idx], bp[idx], be[idx], tr[idx], return_verts=True, dtype=torch.float64)
     assert float((out.vertices[idx.to(cuda_device)].cpu().double() - v).abs().max()) < 5e-5
+
+
+def test_global_guidance_mode_reproduces_the_unsharded_gradient(cuda_device):
+    """Clip-sharded guidance with batch-GLOBAL normalisers (the 4-float all-reduce of rohm_b200.parallel.global_guidance,
+    emulated here by adding the other shard's sums): the concatenated shard gradients equal the unsharded gradient, while the
+    default per-shard normalisation does not."""
+    B, T = 6, 40
+    ds, x = _motion(B, T, 11)
+    m, _ = _posenet(cuda_device, ds)
+    bm = m.smplx_model
+    mean, std = torch.from_numpy(ds.Mean).to(cuda_device), torch.from_numpy(ds.Std).to(cuda_device)
+    xg = x.to(cuda_device)
+    full = kernels_for(bm, cuda_device, B * T, with_vertices=False).skating_guidance(xg, mean, std)
+    halves = [xg[:2].contiguous(), xg[2:].contiguous()]  # ragged shards: 2 + 4 clips
+    k = kernels_for(bm, cuda_device, B * T, with_vertices=False)
+    local = []
+    for h in halves:  # pass 1: every shard's own sums
+        rec = {}
+        k.skating_guidance_global(h, mean, std, lambda s, rec=rec: rec.setdefault("s", s.clone()))
+        local.append(rec["s"])
+    total = local[0] + local[1]
+    grads = [k.skating_guidance_global(h, mean, std, lambda s: s.copy_(total)) for h in halves]
+    got = torch.cat(grads, dim=0)
+    scale = float(full.abs().max())
+    assert scale > 0 and float((got - full).abs().max()) < 1e-5 * scale
+    per_shard = torch.cat([k.skating_guidance(h, mean, std) for h in halves], dim=0)
+    assert float((per_shard - full).abs().max()) > 1e-2 * scale  # the default contract is per-shard semantics
+    # and through the model hook
+    m.guidance_sum_reducer = lambda s: s.copy_(total)
+    g2 = m.guide_skating_with_smpl({}, {'pred_xstart': halves[1]}, None, compute_grad='x_0')
+    del m.guidance_sum_reducer
+    assert torch.equal(g2, grads[1])

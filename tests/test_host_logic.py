@@ -230,3 +230,28 @@ def test_sampler_guards_fire_before_any_denoiser_call():
     for kw in (dict(cond_fn_with_grad=True, grad_type='amass'), dict(early_stop=True)):
         with pytest.raises(RohmB200Error):
             d.eval_losses(model=Boom(), batch={}, shape=[1, 294, 1, 8], timestep_respacing='ddim10', compute_loss=False, **kw)
+
+
+def test_dropin_motion_representation_keeps_the_reference_symbols(tmp_path):
+    """dropin/data_loaders/motion_representation.py shadows only recover_from_repr_smpl; every other symbol of the
+    reference's module (found further down sys.path) is re-exported, and data_loaders.common still resolves to the reference
+    tree (namespace-package merge).  A stand-in 'reference' tree is used: the real one is not on the GPU box."""
+    ref = tmp_path / "ref"
+    (ref / "data_loaders" / "common").mkdir(parents=True)
+    (ref / "data_loaders" / "common" / "__init__.py").write_text("")
+    (ref / "data_loaders" / "common" / "quaternion.py").write_text("def qinv(q):\n    return 'ref-qinv'\n")
+    (ref / "data_loaders" / "motion_representation.py").write_text(
+        "from data_loaders.common.quaternion import *\n"
+        "def get_repr_smplx(*a, **k):\n    return 'ref-get_repr'\n"
+        "def recover_from_repr_smpl(data_dict, recover_mode='joint_abs_traj', smplx_model=None, return_verts=False,"
+        " return_full_joints=False):\n    return 'ref-recover'\n")
+    dropin = os.path.join(ROOT, "rohm_b200", "dropin")
+    code = ("import sys; sys.path[:0] = [%r, %r, %r];"
+            "import torch;"
+            "from data_loaders.motion_representation import *;"
+            "import data_loaders.motion_representation as mr, data_loaders.common.quaternion as q;"
+            "assert 'dropin' in mr.__file__ and get_repr_smplx() == 'ref-get_repr' and qinv(0) == 'ref-qinv';"
+            "assert recover_from_repr_smpl({'a': torch.zeros(1, 2, 1)}) == 'ref-recover';"  # CPU tensors: the reference's own code
+            "print('ok')") % (dropin, ROOT, str(ref))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

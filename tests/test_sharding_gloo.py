@@ -66,3 +66,36 @@ def test_two_rank_sharded_run_equals_single_process(n_clips):
         p.join(120)
         assert p.exitcode == 0
     assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_guidance(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class M:  # the attribute protocol PoseNet.guide_skating_with_smpl reads
+            pass
+
+        m = parallel.global_guidance(M())
+        sums = torch.tensor([1.0 + rank, 10.0 * (rank + 1), 0.5, 2.0])  # this shard's {sum_abs, cnt_abs, sum_smpl, cnt_smpl}
+        m.guidance_sum_reducer(sums)
+        ok = torch.equal(sums, torch.tensor([3.0, 30.0, 1.0, 4.0]))
+        parallel.global_guidance(m, enable=False)
+        ret[rank] = bool(ok) and not hasattr(m, "guidance_sum_reducer")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_guidance_reducer_sums_the_shard_statistics():
+    """The optional exact-global guidance mode: the four loss sums of every shard are all-reduced (one 4-float collective
+    per guided step), so the batch-wide normalisers of an unsharded reference run are reproduced."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [mp.get_context("spawn").Process(target=_worker_guidance, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: True, 1: True}
