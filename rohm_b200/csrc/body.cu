@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "common.h"
 #include "gemm.cuh"
@@ -692,13 +693,13 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
       const long v = atol(env);
       if (v >= 128 && v % 128 == 0) bd->chunk = v;
     }
-    bd->vposed_stride = std::min<int64_t>(F, bd->chunk) * round_up(V * 3, 128);
+    bd->vposed_stride = std::min<int64_t>(F, bd->chunk) * round_up(V * 3, 384);
     bd->vposed = bd->pool.floats(2 * bd->vposed_stride);
     bd->bone_idx = static_cast<int*>(bd->pool.bytes(static_cast<int64_t>(V) * kMaxBones * sizeof(int)));
     bd->bone_w = bd->pool.floats(static_cast<int64_t>(V) * kMaxBones);
     bd->lbs_w_copy = bd->pool.floats(static_cast<int64_t>(V) * kJ);
     bd->blend.N = V * 3, bd->blend.K = kBlendK, bd->blend.Kp = kBlendK, bd->blend.block_n = 128;
-    bd->blend.Np = static_cast<int>(round_up(V * 3, 128));
+    bd->blend.Np = static_cast<int>(round_up(V * 3, 384));  // whole 128-column (two-kernel path) and 96-column (fused path) tiles
     bd->blend.hi = bd->pool.floats(static_cast<int64_t>(bd->blend.Np) * kBlendK);
     bd->blend.lo = bd->pool.floats(static_cast<int64_t>(bd->blend.Np) * kBlendK);
     ok = bd->A && bd->feat_h && bd->feat_l && bd->vposed && bd->bone_idx && bd->bone_w && bd->lbs_w_copy && bd->blend.hi &&
@@ -759,6 +760,63 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
       delete bd;
       return fail(ctx, ROHM_ERR_CUDA, "rohm_body_create: store tensor map failed");
     }
+    // ---- fused LBS tables: per 32-vertex column tile the bones it touches and the dense [bone][vertex] weights ----
+    {
+      const char* env = getenv("ROHM_B200_FUSED_LBS");
+      bool want = bd->kind == kKindF16 && !(env != nullptr && env[0] == '0');
+      const int tiles = bd->blend.Np / 96;  // column tiles of the fused launch (those past the last vertex touch no bone)
+      std::vector<float> hw;
+      std::vector<int> h_nb(tiles, 0), h_bone(static_cast<size_t>(tiles) * kSkinTileBones, 0);
+      std::vector<float> h_w(static_cast<size_t>(tiles) * kSkinTileBones * 32, 0.0f);
+      if (want) {
+        hw.resize(static_cast<size_t>(V) * kJ);
+        want = cudaMemcpy(hw.data(), lbs_weights, sizeof(float) * hw.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+      for (int t = 0; t < tiles && want; ++t) {
+        int slot_of[kJ];
+        for (int j = 0; j < kJ; ++j) slot_of[j] = -1;
+        for (int vl = 0; vl < 32 && want; ++vl) {
+          const int v = t * 32 + vl;
+          if (v >= V) break;
+          for (int j = 0; j < kJ; ++j) {
+            const float w = hw[static_cast<size_t>(v) * kJ + j];
+            if (w == 0.0f) continue;
+            if (slot_of[j] < 0) {
+              if (h_nb[t] == kSkinTileBones) {
+                want = false;  // more distinct bones than the epilogue's table holds: keep the two-kernel path
+                break;
+              }
+              slot_of[j] = h_nb[t];
+              h_bone[static_cast<size_t>(t) * kSkinTileBones + h_nb[t]++] = j;
+            }
+            h_w[(static_cast<size_t>(t) * kSkinTileBones + slot_of[j]) * 32 + vl] = w;
+          }
+        }
+      }
+      if (want) {
+        bd->skin_nb = static_cast<int*>(bd->pool.bytes(sizeof(int) * h_nb.size()));
+        bd->skin_bone = static_cast<int*>(bd->pool.bytes(sizeof(int) * h_bone.size()));
+        bd->skin_w = bd->pool.floats(static_cast<int64_t>(h_w.size()));
+        want = bd->skin_nb && bd->skin_bone && bd->skin_w &&
+               cudaMemcpy(bd->skin_nb, h_nb.data(), sizeof(int) * h_nb.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(bd->skin_bone, h_bone.data(), sizeof(int) * h_bone.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(bd->skin_w, h_w.data(), sizeof(float) * h_w.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+      }
+      if (want) {
+        GemmParams& k = bd->g_skin;
+        k = GemmParams{};
+        int rs = make_tmap_2d(&k.a_hi[0], bd->feat_h, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
+        rs |= make_tmap_2d(&k.a_lo[0], bd->feat_l, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
+        rs |= make_tmap_2d(&k.b_hi, bd->blend.hi, bd->blend.Np, kBlendK, kBlendK, 96, 1, bd->kind);
+        rs |= make_tmap_2d(&k.b_lo, bd->blend.lo, bd->blend.Np, kBlendK, kBlendK, 96, 1, bd->kind);
+        k.num_segs = 1, k.seg_kblocks[0] = kBlendK / gemm_block_k(bd->kind), k.seg_row_mul[0] = 1;
+        k.acc_scale = 1.0f / bd->blend.scale;
+        k.ldo = V * 3, k.N = V * 3, k.out_row_mul = 1;
+        k.skin_A = bd->A, k.skin_nb = bd->skin_nb, k.skin_bone = bd->skin_bone, k.skin_w = bd->skin_w;
+        want = rs == 0 && bd->blend.Np % 96 == 0;
+      }
+      bd->fused_lbs = want;
+    }
     bool ev_ok = cudaStreamCreateWithFlags(&bd->skin_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ev_ok; ++i)
       ev_ok = cudaEventCreateWithFlags(&bd->gemm_done[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -801,7 +859,13 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
       global_orient, body_pose, betas, transl, bd->Jt, bd->Jd, static_cast<int>(N), joints, num_joints,
       verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr, bd->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(ctx, cudaGetLastError());
-  if (verts) {
+  if (verts && bd->fused_lbs) {
+    // one launch: blend GEMM with the skinning epilogue (gemm.cu, EPI 4); v_posed stays in TMEM / registers
+    GemmParams g = bd->g_skin;
+    g.M = static_cast<int>(N);
+    g.out = vertices;
+    ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 96, bd->passes, st, false, bd->kind));
+  } else if (verts) {
     // Pipeline over chunks of kLbsChunk frames: blend GEMM of chunk i on the caller's stream into v_posed buffer i % 2,
     // skinning of chunk i on a second stream (HBM-bound next to the tensor-bound GEMM of chunk i + 1).
     const int vblocks = (bd->V + 255) / 256;

@@ -25,6 +25,14 @@ struct rohm_body {
   float* jwork = nullptr;          // [max_frames, 22, 3] scratch joints (glue)
   float* gwork = nullptr;          // [max_frames, 22, 3] scratch joint gradients (2-D guidance)
   rohm::GemmParams g_blend{};
+  // fused LBS (blend GEMM with the skinning epilogue, gemm.cuh: GemmParams::skin_A): one launch, v_posed never leaves the SM.
+  // Needs fp16 pairs and at most kSkinTileBones distinct bones per 32 consecutive vertices; ROHM_B200_FUSED_LBS=0 keeps the
+  // two-kernel path (blend GEMM -> v_posed -> skin_kernel), which is also the fallback.
+  rohm::GemmParams g_skin{};
+  bool fused_lbs = false;
+  int* skin_nb = nullptr;
+  int* skin_bone = nullptr;
+  float* skin_w = nullptr;
   // full LBS pipeline: v_posed double buffer (one chunk each), second stream for the skinning kernels
   int64_t vposed_stride = 0;
   // frames per chunk.  Measured on B200 (32 x 143 frames): chunking v_posed through L2 (384-frame chunks, with or without the

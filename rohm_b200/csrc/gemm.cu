@@ -16,6 +16,10 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSmemBudget = 192 * 1024;  // operand ring budget (BLOCK_N = 128, PASSES = 3: 6 x 32 KB or 3 x 64 KB)
 constexpr int kEpiTileFloats = 32 * 32;   // per-epilogue-warp staging tile (32 x 32, XOR-swizzled columns): coalesced stores
+// fused skinning epilogue (EPI 4): one 128 x 96 fp32 staging tile for the whole CTA, pitch 97 floats (conflict-free both for the
+// row-per-thread writes and the row-contiguous reads)
+constexpr int kSkinPitch = 97;
+constexpr int kSkinStageBytes = kGemmBlockM * kSkinPitch * 4;
 
 template <int BLOCK_N, int PASSES>
 struct TileCfg {
@@ -62,34 +66,25 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// Exact (erf) GELU, nn.GELU's default, without erff's data-dependent branches: both erf branches are evaluated for every
-// element (|z| < 1: z + z P(z^2); otherwise sign(z) (1 - exp(Q(min(|z|, 4))))) and selected, so the 32 independent
-// elements of an epilogue chunk interleave freely.  Coefficients: tools/fit_gelu_erf.py (least squares on Chebyshev
-// nodes); max |error| of the whole GELU against float64 3.0e-7, the same as the fp32 erff formulation (4.5e-7).
+// Exact (erf) GELU, nn.GELU's default, as x Phi(x) = max(x, 0) - |x| Phi(-|x|) with Phi(-u) = 2^Q(u): one degree-8
+// polynomial in u = min(|x|, 6.5), one MUFU.EX2, no erf branches -- 12 instructions per element (the two-branch erf form
+// it replaces took 28, and the FFN1 epilogue is bound by the FP32 pipe).  Only the absolute error of |x| Phi(-|x|) matters,
+// so Q is a least-squares fit of log2 Phi(-u) weighted by u Phi(-u) (tools/fit_gelu_erf.py); max |error| of the whole GELU
+// against float64: 2.5e-7, i.e. the rounding of the result (the fp32 erff formulation: 4.5e-7).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float s = z * z;
-  float r = 7.680843555e-05f;
-  r = fmaf(r, s, -7.953780587e-04f);
-  r = fmaf(r, s, 5.181253888e-03f);
-  r = fmaf(r, s, -2.684955671e-02f);
-  r = fmaf(r, s, 1.128346100e-01f);
-  r = fmaf(r, s, -3.761261106e-01f);
-  r = fmaf(r, s, 1.283791661e-01f);
-  const float e_small = fmaf(r, z, z);
-  const float t = fminf(fabsf(z), 4.0f);
-  float q = -2.117903023e-05f;
-  q = fmaf(q, t, 4.352589312e-04f);
-  q = fmaf(q, t, -4.174096975e-03f);
-  q = fmaf(q, t, 2.512531355e-02f);
-  q = fmaf(q, t, -1.082860529e-01f);
-  q = fmaf(q, t, -6.333442330e-01f);
-  q = fmaf(q, t, -1.129514933e+00f);
-  q = fmaf(q, t, 1.744384354e-04f);
-  const float e_large = copysignf(1.0f - __expf(q), z);
-  const float e = fabsf(z) < 1.0f ? e_small : e_large;
-  const float h = 0.5f * x;
-  return fmaf(h, e, h);
+  const float u = fminf(fabsf(x), 6.5f);
+  float q = -1.657032612e-06f;
+  q = fmaf(q, u, 2.461445729e-05f);
+  q = fmaf(q, u, -1.118122309e-04f);
+  q = fmaf(q, u, -3.311361652e-04f);
+  q = fmaf(q, u, 7.346248254e-03f);
+  q = fmaf(q, u, -5.272617936e-02f);
+  q = fmaf(q, u, -4.591094553e-01f);
+  q = fmaf(q, u, -1.151124716e+00f);
+  q = fmaf(q, u, -9.999987483e-01f);
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(q));
+  return fmaf(-fabsf(x), p, fmaxf(x, 0.0f));
 }
 
 struct EpiParams {
@@ -202,7 +197,7 @@ __device__ __forceinline__ void stage_pair_chunk(const float (&v)[32], uint8_t* 
 // epilogue is ~7000 SASS instructions, most of them predicated-off activation code when unused).
 template <int BLOCK_N, int PASSES, int EPI, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
-  constexpr bool LEAN = EPI != 2;
+  constexpr bool LEAN = EPI != 2;  // EPI: 0 bias / stores, 1 + exact GELU, 2 everything (TrajNet), 3 LayerNorm-folding producer, 4 skinning
   constexpr int kElemK = gemm_block_k(KIND);  // K elements per pipeline stage (TMA coordinates are in elements)  // EPI: 0 = bias/residual/stores, 1 = the same + exact GELU, 2 = everything
   using Cfg = TileCfg<BLOCK_N, PASSES>;
   extern __shared__ uint8_t smem_raw[];
@@ -220,6 +215,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   __shared__ __align__(16) float corr_s[BLOCK_N];
   __shared__ __align__(16) float beta_s[EPI == 3 ? BLOCK_N : 4];
   __shared__ uint64_t res_bar[EPI == 3 ? kEpiWarps : 1];  // EPI 3: one transaction barrier per epilogue warp (residual tile loads)
+  // EPI 4 (skinning): the current column tile's bone list and dense [bone][vertex] weights
+  __shared__ __align__(16) float skin_w_s[EPI == 4 ? kSkinTileBones * 32 : 4];
+  __shared__ int skin_bone_s[EPI == 4 ? kSkinTileBones : 1];
+  __shared__ int skin_nb_s;
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -285,6 +284,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   // prologue then overlaps this kernel's tail; it blocks in its own griddepcontrol.wait until this grid has completed
   // and flushed), then order everything below after the previous kernel.
   ptx::pdl_launch_dependents();
+  // The B operand is a weight matrix that no kernel of the chain writes: the producer thread puts the B tiles of the first
+  // pipeline stages in flight BEFORE it waits for the previous grid, so the pipeline fill (~1 us) overlaps that grid's tail.
+  int prefetched = 0;
+  if (warp_idx == 0 && lane == 0 && !p.multicast_a && static_cast<int>(blockIdx.x) < num_tiles) {
+    const int n0 = (static_cast<int>(blockIdx.x) % tiles_n) * BLOCK_N;
+    prefetched = total_iters < Cfg::kStages ? total_iters : Cfg::kStages;
+    for (int i = 0; i < prefetched; ++i) {
+      uint8_t* st = smem + i * Cfg::kStageBytes;
+      ptx::mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+      ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[i], i * kElemK, n0);
+      if (PASSES == 3) ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[i], i * kElemK, n0);
+    }
+  }
   ptx::pdl_wait_prior_grid();
 
   if (warp_idx == 0) {
@@ -300,9 +312,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
           const int nkb = p.seg_kblocks[s];
           for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kElemK) {
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            if (it < prefetched) {  // B of this stage is already in flight (see above): only A is missing
+              if (it == 0) stamp(p, 2);
+              ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kElemK, row);
+              if (PASSES == 3) ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kElemK, row);
+              if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+              continue;
+            }
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (it == 0) stamp(p, 2);
-            uint8_t* st = smem + stage * Cfg::kStageBytes;
             ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             if (PASSES == 3 && p.multicast_a) {
               // my half of the stripe's A tile goes to both CTAs of the pair (the partner sends the other half)
@@ -382,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         ptx::mma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
         if (tcount == 0) stamp(p, 4);
         stamp(p, 12);  // last write wins: all MMAs of this CTA issued
+        if (tcount < 8) stamp(p, 16 + tcount);
       }
     }
   } else {
@@ -428,6 +448,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           } else {
             corr_s[i] = (e.a_stats != nullptr && col_ok) ? __ldg(e.a_corr + n0 + i) : 0.0f;
           }
+        }
+        if constexpr (EPI == 4) {
+          const int tile_n = tile_idx % tiles_n;
+          const float* wsrc = p.skin_w + static_cast<int64_t>(tile_n) * (kSkinTileBones * 32);
+          skin_w_s[i] = __ldg(wsrc + i), skin_w_s[i + 256] = __ldg(wsrc + i + 256);
+          if (i < kSkinTileBones) skin_bone_s[i] = __ldg(p.skin_bone + tile_n * kSkinTileBones + i);
+          if (i == 0) skin_nb_s = __ldg(p.skin_nb + tile_n);
         }
         if (e.residual != nullptr && row_ok) {
           const float* r = e.residual + orow * e.ldr + n0 + half * 32;
@@ -487,6 +514,76 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 5);
       ptx::tc_fence_after_sync();
+
+      if constexpr (EPI == 4) {
+        // ===== linear-blend skinning of the accumulator tile: thread = frame m, 16 of the tile's 32 vertices =====
+        static_assert(BLOCK_N == 96 && PASSES == 3 && KIND == kKindF16, "skinning epilogue: 32 vertices x 3 per tile, fp16 pairs");
+        float vp[48];
+        {
+          uint32_t a0[32], a1[16], c0[32], c1[16];
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
+                                 (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(48 * half);
+          ptx::tmem_ld_32x32(taddr, a0);
+          ptx::tmem_ld_32x16(taddr + 32, a1);
+          ptx::tmem_ld_32x32(taddr + BLOCK_N, c0);
+          ptx::tmem_ld_32x16(taddr + BLOCK_N + 32, c1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vp[j] = (__uint_as_float(a0[j]) + __uint_as_float(c0[j])) * e.acc_scale;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vp[32 + j] = (__uint_as_float(a1[j]) + __uint_as_float(c1[j])) * e.acc_scale;
+        }
+        // the accumulator is drained: the MMA warp may start the tile after next
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+        float o[48];
+#pragma unroll
+        for (int j = 0; j < 48; ++j) o[j] = 0.0f;
+        const int nb = skin_nb_s;
+        const float* arow = p.skin_A + static_cast<int64_t>(row_ok ? m : 0) * (55 * 12);
+        for (int b = 0; b < nb; ++b) {
+          const float4* a = reinterpret_cast<const float4*>(arow + skin_bone_s[b] * 12);
+          const float4 r0 = __ldg(a), r1 = __ldg(a + 1), r2 = __ldg(a + 2);
+          const float* wrow = &skin_w_s[b * 32 + 16 * half];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float w = wrow[j];  // the same for every lane: the branch below is warp-uniform
+            if (w != 0.0f) {
+              const float x = vp[3 * j], y = vp[3 * j + 1], z = vp[3 * j + 2];
+              o[3 * j] = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[3 * j]);
+              o[3 * j + 1] = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[3 * j + 1]);
+              o[3 * j + 2] = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[3 * j + 2]);
+            }
+          }
+        }
+        // transpose through the CTA-wide staging tile: the output row pitch (3 V floats) is not a multiple of 16 bytes, so
+        // neither TMA nor vector stores apply; lanes along the columns give fully coalesced 4-byte stores
+        float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+        {
+          float* srow = stg + (q * 32 + lane) * kSkinPitch + 48 * half;
+#pragma unroll
+          for (int j = 0; j < 48; ++j) srow[j] = o[j];
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32));
+        {
+          const int w8 = warp_idx - 2;
+#pragma unroll 4
+          for (int rr = 0; rr < kGemmBlockM / kEpiWarps; ++rr) {
+            const int r = w8 * (kGemmBlockM / kEpiWarps) + rr;
+            const int mr = m0 + r;
+            if (mr >= e.M) break;
+            float* dst = e.out + static_cast<int64_t>(mr) * e.ldo + n0;
+            const float* src = stg + r * kSkinPitch;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int col = lane + 32 * c;
+              if (n0 + col < e.N) __stcs(dst + col, src[col]);
+            }
+          }
+        }
+        continue;  // the bar.sync 1 at the top of the next tile keeps the staging tile intact until every row is stored
+      }
 
       if constexpr (EPI == 3) {
         // ===== u = LN_prev(residual) + acc * 2^-s + bias, written in place as an fp16 pair + per-row partial statistics =====
@@ -559,6 +656,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (e.tma_store && full && (m0 + q * 32 + 32 <= e.M)) {
           // ---- TMA-store path: row-per-thread registers -> swizzled staging tile -> bulk tensor store ----
           ptx::tmem_ld_wait();
+          if (p.debug_flags & 1) continue;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -634,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           }
           ptx::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.debug_flags & 2)) {
             if (e.out != nullptr) {
               ptx::tma_store_2d(&p.st_out, tb, nb, m0 + q * 32);
             } else {
@@ -888,6 +986,24 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
       return cudaErrorInvalidValue;
     }
   }
+  int smem_bytes = Cfg::kSmemBytes;
+  if (p.skin_A != nullptr) {
+    if constexpr (BLOCK_N == 96 && PASSES == 3 && KIND == kKindF16) {
+      if (!plain || p.act != kActNone || p.out == nullptr || p.skin_nb == nullptr || p.skin_bone == nullptr || p.skin_w == nullptr ||
+          p.bias != nullptr || p.residual != nullptr || p.a_stats != nullptr || p.stats_out != nullptr || p.multicast_a)
+        return cudaErrorInvalidValue;
+      kern = gemm_tile_kernel<BLOCK_N, PASSES, 4, KIND>;
+      smem_bytes = Cfg::kStages * Cfg::kStageBytes + 1024 + kSkinStageBytes;
+      static bool skin_attr_set = false;
+      if (!skin_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        skin_attr_set = true;
+      }
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {  // normally done up front by gemm_init_attributes(); kept for stand-alone users of launch_gemm
     cudaError_t e = set_attr<BLOCK_N, PASSES, KIND>();
@@ -912,7 +1028,7 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   if (q.multicast_a) grid -= grid % 2;  // pairs: tiles 2j, 2j+1 of a round are neighbouring column tiles of one stripe
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;

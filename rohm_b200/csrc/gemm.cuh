@@ -26,6 +26,7 @@
 
 namespace rohm {
 
+constexpr int kSkinTileBones = 16;  // most distinct bones a 32-vertex column tile may touch (fused skinning epilogue)
 constexpr int kGemmBlockM = 128;
 // K extent of one pipeline stage in fp32 elements: 32 = 128-byte rows (SWIZZLE_128B), 64 KB stages, 3 in flight;
 // 16 = 64-byte rows (SWIZZLE_64B), 32 KB stages, 6 in flight.  Both are implemented and pass the self-test; measured on
@@ -119,8 +120,20 @@ struct alignas(64) GemmParams {
   CUtensorMap a_hi_half;
   CUtensorMap a_lo_half;
   int multicast_a;
+  // Linear-blend skinning in the epilogue (`skin_A` != nullptr; BLOCK_N = 96 = 32 vertices x 3, fp16 pairs): the
+  // accumulator row of frame m is v_posed[m][32 vertices]; the epilogue applies  verts[m][v] = sum_b w[v][b] (R[m][b] v_posed +
+  // t[m][b])  with the bone transforms skin_A [rows][55][12] (row-major 3 x 4, translation folded in) and the per-tile tables
+  // built by the host: skin_nb[tile] bones touched by the tile's 32 vertices, their indices skin_bone[tile][16] and the dense
+  // weights skin_w[tile][16][32].  `out` (ldo = N = 3 V) receives the vertices; v_posed never exists in memory.
+  const float* skin_A;
+  const int* skin_nb;
+  const int* skin_bone;
+  const float* skin_w;
   // optional: CTA 0 records %globaltimer at 8 milestones (developer instrumentation, see tools/gemm_selftest)
   unsigned long long* debug_ts;
+  // developer experiments (tools/gemm_selftest only; results are wrong when set): bit 0 = the epilogue only drains TMEM (no
+  // staging, no stores), bit 1 = staging writes but no TMA stores.  Slots 16.. of debug_ts: "all MMAs of tile i issued".
+  int debug_flags;
   // filled in by launch_gemm: extent of the tile grid
   int grid_m_rows;
   int grid_n_cols;

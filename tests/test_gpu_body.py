@@ -156,7 +156,7 @@ def test_full_lbs_throughput_shape(body, cuda_device):
     go, bp, be, tr = _params(N, 99)
     out = bm(transl=tr.to(cuda_device), global_orient=go.to(cuda_device), body_pose=bp.to(cuda_device),
              betas=be.to(cuda_device))
-    idx = torch.tensor([0, 1000, N - 1])
+    idx = torch.tensor([0, 127, 128, 1000, 4479, 4480, N - 1])  # first / last rows of row tiles, the ragged last tile
     j, v = ko.smplx_forward(model, go[idx], bp[idx], be[idx], tr[idx], return_verts=True, dtype=torch.float64)
     assert float((out.vertices[idx.to(cuda_device)].cpu().double() - v).abs().max()) < 5e-5
 

@@ -192,17 +192,21 @@ def test_dense_skinning_fallback_matches_sparse():
         "dev = torch.device('cuda:0')\n"
         "bm = BodyModel.create('', device=dev)\n"
         "g = torch.Generator().manual_seed(3)\n"
-        "N = 19\n"
+        "N = 147\n"
         "go, bp, be, tr = 0.3*torch.randn(N,3,generator=g), 0.3*torch.randn(N,63,generator=g), torch.randn(N,10,generator=g), torch.randn(N,3,generator=g)\n"
         "out = bm(transl=tr.to(dev), global_orient=go.to(dev), body_pose=bp.to(dev), betas=be.to(dev))\n"
         "j, v = ko.smplx_forward(synthetic.smplx_like_model(0), go, bp, be, tr, return_verts=True, dtype=torch.float64)\n"
         "err = float((out.vertices.cpu().double() - v).abs().max())\n"
         "print('dense skin err', err)\n"
         "assert err < 5e-5, err\n")
-    env = dict(os.environ, ROHM_B200_DENSE_SKIN="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "dense skin err" in r.stdout
+    # the fused blend + skinning launch takes precedence over both skin kernels: switch it off to reach them.  First the dense
+    # fallback, then the sparse two-kernel path (blend GEMM -> v_posed -> skin_kernel), the fallback for models whose 32-vertex
+    # tiles touch more than 16 bones.
+    for extra in ({"ROHM_B200_DENSE_SKIN": "1"}, {}):
+        env = dict(os.environ, ROHM_B200_FUSED_LBS="0", **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "dense skin err" in r.stdout
 
 
 def test_body_model_rejects_nonzero_hand_pose(body, cuda_device):

@@ -9,6 +9,7 @@ import torch
 
 from helpers import NoiseTape, TOL, golden
 from oracle import diffusion_oracle as do
+from oracle import kinematics_oracle as ko
 from oracle import pipeline_oracle
 from rohm_b200 import diffusion, pipeline, synthetic
 from rohm_b200.body_model import BodyModel
@@ -153,21 +154,51 @@ def test_guided_tail_at_benchmark_size(cuda_device):
     t_rows = d._t_rows(B, dev)
     batch = {'cond': cond.to(dev)}
     x_free = x.to(dev)
-    worst_tf, worst_free, lines = 0.0, 0.0, []
+    from rohm_b200.body_model import kernels_for
+    kern = kernels_for(mp.smplx_model, dev, B * T, with_vertices=False)
+    mean_d, std_d = mean_p.to(dev), std_p.to(dev)
+    worst_fwd, worst_upd, worst_ratio, worst_gain, worst_free, lines = 0.0, 0.0, 0.0, 0.0, 0.0, []
     for i in range(first, -1, -1):
         nz = tape.randn(B, 294, 1, T)
-        x_next, _ = pipeline_oracle.posenet_guided_step(tables, tmap, i, x, cond, sd_p, mean_p, std_p, body_o, nz)
+        x_next, x0_o = pipeline_oracle.posenet_guided_step(tables, tmap, i, x, cond, sd_p, mean_p, std_p, body_o, nz)
         d._randn_like = lambda t_, _n=nz.to(dev): _n
         o_tf = d.p_sample_with_grad(mp, batch, x.to(dev), t_rows[i], clip_denoised=False, grad_type='amass', _step_index=i)
         o_fr = d.p_sample_with_grad(mp, batch, x_free, t_rows[i], clip_denoised=False, grad_type='amass', _step_index=i)
         x_free = o_fr['sample']
+        # The update adds K = 3e6 * posterior_variance[i] times the skating gradient g(x0), and x0 -> K g(x0) is violently
+        # ill-conditioned wherever a 6-D rotation is close to degenerate (Gram-Schmidt divides by a small norm; the elements
+        # that make |x| jump are exactly those): a 2e-5 difference in x0 -- the denoiser's fp32 rounding -- moves the update by
+        # O(1).  So the step is checked in its two well-posed halves: (1) the denoiser output x0 against the oracle's, and
+        # (2) the guided update against the ORACLE's update evaluated at the CUDA path's own x0.  The amplification the
+        # oracle itself shows between the two x0 is printed, and every fifth step the analytic CUDA gradient is held to the
+        # oracle's float64 gradient next to the reference's own fp32 autograd.
+        K = 3e6 * float(do.extract(tables["posterior_variance"], i))
+        x0_c = o_tf['pred_xstart'].cpu()
+        g_at_c = ko.guide_skating(x0_c, mean_p, std_p, body_o)
+        upd_o = do.p_sample_step(tables, i, x, x0_c, nz, [(3e6, g_at_c)] if (g_at_c.dim() != 0 and i <= 50) else None)
+        e_upd = float((o_tf['sample'].cpu() - upd_o).abs().max())
+        e_fwd = float((x0_c - x0_o).abs().max())
         e_tf = float((o_tf['sample'].cpu() - x_next).abs().max())
         e_fr = float((x_free.cpu() - x_next).abs().max())
         mag = float(x_next.abs().max())
-        lines.append(f"t={i:2d} |x|={mag:8.2f} teacher-forced {e_tf:.3e} free-running {e_fr:.3e}")
-        worst_tf, worst_free = max(worst_tf, e_tf / max(1.0, mag)), max(worst_free, e_fr)
+        gain = e_tf / max(e_fwd, 1e-12)
+        extra = ""
+        if i % 5 == 0 and i > 0:
+            g32 = ko.guide_skating(x0_o, mean_p, std_p, body_o)
+            g64 = ko.guide_skating(x0_o.double(), mean_p.double(), std_p.double(), body_o)
+            gc = kern.skating_guidance(x0_o.to(dev).contiguous(), mean_d, std_d).cpu()
+            ref_unc = K * float((g32.double() - g64).abs().max())
+            cuda_err = K * float((gc.double() - g64).abs().max())
+            worst_ratio = max(worst_ratio, cuda_err / max(ref_unc, 1e-5 * max(1.0, mag)))
+            extra = f" | K|g_ref32-g64| {ref_unc:.2e} K|g_cuda-g64| {cuda_err:.2e}"
+        lines.append(f"t={i:2d} |x|={mag:8.2f} x0 err {e_fwd:.2e} | update at the same x0: err {e_upd:.2e} ({e_upd / max(1.0, mag):.1e} rel) | "
+                     f"whole step: teacher-forced {e_tf:.3e} (= {gain:.1e} x the x0 err) free-running {e_fr:.3e}{extra}")
+        worst_fwd, worst_upd = max(worst_fwd, e_fwd), max(worst_upd, e_upd / max(1.0, mag))
+        worst_gain, worst_free = max(worst_gain, gain), max(worst_free, e_fr)
         x = x_next
-    print("guided tail 32x143, t=50..0 (CUDA vs CPU oracle):\n" + "\n".join(lines))
-    print(f"guided tail summary: worst teacher-forced error / max(1,|x|) = {worst_tf:.3e}; final free-running error = "
+    print("guided tail 32x143, t=50..0 (CUDA vs CPU oracle; g64 = the oracle's gradient in float64):\n" + "\n".join(lines))
+    print(f"guided tail summary: worst x0 error {worst_fwd:.3e}; worst guided-update error at the same x0 / max(1,|x|) = "
+          f"{worst_upd:.3e}; worst K|g_cuda-g64| / max(K|g_ref32-g64|, 1e-5 |x|) = {worst_ratio:.2f}; largest amplification of "
+          f"the x0 error by one guided step = {worst_gain:.1e}; final free-running error = "
           f"{float((x_free.cpu() - x).abs().max()):.3e}; worst free-running = {worst_free:.3e}")
-    assert worst_tf < 1e-3
+    assert worst_fwd < 1e-4 and worst_upd < 1e-4 and worst_ratio < 3.0

@@ -263,17 +263,33 @@ static void case_linear_f16(int M, int N, int K, int block_n, int act, bool with
     const double us = ms * 1000.0 / iters;
     printf("    timing: %.2f us/launch  -> %.1f TFLOP/s algorithmic (fp16 hi/lo, 3 tensor passes)\n", us, 2.0 * M * N * K / us * 1e-6);
     unsigned long long* dts;
-    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
-    p.debug_ts = dts;
-    CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
-    CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
-    CK(cudaDeviceSynchronize());
-    unsigned long long h[16];
-    CK(cudaMemcpy(h, dts, sizeof h, cudaMemcpyDeviceToHost));
-    printf("    CTA0 timeline (ns): setup %llu | first_tma %llu | first_full %llu | tile0 mma issued %llu | tile0 epi start %llu | "
-           "tile0 epi done %llu | all mma issued %llu | last epi done %llu | stores done %llu | end %llu\n",
-           h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0],
-           h[7] - h[0]);
+    CK(cudaMalloc(&dts, 32 * sizeof(unsigned long long)));
+    // flags 1 / 2: developer experiments that break the result (epilogue drains TMEM only / stages without storing) -- they
+    // show how much of the main loop's steady-state slowdown comes from the concurrent epilogue of the previous tile
+    for (int flags = 0; flags < (tma_mode == 2 && N >= 1024 ? 3 : 1); ++flags) {
+      p.debug_flags = flags;
+      p.debug_ts = nullptr;
+      for (int i = 0; i < 3; ++i) CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < iters; ++i) CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      CK(cudaMemset(dts, 0, 32 * sizeof(unsigned long long)));
+      p.debug_ts = dts;
+      CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+      CK(launch_gemm(p, M, N, block_n, 3, 0, false, kKindF16));
+      CK(cudaDeviceSynchronize());
+      unsigned long long h[32];
+      CK(cudaMemcpy(h, dts, sizeof h, cudaMemcpyDeviceToHost));
+      printf("    [debug_flags %d: %.2f us/launch] CTA0 timeline (ns): setup %llu | first_tma %llu | first_full %llu | tile0 mma issued %llu | tile0 epi start %llu | "
+             "tile0 epi done %llu | all mma issued %llu | last epi done %llu | stores done %llu | end %llu | per-tile mma issued:",
+             flags, ms * 1000.0 / iters, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[12] - h[0],
+             h[13] - h[0], h[14] - h[0], h[7] - h[0]);
+      for (int i = 16; i < 24 && h[i] != 0; ++i) printf(" %llu", h[i] - h[0]);
+      printf("\n");
+    }
+    p.debug_flags = 0;
     p.debug_ts = nullptr;
     cudaFree(dts);
   }
@@ -441,7 +457,7 @@ static void case_linear_ln(int M, int K, bool timing) {
       printf("    timing %s: %.2f us/launch\n", q == &pc ? "(C) producer" : "(B) consumer N=1024", ms * 1000.0 / iters);
     }
     unsigned long long* dts;
-    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&dts, 32 * sizeof(unsigned long long)));
     pc.debug_ts = dts;
     CK(launch_gemm(pc, M, D, 128, 3, 0, false, kKindF16));
     CK(launch_gemm(pc, M, D, 128, 3, 0, false, kKindF16));
@@ -594,7 +610,7 @@ static void bench_fixed(int M, int N, int K, int outputs /*0 none, 1 fp32, 2 hi/
          ms * 1000.0 / iters);
   {
     unsigned long long* dts;
-    CK(cudaMalloc(&dts, 16 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&dts, 32 * sizeof(unsigned long long)));
     p.debug_ts = dts;
     CK(launch_gemm(p, M, N, 128, passes, 0));
     CK(launch_gemm(p, M, N, 128, passes, 0));
