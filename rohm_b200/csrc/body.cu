@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __r
                                                                 const float* __restrict__ transl,
                                                                 const float* __restrict__ Jt, const float* __restrict__ Jd,
                                                                 int N, float* __restrict__ joints, int nj,
-                                                                float* __restrict__ A, float* __restrict__ feat_hi,
-                                                                float* __restrict__ feat_lo, int f16) {
+                                                                float* __restrict__ A, int64_t a_frame_stride,
+                                                                float* __restrict__ feat_hi, float* __restrict__ feat_lo,
+                                                                int f16) {
   __shared__ float sW[kFkWarps][kJ][12];   // world transforms [R | t] row-major 3x4
   __shared__ float sJ[kFkWarps][kJ][3];    // rest joints
   __shared__ int sDone[kFkWarps][kJ];
@@ -221,10 +222,16 @@ __global__ void __launch_bounds__(32 * kFkWarps) fk_full_kernel(const float* __r
       }
       if (A != nullptr) {  // A_j = [W_r | W_t - W_r J_rest + transl]
         const V3 t = Wt - mul(Wr, J) + tr;
-        float* o = A + (static_cast<int64_t>(n) * kJ + j) * 12;
-        o[0] = Wr.c0.x, o[1] = Wr.c1.x, o[2] = Wr.c2.x, o[3] = t.x;
-        o[4] = Wr.c0.y, o[5] = Wr.c1.y, o[6] = Wr.c2.y, o[7] = t.y;
-        o[8] = Wr.c0.z, o[9] = Wr.c1.z, o[10] = Wr.c2.z, o[11] = t.z;
+        const float a12[12] = {Wr.c0.x, Wr.c1.x, Wr.c2.x, t.x, Wr.c0.y, Wr.c1.y, Wr.c2.y, t.y, Wr.c0.z, Wr.c1.z, Wr.c2.z, t.z};
+        if (a_frame_stride == 0) {  // [frame][joint][12]: skin_kernel stages whole frames
+          float* o = A + (static_cast<int64_t>(n) * kJ + j) * 12;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) o[e] = a12[e];
+        } else {  // [joint][12][frame]: the fused skinning epilogue reads one frame per lane, coalesced
+          float* o = A + static_cast<int64_t>(j) * 12 * a_frame_stride + n;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) o[e * a_frame_stride] = a12[e];
+        }
       }
     }
     __syncwarp();
@@ -685,7 +692,8 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
             bd->jwork && bd->gwork && bd->parents_dev;
   if (ok) ok = cudaMemcpy(bd->parents_dev, parents_host, sizeof(int) * kJ, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok && with_vertices) {
-    bd->A = bd->pool.floats(F * kJ * 12);
+    bd->a_frame_stride = round_up(F, 128);  // whole 128-frame row tiles: the epilogue's bulk copies never leave a row
+    bd->A = bd->pool.floats(bd->a_frame_stride * kJ * 12);
     bd->feat_h = bd->pool.floats(F * kBlendK), bd->feat_l = bd->pool.floats(F * kBlendK);
     // v_posed lives only for one chunk of kLbsChunk frames (48 MB): the blend GEMM writes it and the skinning kernel reads it
     // back while it is still in the 126 MB L2, so the 2 x 531 MB round trip of a whole-batch intermediate never reaches HBM
@@ -805,14 +813,24 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
       if (want) {
         GemmParams& k = bd->g_skin;
         k = GemmParams{};
-        int rs = make_tmap_2d(&k.a_hi[0], bd->feat_h, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
-        rs |= make_tmap_2d(&k.a_lo[0], bd->feat_l, F, kBlendK, kBlendK, kGemmBlockM, 1, bd->kind);
-        rs |= make_tmap_2d(&k.b_hi, bd->blend.hi, bd->blend.Np, kBlendK, kBlendK, 96, 1, bd->kind);
-        rs |= make_tmap_2d(&k.b_lo, bd->blend.lo, bd->blend.Np, kBlendK, kBlendK, 96, 1, bd->kind);
+        // The tensor maps end at the last live K column (200 -> 208: the rest of the fourth K block is zero-filled by TMA without
+        // being read: 19 % less L2 -> SM operand traffic).  ROHM_B200_LBS_MULTICAST=1 additionally shares the A tile of a row
+        // stripe between the two CTAs of a pair; measured on B200 neither moves the launch (442 vs 434 us for 4576 frames): it is
+        // bound by the epilogue's load / store instruction count (4-byte accesses), not by operand traffic.
+        constexpr int kLiveK = (kPoseFeat + kBetas + 1 + 15) / 16 * 16;
+        int rs = make_tmap_2d(&k.a_hi[0], bd->feat_h, F, kLiveK, kBlendK, kGemmBlockM, 1, bd->kind);
+        rs |= make_tmap_2d(&k.a_lo[0], bd->feat_l, F, kLiveK, kBlendK, kGemmBlockM, 1, bd->kind);
+        rs |= make_tmap_2d(&k.b_hi, bd->blend.hi, bd->blend.Np, kLiveK, kBlendK, 96, 1, bd->kind);
+        rs |= make_tmap_2d(&k.b_lo, bd->blend.lo, bd->blend.Np, kLiveK, kBlendK, 96, 1, bd->kind);
+        const char* mc = getenv("ROHM_B200_LBS_MULTICAST");
+        if (rs == 0 && mc != nullptr && mc[0] == '1') {
+          k.num_segs = 1, k.seg_row_mul[0] = 1;
+          rs |= gemm_enable_multicast(&k, bd->feat_h, bd->feat_l, F, kLiveK, kBlendK, bd->blend.Np, 96, bd->kind);
+        }
         k.num_segs = 1, k.seg_kblocks[0] = kBlendK / gemm_block_k(bd->kind), k.seg_row_mul[0] = 1;
         k.acc_scale = 1.0f / bd->blend.scale;
         k.ldo = V * 3, k.N = V * 3, k.out_row_mul = 1;
-        k.skin_A = bd->A, k.skin_nb = bd->skin_nb, k.skin_bone = bd->skin_bone, k.skin_w = bd->skin_w;
+        k.skin_A = bd->A, k.skin_lda = bd->a_frame_stride, k.skin_nb = bd->skin_nb, k.skin_bone = bd->skin_bone, k.skin_w = bd->skin_w;
         want = rs == 0 && bd->blend.Np % 96 == 0;
       }
       bd->fused_lbs = want;
@@ -857,14 +875,32 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
   const bool verts = vertices != nullptr;
   fk_full_kernel<<<static_cast<unsigned>((N + kFkWarps - 1) / kFkWarps), 32 * kFkWarps, 0, st>>>(
       global_orient, body_pose, betas, transl, bd->Jt, bd->Jd, static_cast<int>(N), joints, num_joints,
-      verts ? bd->A : nullptr, verts ? bd->feat_h : nullptr, verts ? bd->feat_l : nullptr, bd->kind == kKindF16 ? 1 : 0);
+      verts ? bd->A : nullptr, (verts && bd->fused_lbs) ? bd->a_frame_stride : 0, verts ? bd->feat_h : nullptr,
+      verts ? bd->feat_l : nullptr, bd->kind == kKindF16 ? 1 : 0);
   ROHM_CUDA(ctx, cudaGetLastError());
   if (verts && bd->fused_lbs) {
     // one launch: blend GEMM with the skinning epilogue (gemm.cu, EPI 4); v_posed stays in TMEM / registers
     GemmParams g = bd->g_skin;
     g.M = static_cast<int>(N);
     g.out = vertices;
+    static int ts_calls = 0;
+    unsigned long long* d_ts = nullptr;
+    if (getenv("ROHM_B200_LBS_TS") != nullptr && ++ts_calls == 3) {  // developer instrumentation: CTA 0's %globaltimer stamps
+      if (cudaMalloc(&d_ts, 32 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(d_ts, 0, 32 * sizeof(unsigned long long));
+      g.debug_ts = d_ts;
+    }
     ROHM_CUDA(ctx, launch_gemm(g, static_cast<int>(N), bd->blend.Np, 96, bd->passes, st, false, bd->kind));
+    if (d_ts != nullptr) {
+      unsigned long long h[32];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
+      cudaFree(d_ts);
+      fprintf(stderr, "fused LBS CTA0 timeline (ns): setup %llu | first_full %llu | tile1: acc ready %llu | drained %llu | skinned %llu | "
+              "staged %llu | stored %llu || mma issued per tile:", h[1] - h[0], h[3] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0],
+              h[10] - h[0], h[11] - h[0]);
+      for (int i = 16; i < 24 && h[i] != 0; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+      fprintf(stderr, " | all mma issued %llu | end %llu\n", h[12] - h[0], h[7] - h[0]);
+    }
   } else if (verts) {
     // Pipeline over chunks of kLbsChunk frames: blend GEMM of chunk i on the caller's stream into v_posed buffer i % 2,
     // skinning of chunk i on a second stream (HBM-bound next to the tensor-bound GEMM of chunk i + 1).

@@ -87,6 +87,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-fabsf(x), p, fmaxf(x, 0.0f));
 }
 
+// fused skinning epilogue: the 3 x 4 transform of one bone for this thread's frame, from the [bone][12][frames] table
+__device__ __forceinline__ void load_bone_transform(const float* frame_col, int64_t lda, int bone, float4& r0, float4& r1,
+                                                    float4& r2) {
+  const float* a = frame_col + static_cast<int64_t>(bone) * 12 * lda;
+  r0 = make_float4(__ldg(a), __ldg(a + lda), __ldg(a + 2 * lda), __ldg(a + 3 * lda));
+  r1 = make_float4(__ldg(a + 4 * lda), __ldg(a + 5 * lda), __ldg(a + 6 * lda), __ldg(a + 7 * lda));
+  r2 = make_float4(__ldg(a + 8 * lda), __ldg(a + 9 * lda), __ldg(a + 10 * lda), __ldg(a + 11 * lda));
+}
+
 struct EpiParams {
   const float* bias;
   const float* residual;
@@ -216,9 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   __shared__ __align__(16) float beta_s[EPI == 3 ? BLOCK_N : 4];
   __shared__ uint64_t res_bar[EPI == 3 ? kEpiWarps : 1];  // EPI 3: one transaction barrier per epilogue warp (residual tile loads)
   // EPI 4 (skinning): the current column tile's bone list and dense [bone][vertex] weights
-  __shared__ __align__(16) float skin_w_s[EPI == 4 ? kSkinTileBones * 32 : 4];
-  __shared__ int skin_bone_s[EPI == 4 ? kSkinTileBones : 1];
-  __shared__ int skin_nb_s;
+  __shared__ __align__(16) float skin_w_s[EPI == 4 ? 2 : 1][EPI == 4 ? kSkinTileBones * 32 : 4];  // double-buffered across tiles
+  __shared__ int skin_bone_s[EPI == 4 ? 2 : 1][EPI == 4 ? kSkinTileBones : 1];
+  __shared__ int skin_nb_s[2];
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -418,7 +427,157 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     float* tile = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes) + (warp_idx - 2) * kEpiTileFloats;
     const int tr = lane >> 3, tc = (lane & 7) * 4;  // transposed mapping: rows tr, tr+4, ..., columns tc..tc+3
     int tcount = 0;
-    for (int tile_idx = blockIdx.x; tile_idx < num_tiles; tile_idx += gridDim.x, ++tcount) {
+    if constexpr (EPI == 4) {
+      // ===== linear-blend skinning epilogue: thread = frame m, 16 of the tile's 32 vertices (warp half) =====
+      // Software pipeline over the CTA's tiles: the next tile's tables (bones, dense weights) are fetched into registers at the
+      // top of a tile and published to the other shared-memory buffer after the compute phase; the next tile's bone transforms
+      // of this thread's frame (up to kSkinRegBones x 12 registers, coalesced loads from the [bone][12][frames] table) are
+      // requested right after that, so their L2 latency hides behind this tile's staging and stores.
+      static_assert(BLOCK_N == 96 && PASSES == 3 && KIND == kKindF16, "skinning epilogue: 32 vertices x 3 per tile, fp16 pairs");
+      constexpr int kSkinRegBones = 4;
+      const int i = (warp_idx - 2) * 32 + lane;
+      float4 sk[kSkinRegBones][3];
+      float* const stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+      auto fetch_tables = [&](int tile_n, float& w0, float& w1, int& bone, int& nbv) {
+        const float* wsrc = p.skin_w + static_cast<int64_t>(tile_n) * (kSkinTileBones * 32);
+        w0 = __ldg(wsrc + i), w1 = __ldg(wsrc + i + 256);
+        bone = i < kSkinTileBones ? __ldg(p.skin_bone + tile_n * kSkinTileBones + i) : 0;
+        nbv = i == 0 ? __ldg(p.skin_nb + tile_n) : 0;
+      };
+      auto publish_tables = [&](int buf, float w0, float w1, int bone, int nbv) {
+        skin_w_s[buf][i] = w0, skin_w_s[buf][i + 256] = w1;
+        if (i < kSkinTileBones) skin_bone_s[buf][i] = bone;
+        if (i == 0) skin_nb_s[buf] = nbv;
+      };
+      auto request_transforms = [&](int buf, int m_first) {
+        const int mm = m_first + q * 32 + lane;
+        const float* col = p.skin_A + (mm < e.M ? mm : 0);
+        const int nbv = skin_nb_s[buf];
+#pragma unroll
+        for (int b = 0; b < kSkinRegBones; ++b)
+          if (b < nbv) load_bone_transform(col, p.skin_lda, skin_bone_s[buf][b], sk[b][0], sk[b][1], sk[b][2]);
+      };
+      int buf = 0;
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
+        float w0, w1;
+        int bone, nbv;
+        fetch_tables(static_cast<int>(blockIdx.x) % tiles_n, w0, w1, bone, nbv);
+        publish_tables(0, w0, w1, bone, nbv);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
+        request_transforms(0, (static_cast<int>(blockIdx.x) / tiles_n) * kGemmBlockM);
+      }
+      for (int tile_idx = blockIdx.x; tile_idx < num_tiles; tile_idx += gridDim.x, ++tcount, buf ^= 1) {
+        const int m0 = (tile_idx / tiles_n) * kGemmBlockM;
+        const int n0 = (tile_idx % tiles_n) * BLOCK_N;
+        const int acc_stage = tcount % Cfg::kAccStages;
+        const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
+        const int m = m0 + q * 32 + lane;
+        const int next = tile_idx + static_cast<int>(gridDim.x);
+        const bool has_next = next < num_tiles;
+        float nw0 = 0.f, nw1 = 0.f;
+        int nbone = 0, nnb = 0;
+        if (has_next) fetch_tables(next % tiles_n, nw0, nw1, nbone, nnb);  // in flight during the accumulator wait and the compute
+
+        ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+        if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 5);
+        ptx::tc_fence_after_sync();
+        // verts = sum_b w[v][b] (R_b v_posed + t_b).  Within a 32-vertex tile nearly every (vertex, bone) pair carries weight
+        // (vertices are indexed by body part), so every vertex is updated per bone: no branches, 12 FMAs per (vertex, bone).
+        // Two rounds of 8 vertices keep the live registers (transforms 48 + v_posed 24 + results 48) under the 168 available.
+        float o[48];
+#pragma unroll
+        for (int j = 0; j < 48; ++j) o[j] = 0.0f;
+        const int nb = skin_nb_s[buf];
+        const float* col = p.skin_A + (m < e.M ? m : 0);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float vp[24];
+          {
+            uint32_t a0[16], a1[8], c0[16], c1[8];
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
+                                   (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(48 * half + 24 * h2);
+            ptx::tmem_ld_32x16(taddr, a0);
+            ptx::tmem_ld_32x8(taddr + 16, a1);
+            ptx::tmem_ld_32x16(taddr + BLOCK_N, c0);
+            ptx::tmem_ld_32x8(taddr + BLOCK_N + 16, c1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vp[j] = (__uint_as_float(a0[j]) + __uint_as_float(c0[j])) * e.acc_scale;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vp[16 + j] = (__uint_as_float(a1[j]) + __uint_as_float(c1[j])) * e.acc_scale;
+          }
+          if (h2 == 1) {  // the accumulator is drained: the MMA warp may start the tile after next
+            if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 8);
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+          }
+          auto apply_bone = [&](const float4& r0, const float4& r1, const float4& r2, const float* wrow) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + 8 * h2 + 4 * g);
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = 4 * g + u;  // vertex inside this round
+                const float x = vp[3 * j], y = vp[3 * j + 1], z = vp[3 * j + 2];
+                float& ox = o[24 * h2 + 3 * j];
+                float& oy = o[24 * h2 + 3 * j + 1];
+                float& oz = o[24 * h2 + 3 * j + 2];
+                ox = fmaf(wv[u], fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), ox);
+                oy = fmaf(wv[u], fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), oy);
+                oz = fmaf(wv[u], fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), oz);
+              }
+            }
+          };
+#pragma unroll
+          for (int b = 0; b < kSkinRegBones; ++b)
+            if (b < nb) apply_bone(sk[b][0], sk[b][1], sk[b][2], &skin_w_s[buf][b * 32 + 16 * half]);
+          if (nb > kSkinRegBones) {  // the rarer tiles that touch more bones: straight from L2, one bone ahead
+            float4 c0, c1, c2;
+            load_bone_transform(col, p.skin_lda, skin_bone_s[buf][kSkinRegBones], c0, c1, c2);
+            for (int b = kSkinRegBones; b < nb; ++b) {
+              const float4 r0 = c0, r1 = c1, r2 = c2;
+              if (b + 1 < nb) load_bone_transform(col, p.skin_lda, skin_bone_s[buf][b + 1], c0, c1, c2);
+              apply_bone(r0, r1, r2, &skin_w_s[buf][b * 32 + 16 * half]);
+            }
+          }
+        }
+        if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 9);
+        if (has_next) publish_tables(buf ^ 1, nw0, nw1, nbone, nnb);
+        // one barrier: the next tile's tables are visible, and every warp has finished storing the previous tile's rows out of
+        // the staging tile that is overwritten below
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
+        if (has_next) request_transforms(buf ^ 1, (next / tiles_n) * kGemmBlockM);
+        // transpose through the CTA-wide staging tile: the output row pitch (3 V floats) is not a multiple of 16 bytes, so
+        // neither TMA nor vector stores apply; lanes along the columns give fully coalesced 4-byte stores
+        {
+          float* srow = stg + (q * 32 + lane) * kSkinPitch + 48 * half;
+#pragma unroll
+          for (int j = 0; j < 48; ++j) srow[j] = o[j];
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32));
+        if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 10);
+        {
+          const int w8 = warp_idx - 2;
+#pragma unroll 4
+          for (int rr = 0; rr < kGemmBlockM / kEpiWarps; ++rr) {
+            const int r = w8 * (kGemmBlockM / kEpiWarps) + rr;
+            const int mr = m0 + r;
+            if (mr >= e.M) break;
+            float* dst = e.out + static_cast<int64_t>(mr) * e.ldo + n0;
+            const float* src = stg + r * kSkinPitch;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int col = lane + 32 * c;
+              if (n0 + col < e.N) __stcs(dst + col, src[col]);
+            }
+          }
+        }
+        if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 11);
+      }
+    }
+    for (int tile_idx = blockIdx.x; EPI != 4 && tile_idx < num_tiles; tile_idx += gridDim.x, ++tcount) {
       const int m0 = (tile_idx / tiles_n) * kGemmBlockM;
       const int n0 = (tile_idx % tiles_n) * BLOCK_N;
       const int acc_stage = tcount % Cfg::kAccStages;
@@ -448,13 +607,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           } else {
             corr_s[i] = (e.a_stats != nullptr && col_ok) ? __ldg(e.a_corr + n0 + i) : 0.0f;
           }
-        }
-        if constexpr (EPI == 4) {
-          const int tile_n = tile_idx % tiles_n;
-          const float* wsrc = p.skin_w + static_cast<int64_t>(tile_n) * (kSkinTileBones * 32);
-          skin_w_s[i] = __ldg(wsrc + i), skin_w_s[i + 256] = __ldg(wsrc + i + 256);
-          if (i < kSkinTileBones) skin_bone_s[i] = __ldg(p.skin_bone + tile_n * kSkinTileBones + i);
-          if (i == 0) skin_nb_s = __ldg(p.skin_nb + tile_n);
         }
         if (e.residual != nullptr && row_ok) {
           const float* r = e.residual + orow * e.ldr + n0 + half * 32;
@@ -514,76 +666,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 5);
       ptx::tc_fence_after_sync();
-
-      if constexpr (EPI == 4) {
-        // ===== linear-blend skinning of the accumulator tile: thread = frame m, 16 of the tile's 32 vertices =====
-        static_assert(BLOCK_N == 96 && PASSES == 3 && KIND == kKindF16, "skinning epilogue: 32 vertices x 3 per tile, fp16 pairs");
-        float vp[48];
-        {
-          uint32_t a0[32], a1[16], c0[32], c1[16];
-          const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols) +
-                                 (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(48 * half);
-          ptx::tmem_ld_32x32(taddr, a0);
-          ptx::tmem_ld_32x16(taddr + 32, a1);
-          ptx::tmem_ld_32x32(taddr + BLOCK_N, c0);
-          ptx::tmem_ld_32x16(taddr + BLOCK_N + 32, c1);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) vp[j] = (__uint_as_float(a0[j]) + __uint_as_float(c0[j])) * e.acc_scale;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vp[32 + j] = (__uint_as_float(a1[j]) + __uint_as_float(c1[j])) * e.acc_scale;
-        }
-        // the accumulator is drained: the MMA warp may start the tile after next
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
-        float o[48];
-#pragma unroll
-        for (int j = 0; j < 48; ++j) o[j] = 0.0f;
-        const int nb = skin_nb_s;
-        const float* arow = p.skin_A + static_cast<int64_t>(row_ok ? m : 0) * (55 * 12);
-        for (int b = 0; b < nb; ++b) {
-          const float4* a = reinterpret_cast<const float4*>(arow + skin_bone_s[b] * 12);
-          const float4 r0 = __ldg(a), r1 = __ldg(a + 1), r2 = __ldg(a + 2);
-          const float* wrow = &skin_w_s[b * 32 + 16 * half];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float w = wrow[j];  // the same for every lane: the branch below is warp-uniform
-            if (w != 0.0f) {
-              const float x = vp[3 * j], y = vp[3 * j + 1], z = vp[3 * j + 2];
-              o[3 * j] = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[3 * j]);
-              o[3 * j + 1] = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[3 * j + 1]);
-              o[3 * j + 2] = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[3 * j + 2]);
-            }
-          }
-        }
-        // transpose through the CTA-wide staging tile: the output row pitch (3 V floats) is not a multiple of 16 bytes, so
-        // neither TMA nor vector stores apply; lanes along the columns give fully coalesced 4-byte stores
-        float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-        {
-          float* srow = stg + (q * 32 + lane) * kSkinPitch + 48 * half;
-#pragma unroll
-          for (int j = 0; j < 48; ++j) srow[j] = o[j];
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32));
-        {
-          const int w8 = warp_idx - 2;
-#pragma unroll 4
-          for (int rr = 0; rr < kGemmBlockM / kEpiWarps; ++rr) {
-            const int r = w8 * (kGemmBlockM / kEpiWarps) + rr;
-            const int mr = m0 + r;
-            if (mr >= e.M) break;
-            float* dst = e.out + static_cast<int64_t>(mr) * e.ldo + n0;
-            const float* src = stg + r * kSkinPitch;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const int col = lane + 32 * c;
-              if (n0 + col < e.N) __stcs(dst + col, src[col]);
-            }
-          }
-        }
-        continue;  // the bar.sync 1 at the top of the next tile keeps the staging tile intact until every row is stored
-      }
 
       if constexpr (EPI == 3) {
         // ===== u = LN_prev(residual) + acc * 2^-s + bias, written in place as an fp16 pair + per-row partial statistics =====
@@ -990,7 +1072,7 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   if (p.skin_A != nullptr) {
     if constexpr (BLOCK_N == 96 && PASSES == 3 && KIND == kKindF16) {
       if (!plain || p.act != kActNone || p.out == nullptr || p.skin_nb == nullptr || p.skin_bone == nullptr || p.skin_w == nullptr ||
-          p.bias != nullptr || p.residual != nullptr || p.a_stats != nullptr || p.stats_out != nullptr || p.multicast_a)
+          p.bias != nullptr || p.residual != nullptr || p.a_stats != nullptr || p.stats_out != nullptr)
         return cudaErrorInvalidValue;
       kern = gemm_tile_kernel<BLOCK_N, PASSES, 4, KIND>;
       smem_bytes = Cfg::kStages * Cfg::kStageBytes + 1024 + kSkinStageBytes;

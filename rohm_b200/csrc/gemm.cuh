@@ -122,10 +122,12 @@ struct alignas(64) GemmParams {
   int multicast_a;
   // Linear-blend skinning in the epilogue (`skin_A` != nullptr; BLOCK_N = 96 = 32 vertices x 3, fp16 pairs): the
   // accumulator row of frame m is v_posed[m][32 vertices]; the epilogue applies  verts[m][v] = sum_b w[v][b] (R[m][b] v_posed +
-  // t[m][b])  with the bone transforms skin_A [rows][55][12] (row-major 3 x 4, translation folded in) and the per-tile tables
+  // t[m][b])  with the bone transforms skin_A [55][12][skin_lda frames] (row-major 3 x 4 per bone, translation folded in; frames contiguous:
+  // one frame per lane = coalesced loads) and the per-tile tables
   // built by the host: skin_nb[tile] bones touched by the tile's 32 vertices, their indices skin_bone[tile][16] and the dense
   // weights skin_w[tile][16][32].  `out` (ldo = N = 3 V) receives the vertices; v_posed never exists in memory.
   const float* skin_A;
+  int64_t skin_lda;  // frames per (bone, element) row of skin_A
   const int* skin_nb;
   const int* skin_bone;
   const float* skin_w;
