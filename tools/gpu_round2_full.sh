@@ -12,12 +12,14 @@ for c in posenet trajcontrol lbs respaced100 pipeline; do
   timeout 900 python bench.py --config $c --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_$c.json 2> gpurun_out/${TAG}_bench_$c.err; echo "bench $c exit $?"
 done
 timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "reference arm exit $?"
-# launch lists (cold-cache, serialised: shares, not absolutes)
+# launch lists (cold-cache, serialised: shares, not absolutes); the ncu --set full captures live in tools/gpu_round2_ncu.sh
+# (a separate call: gpurun_out/ may not exceed 64 MiB per call)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 140 -c 200 --csv --log-file gpurun_out/${TAG}_launches_posenet_step.csv python tools/profile_target.py 4 > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_trajnet_forward.csv python tools/profile_target_trajnet.py 3 > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_lbs.csv python tools/profile_lbs.py 3 > /dev/null 2>&1
-# full captures of the dominant kernels (one layer of the PoseNet forward; LBS; a TrajNet stretch)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tile|attention_tc|ddpm_step" -s 52 -c 8 -o gpurun_out/${TAG}_prof_posenet python tools/profile_target.py 4 > gpurun_out/${TAG}_ncu_posenet.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"skin_kernel|gemm_tile|fk_full" -s 6 -c 3 -o gpurun_out/${TAG}_prof_lbs python tools/profile_lbs.py 3 > gpurun_out/${TAG}_ncu_lbs.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tile|gn_mish" -s 130 -c 8 -o gpurun_out/${TAG}_prof_trajnet python tools/profile_target_trajnet.py 3 > gpurun_out/${TAG}_ncu_trajnet.log 2>&1
-ls -la gpurun_out/${TAG}_prof_*.ncu-rep
+ROHM_B200_ATTN_TS=1 ROHM_B200_LBS_TS=1 timeout 300 python tools/profile_target.py 12 2> gpurun_out/${TAG}_timelines.txt > /dev/null
+ROHM_B200_LBS_TS=1 timeout 300 python tools/profile_lbs.py 4 2>> gpurun_out/${TAG}_timelines.txt > /dev/null
+python tools/launch_list_summary.py gpurun_out/${TAG}_launches_posenet_step.csv > gpurun_out/${TAG}_launches_posenet_step_summary.txt 2>&1
+python tools/launch_list_summary.py gpurun_out/${TAG}_launches_trajnet_forward.csv pack_rows unpack_rows > gpurun_out/${TAG}_launches_trajnet_forward_summary.txt 2>&1
+python tools/launch_list_summary.py gpurun_out/${TAG}_launches_lbs.csv repr_to_smplx gemm_tile > gpurun_out/${TAG}_launches_lbs_summary.txt 2>&1
+du -sh gpurun_out
