@@ -192,7 +192,7 @@ ROHM_API int rohm_trajnet_set_cond(rohm_trajnet* tn, const float* cond, const fl
 /* TrajNet.forward (trajnet.py:177-275).  x_t: [B, frames, traj_feat_dim]; time: int64 [B]; out: same shape as x_t. */
 ROHM_API int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
                                   void* stream);
-ROHM_API int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value); /* 0: CUDA-graph replay (default 1) */
+ROHM_API int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value); /* 0: CUDA-graph replay, 1: programmatic dependent launch (both default 1) */
 ROHM_API int rohm_trajnet_launches_per_forward(const rohm_trajnet* tn);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
                                                       float* __restrict__ out, float* __restrict__ out_hi,
                                                       float* __restrict__ out_lo, int C, int Tp, int T, int groups,
                                                       int64_t total4, int f16) {
+  // programmatic dependent launch (run_gn passes the attribute): the next convolution GEMM may become resident and fetch its
+  // weight tiles while this grid runs; nothing is read before the producing GEMM has completed
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -276,7 +280,15 @@ struct rohm_trajnet {
   };
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
+  bool use_pdl = true;  // ROHM_B200_PDL / rohm_trajnet_set_option(1): programmatic dependent launch along the conv / GroupNorm chains
   cudaStream_t capture_stream = nullptr;
+  void drop_graphs() {
+    for (auto& g : graphs) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    graphs.clear();
+  }
   ~rohm_trajnet() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
     for (cudaStream_t q : side)
@@ -497,7 +509,7 @@ int run_conv(rohm_trajnet* tn, const std::string& name, int B, cudaStream_t st) 
   Conv& cv = it->second;
   const int rows = B * tn->Tp[cv.level_out];
   cv.g.M = rows;
-  ROHM_CUDA(tn->ctx, launch_gemm(cv.g, rows, cv.w.N, cv.w.block_n, tn->passes, st, false, tn->kind));
+  ROHM_CUDA(tn->ctx, launch_gemm(cv.g, rows, cv.w.N, cv.w.block_n, tn->passes, st, tn->use_pdl, tn->kind));
   tn->launches++;
   return ROHM_OK;
 }
@@ -507,10 +519,16 @@ int run_gn(rohm_trajnet* tn, const std::string& conv_name, const std::string& no
   const Conv& cv = tn->convs[conv_name];
   auto nb = tn->norms[norm_prefix];
   const int64_t total4 = static_cast<int64_t>(B) * tn->Tp[level] * C / 4;
-  gn_mish_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
-      y, cv.stats, nb.first, nb.second, tp, tn->tp_total, r1, r2, out->f32, out->hi, out->lo, C, tn->Tp[level],
-      tn->Tl[level], kGroups, total4, tn->kind == kKindF16 ? 1 : 0);
-  ROHM_CUDA(tn->ctx, cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>((total4 + 255) / 256)), cfg.blockDim = dim3(256), cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = tn->use_pdl ? 1 : 0;
+  ROHM_CUDA(tn->ctx, cudaLaunchKernelEx(&cfg, gn_mish_kernel, static_cast<const float*>(y), static_cast<const double*>(cv.stats),
+                                        static_cast<const float*>(nb.first), static_cast<const float*>(nb.second), tp, tn->tp_total,
+                                        r1, r2, out->f32, out->hi, out->lo, C, tn->Tp[level], tn->Tl[level], kGroups, total4,
+                                        tn->kind == kKindF16 ? 1 : 0));
   tn->launches++;
   return ROHM_OK;
 }
@@ -1005,6 +1023,11 @@ extern "C" int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value) 
   if (tn == nullptr) return ROHM_ERR_INVALID;
   if (option == 0) {
     tn->use_graph = value != 0;
+    return ROHM_OK;
+  }
+  if (option == 1) {  // programmatic dependent launch along the convolution / GroupNorm chains (captured graphs are rebuilt)
+    if (tn->use_pdl != (value != 0)) tn->drop_graphs();
+    tn->use_pdl = value != 0;
     return ROHM_OK;
   }
   return fail(tn->ctx, ROHM_ERR_INVALID, "rohm_trajnet_set_option: unknown option %d", option);

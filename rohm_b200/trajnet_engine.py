@@ -1,6 +1,7 @@
 """Python side of the TrajNet CUDA engine: hands the module's parameters to ``rohm_trajnet_create`` by their reference
 state-dict keys, tracks the step-invariant condition and runs ``rohm_trajnet_forward``."""
 import ctypes as C
+import os
 
 import torch
 
@@ -28,6 +29,10 @@ class TrajNetEngine:
                                               module.control_cond_dim, max_batch, frames, precision, C.byref(handle))
         _lib.check(rc, self.ctx)
         self.handle = handle
+        if os.environ.get("ROHM_B200_PDL", "1") == "0":
+            self.lib.rohm_trajnet_set_option(handle, 1, 0)
+        if os.environ.get("ROHM_B200_GRAPH", "1") == "0":
+            self.lib.rohm_trajnet_set_option(handle, 0, 0)
         # strong references to the tensors whose step-invariant pyramid the engine holds (see PoseNetEngine)
         self.cond_ref, self.cond_version = None, -1
         self.control_ref, self.control_version = None, -1
