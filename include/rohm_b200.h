@@ -210,6 +210,10 @@ ROHM_API int rohm_body_create(rohm_ctx* ctx, const float* v_template, const floa
                               const int* parents_host, int num_verts, int64_t max_frames, int with_vertices,
                               int precision, rohm_body** out);
 ROHM_API void rohm_body_destroy(rohm_body* bd);
+/* 1 if rohm_body_forward computes the vertices with the fused blend-GEMM + skinning launch, 0 if the handle uses the
+ * two-kernel path (no vertex support, TF32 precision, ROHM_B200_FUSED_LBS=0, or a body model whose 32-vertex tiles touch
+ * more than 16 bones).  Introspection only. */
+ROHM_API int rohm_body_uses_fused_lbs(const rohm_body* bd);
 
 /* SMPLX.forward with jaw / eyes / hands / expression = 0 (exactly how RoHM calls it): global_orient [N,3], body_pose
  * [N,63] axis-angle, betas [N,10], transl [N,3] -> joints [N, num_joints, 3] (first num_joints <= 55 posed joints +

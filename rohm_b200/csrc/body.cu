@@ -857,6 +857,8 @@ extern "C" int rohm_body_create(rohm_ctx* ctx, const float* v_template, const fl
 
 extern "C" void rohm_body_destroy(rohm_body* bd) { delete bd; }
 
+extern "C" int rohm_body_uses_fused_lbs(const rohm_body* bd) { return bd != nullptr && bd->fused_lbs ? 1 : 0; }
+
 // SMPLX.forward as RoHM calls it (jaw / eyes / hands / expression zero).  global_orient [N,3], body_pose [N,63]
 // (axis-angle), betas [N,10], transl [N,3] -> joints [N, num_joints<=55, 3] and (optionally) vertices [N, V, 3].
 extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, const float* body_pose, const float* betas,

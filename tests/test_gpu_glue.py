@@ -297,3 +297,27 @@ def test_eval_loss_dictionaries_match_reference(body, cuda_device):
     got = mt.compute_losses_with_smpl({'motion_repr_clean': clean_cl}, torch.from_numpy(g["traj_loss_rec"]).to(dev),
                                       smplx_model=bm)
     _check_losses(got, g["traj_loss_names"], g["traj_loss_values"])
+
+
+def test_fused_lbs_falls_back_when_a_tile_touches_too_many_bones(cuda_device):
+    """The fused blend + skinning launch needs at most 16 distinct bones per 32 consecutive vertices.  A body model whose
+    vertices are in random order breaks that: the handle must choose the two-kernel path by itself and stay correct; the
+    body-part-ordered model takes the fused path."""
+    t = synthetic.smplx_like_model(0)
+    V = t['v_template'].shape[0]
+    perm = torch.randperm(V, generator=torch.Generator().manual_seed(5))
+    shuffled = dict(t)
+    shuffled['v_template'], shuffled['shapedirs'] = t['v_template'][perm], t['shapedirs'][perm]
+    shuffled['lbs_weights'], shuffled['J_regressor'] = t['lbs_weights'][perm], t['J_regressor'][:, perm]
+    shuffled['posedirs'] = t['posedirs'].view(-1, V, 3)[:, perm].reshape(-1, V * 3)
+    g = torch.Generator().manual_seed(9)
+    N = 40
+    gor, bp = 0.3 * torch.randn(N, 3, generator=g), 0.3 * torch.randn(N, 63, generator=g)
+    be, tr = torch.randn(N, 10, generator=g), torch.randn(N, 3, generator=g)
+    for tensors, fused in ((shuffled, 0), (t, 1)):
+        bm = BodyModel(tensors).to(cuda_device)
+        out = bm(transl=tr.to(cuda_device), global_orient=gor.to(cuda_device), body_pose=bp.to(cuda_device), betas=be.to(cuda_device))
+        k = kernels_for(bm, cuda_device, N, with_vertices=True)
+        assert k.lib.rohm_body_uses_fused_lbs(k.handle) == fused
+        _, v = ko.smplx_forward(tensors, gor, bp, be, tr, return_verts=True, dtype=torch.float64)
+        assert float((out.vertices.cpu().double() - v).abs().max()) < 5e-5

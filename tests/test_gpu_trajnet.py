@@ -182,3 +182,25 @@ def test_eval_losses_default_compute_loss(nets, cuda_device):
                               cond_fn_with_grad=True, smplx_model=BodyModel.create('', device=cuda_device))
     assert out.shape == (B, T, 13) and 'loss' in loss and float(loss['loss_root_pos_global_from_rel_traj']) == 0.0
     assert all(bool(torch.isfinite(v)) for v in loss.values())
+
+
+def test_launch_switches_do_not_change_the_result(nets, cuda_device):
+    """Programmatic dependent launch and CUDA-graph replay only change how the kernels are scheduled: the forward must be
+    bit-identical with either switched off (rohm_trajnet_set_option 1 / 0)."""
+    m, _ = nets[True]
+    B, T = 5, 144
+    gen = torch.Generator().manual_seed(31)
+    batch = {k: v.to(cuda_device) for k, v in synthetic.trajnet_batch(B, T, 3, control=True).items()}
+    batch['x_t'] = torch.randn(B, T, 13, generator=gen).to(cuda_device)
+    ts = torch.randint(0, 1000, (B,), generator=gen).to(cuda_device)
+    ref = m(batch, ts).clone()
+    eng = m._engine
+    try:
+        for option in (1, 0):
+            assert eng.lib.rohm_trajnet_set_option(eng.handle, option, 0) == 0
+            assert torch.equal(m(batch, ts), ref)
+            assert eng.lib.rohm_trajnet_set_option(eng.handle, option, 1) == 0
+            assert torch.equal(m(batch, ts), ref)
+    finally:
+        eng.lib.rohm_trajnet_set_option(eng.handle, 0, 1)
+        eng.lib.rohm_trajnet_set_option(eng.handle, 1, 1)
