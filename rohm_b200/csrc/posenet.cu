@@ -796,7 +796,7 @@ constexpr uint32_t kAtColS = 32, kAtColO0 = 32 + 2 * kAtKeys;  // TMEM column ma
 constexpr int kAtQKBuf = kAtKeys * 128;       // bytes of one 160-row x 128-byte buffer: {plane, dh-chunk} of Q, K or V, {plane, key-chunk} of P
 constexpr int kAtTile = 128 * 128;            // bytes of the 128 rows of one query tile inside such a buffer
 constexpr int kAtSmemBytes = 10 * kAtQKBuf + 1024;
-constexpr int kAtThreads = 320;
+constexpr int kAtThreads = 32 * (2 + 16);  // TMA warp, MMA warp, 2 query tiles x 4 lane quarters x 2 column halves
 
 __device__ __forceinline__ void at_stamp(const AttnTcParams& p, int slot) {
   if (p.debug_ts != nullptr && blockIdx.x == 0) {
@@ -810,10 +810,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   extern __shared__ uint8_t at_smem_raw[];
   __shared__ uint64_t qk_full, v_full, s_full[2], p_ready[2], o_full[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float at_red[2][128][4];  // [tile][row][{max, max, sum, sum} of the two column halves]
   const uint32_t raw_addr = ptx::smem_u32(at_smem_raw);
   uint8_t* smem = at_smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int b = blockIdx.x / p.H, h_ = blockIdx.x % p.H;  // clip, head
   const int S = p.S;
   const int ntiles = S > 128 ? 2 : 1;
   const int row0 = b * S;  // first token row of this clip
@@ -822,7 +823,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.qkv_hi), ptx::prefetch_tmap(&p.qkv_lo), ptx::prefetch_tmap(&p.st_hi), ptx::prefetch_tmap(&p.st_lo);
     ptx::mbar_init(&qk_full, 1), ptx::mbar_init(&v_full, 1);
-    for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 4), ptx::mbar_init(&o_full[t], 1);
+    for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 8), ptx::mbar_init(&o_full[t], 1);
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) ptx::tmem_alloc<512>(&tmem_base_smem);
@@ -845,8 +846,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       for (int pl = 0; pl < 2; ++pl) {
         const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
         for (int kc = 0; kc < 2; ++kc) {
-          ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h * 128 + kc * 64, row0);
-          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h_ * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h_ * 128 + kc * 64, row0);
         }
       }
       // V lands on top of K: wait until every S MMA has read it
@@ -855,7 +856,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       for (int pl = 0; pl < 2; ++pl) {
         const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
         for (int kc = 0; kc < 2; ++kc)
-          ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Vb + (pl * 2 + kc) * kAtQKBuf, m, &v_full, 2 * p.D + h_ * 128 + kc * 64, row0);
       }
     }
   } else if (warp_idx == 1) {
@@ -906,144 +907,149 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       }
     }
   } else {
-    // ===================== softmax + output warps: tile t = (warp_idx - 2) / 4, one thread per query row =====================
-    // TMEM loads are software-pipelined (the load of chunk c + 1 is in flight while chunk c is processed) and the row
-    // reductions keep four partial accumulators: with one warp per scheduler the phase is latency-, not issue-bound.
-    const int t = (warp_idx - 2) >> 2;
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    // ===================== softmax + output warps: 8 per query tile, TWO threads per query row =====================
+    // tile t = (warp_idx - 2) / 8; TMEM lane quarter q = warp_idx % 4 (hardware rule); half h = ((warp_idx - 2) / 4) % 2:
+    // the two warps of a (tile, quarter) pair split the 160 key columns of their 32 rows (80 each: row maximum and row sum are
+    // exchanged through shared memory under a 64-thread named barrier) and, in the output phase, the 128 feature columns.
+    // One thread per row left the four schedulers with one latency-bound warp each for 4.2 us of the 12 us chain.
+    const int t = (warp_idx - 2) >> 3;
+    const int h = ((warp_idx - 2) >> 2) & 1;
+    const int q = warp_idx & 3;
     const int row = q * 32 + lane;
     const int grow = t * 128 + row;  // token index inside the clip
     const bool valid = grow < S;
     if (t < ntiles && t * 128 + q * 32 >= S) {
-      // no real query row in this warp's 32 lanes (the tail of tile 1): nothing to compute, just release the MMA warp
+      // no real query row in this pair's 32 lanes (the tail of tile 1): nothing to compute, just release the MMA warp
       if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
     } else if (t < ntiles) {
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-      const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys);
-      constexpr int NC = kAtKeys / 32;
-      uint32_t r0[32], r1[32];
+      const uint32_t s_addr = tmem_base + lane_addr + kAtColS + static_cast<uint32_t>(t * kAtKeys + 80 * h);
+      const int pair_bar = 1 + t * 4 + q;  // named barrier of this (tile, quarter) pair
+      constexpr int NC = 5;                // 16-column chunks per thread
+      uint32_t r0[16], r1[16];
       ptx::mbar_wait(&s_full[t], 0);
       if (t == 0 && warp_idx == 2 && lane == 0) at_stamp(p, 3);
       ptx::tc_fence_after_sync();
-      // pass 1: row maximum over the real keys
+      // pass 1: maximum over this thread's real keys
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      ptx::tmem_ld_32x32(s_addr, r0);
+      ptx::tmem_ld_32x16(s_addr, r0);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
-        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
-        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32, nxt);
+        uint32_t(&cur)[16] = (c & 1) ? r1 : r0;
+        uint32_t(&nxt)[16] = (c & 1) ? r0 : r1;
+        if (c + 1 < NC) ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, nxt);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
+        for (int j = 0; j < 16; ++j)
+          if (80 * h + c * 16 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
         if (c + 1 < NC) ptx::tmem_ld_wait();
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      at_red[t][row][h] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, at_red[t][row][h ^ 1]);
       if (t == 0 && warp_idx == 2 && lane == 0) at_stamp(p, 5);
       // the P buffers overlap Q and K: every S MMA must have completed
       ptx::mbar_wait(&s_full[ntiles - 1], 0);
-      // pass 2: p = exp(scale (s - max)), row sum, fp16 hi/lo -> K-major SWIZZLE_128B rows (16-byte unit u of row r at
+      // pass 2: p = exp(scale (s - max)), partial row sum, fp16 hi/lo -> K-major SWIZZLE_128B rows (16-byte unit u of row r at
       // slot u ^ (r & 7))
       float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       const float sc2 = p.scale * 1.4426950408889634f;  // exp(x) = 2^(x log2 e): one FFMA + one MUFU.EX2 per element
       const float ms2 = mx * sc2;
-      ptx::tmem_ld_32x32(s_addr, r0);
+      ptx::tmem_ld_32x16(s_addr, r0);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
-        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
-        if (c + 1 < NC) ptx::tmem_ld_32x32(s_addr + (c + 1) * 32, nxt);
-        float pv[32];
+        uint32_t(&cur)[16] = (c & 1) ? r1 : r0;
+        uint32_t(&nxt)[16] = (c & 1) ? r0 : r1;
+        if (c + 1 < NC) ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, nxt);
+        const int k0 = 80 * h + 16 * c;  // first key of this chunk
+        float pv[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float x = fmaf(__uint_as_float(cur[j]), sc2, -ms2);  // <= 0
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[j]) : "f"(x));
         }
-        if (c * 32 + 31 >= S) {  // only the last chunk(s) hold padded keys
+        if (k0 + 15 >= S) {  // only the last chunk(s) hold padded keys
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] = (c * 32 + j < S) ? pv[j] : 0.0f;
+          for (int j = 0; j < 16; ++j) pv[j] = (k0 + j < S) ? pv[j] : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum4[j & 3] += pv[j];
+        for (int j = 0; j < 16; ++j) sum4[j & 3] += pv[j];
         if (valid) {
-          uint8_t* ph = Pb + (0 * 3 + (c >> 1)) * kAtQKBuf + grow * 128;
-          uint8_t* pl = Pb + (1 * 3 + (c >> 1)) * kAtQKBuf + grow * 128;
+          uint8_t* ph = Pb + (0 * 3 + (k0 >> 6)) * kAtQKBuf + grow * 128;
+          uint8_t* pl = Pb + (1 * 3 + (k0 >> 6)) * kAtQKBuf + grow * 128;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) ptx::split_f16x2(pv[8 * u + 2 * i], pv[8 * u + 2 * i + 1], hw[i], lw[i]);
-            const int slot = (((c & 1) * 4 + u) ^ (row & 7)) << 4;
+            const int slot = ((((k0 & 63) >> 3) + u) ^ (row & 7)) << 4;
             *reinterpret_cast<uint4*>(ph + slot) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(pl + slot) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
         if (c + 1 < NC) ptx::tmem_ld_wait();
       }
-      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      at_red[t][row][2 + h] = sum;
       ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
       ptx::tc_fence_before_sync();
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      sum += at_red[t][row][2 + (h ^ 1)];
       if (lane == 0) ptx::mbar_arrive(&p_ready[t]);
 
-      // output: O / sum -> fp16 hi/lo rows of ctx.  Full 32-row groups go through a SWIZZLE_64B staging tile (carved out
-      // of the first P buffer, whose tile-0 rows are dead once the O MMAs of tile 0 have completed) and TMA stores; a
-      // group that straddles the end of the clip writes its real rows directly.
+      // output: O / sum -> fp16 hi/lo rows of ctx; this warp owns the 32-column chunks 2h and 2h + 1.  Full 32-row groups go
+      // through a SWIZZLE_64B staging tile (carved out of P buffer c, whose tile-0 rows are dead once the O MMAs of tile 0 have
+      // completed) and TMA stores; a group that straddles the end of the clip writes its real rows directly.
       ptx::mbar_wait(&o_full[t], 0);
-      if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 7 + 3 * t);
+      if (warp_idx == 4 + 8 * t && lane == 0) at_stamp(p, 7 + 3 * t);
       ptx::tc_fence_after_sync();
       const float inv = 1.0f / sum;
-      const uint32_t o_addr = tmem_base + lane_addr + (t == 0 ? kAtColO0 : kAtColS);
-      const int64_t o = (static_cast<int64_t>(row0) + grow) * p.D + h * 128;
+      const uint32_t o_addr = tmem_base + lane_addr + (t == 0 ? kAtColO0 : kAtColS) + static_cast<uint32_t>(64 * h);
+      const int64_t o = (static_cast<int64_t>(row0) + grow) * p.D + h_ * 128 + 64 * h;
       const bool group_full = t == 0 && (q * 32 + 32 <= S);  // tile 0 only: the staging area belongs to tile 0's P rows
-      if (group_full) ptx::mbar_wait(&o_full[0], 0);
-      ptx::tmem_ld_32x32(o_addr, r0);
+      ptx::tmem_ld_32x16(o_addr, r0);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? r1 : r0;
-        uint32_t(&nxt)[32] = (c & 1) ? r0 : r1;
-        if (c + 1 < 4) ptx::tmem_ld_32x32(o_addr + (c + 1) * 32, nxt);
+      for (int cc = 0; cc < 4; ++cc) {  // 16 columns per step; two steps per 32-column chunk
+        uint32_t(&cur)[16] = (cc & 1) ? r1 : r0;
+        uint32_t(&nxt)[16] = (cc & 1) ? r0 : r1;
+        if (cc + 1 < 4) ptx::tmem_ld_32x16(o_addr + (cc + 1) * 16, nxt);
+        const int c = 2 * h + (cc >> 1);  // 32-column chunk of the head's 128 features
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          ptx::split_f16x2(__uint_as_float(cur[2 * i]) * inv, __uint_as_float(cur[2 * i + 1]) * inv, hw[i], lw[i]);
         if (group_full) {
-          // chunk c stages in the tile-0 rows of P buffer c (all four are dead now): no wait between chunks
           uint8_t* const tb = Pb + c * kAtQKBuf + q * 4096;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              ptx::split_f16x2(__uint_as_float(cur[8 * u + 2 * i]) * inv, __uint_as_float(cur[8 * u + 2 * i + 1]) * inv, hw[i],
-                               lw[i]);
-            const int off = lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(tb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(tb + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          for (int u = 0; u < 2; ++u) {
+            const int off = lane * 64 + (((2 * (cc & 1) + u) ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(tb + off) = make_uint4(hw[4 * u], hw[4 * u + 1], hw[4 * u + 2], hw[4 * u + 3]);
+            *reinterpret_cast<uint4*>(tb + 2048 + off) = make_uint4(lw[4 * u], lw[4 * u + 1], lw[4 * u + 2], lw[4 * u + 3]);
           }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(&p.st_hi, tb, h * 128 + c * 32, row0 + q * 32);
-            ptx::tma_store_2d(&p.st_lo, tb + 2048, h * 128 + c * 32, row0 + q * 32);
-            ptx::bulk_commit();
+          if (cc & 1) {  // the 32-column chunk is complete
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&p.st_hi, tb, h_ * 128 + c * 32, row0 + q * 32);
+              ptx::tma_store_2d(&p.st_lo, tb + 2048, h_ * 128 + c * 32, row0 + q * 32);
+              ptx::bulk_commit();
+            }
           }
         } else if (valid) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              ptx::split_f16x2(__uint_as_float(cur[8 * u + 2 * i]) * inv, __uint_as_float(cur[8 * u + 2 * i + 1]) * inv, hw[i],
-                               lw[i]);
-            *reinterpret_cast<uint4*>(p.ctx_hi + o + c * 32 + u * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(p.ctx_lo + o + c * 32 + u * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          for (int u = 0; u < 2; ++u) {
+            *reinterpret_cast<uint4*>(p.ctx_hi + o + cc * 16 + u * 8) = make_uint4(hw[4 * u], hw[4 * u + 1], hw[4 * u + 2], hw[4 * u + 3]);
+            *reinterpret_cast<uint4*>(p.ctx_lo + o + cc * 16 + u * 8) = make_uint4(lw[4 * u], lw[4 * u + 1], lw[4 * u + 2], lw[4 * u + 3]);
           }
         }
-        if (c + 1 < 4) ptx::tmem_ld_wait();
+        if (cc + 1 < 4) ptx::tmem_ld_wait();
       }
       if (group_full && lane == 0) ptx::bulk_wait_read_all();  // staging tiles must outlive the TMA reads, not the writes
       ptx::tc_fence_before_sync();
-      if ((warp_idx & 3) == 2 && lane == 0) at_stamp(p, 8 + 3 * t);
+      if (warp_idx == 4 + 8 * t && lane == 0) at_stamp(p, 8 + 3 * t);
     }
   }
   __syncthreads();
