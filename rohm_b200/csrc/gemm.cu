@@ -16,9 +16,10 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSmemBudget = 192 * 1024;  // operand ring budget (BLOCK_N = 128, PASSES = 3: 6 x 32 KB or 3 x 64 KB)
 constexpr int kEpiTileFloats = 32 * 32;   // per-epilogue-warp staging tile (32 x 32, XOR-swizzled columns): coalesced stores
-// fused skinning epilogue (EPI 4): one 128 x 96 fp32 staging tile for the whole CTA, pitch 97 floats (conflict-free both for the
-// row-per-thread writes and the row-contiguous reads)
-constexpr int kSkinPitch = 97;
+// fused skinning epilogue (EPI 4): one 128 x 96 fp32 staging tile for the whole CTA.  Pitch 100 floats: the 16-byte
+// row-per-thread writes (8 lanes per wavefront hit 8 distinct 16-byte bank groups: 25 r mod 8) and the 4-byte row-contiguous
+// reads are both conflict-free
+constexpr int kSkinPitch = 100;
 constexpr int kSkinStageBytes = kGemmBlockM * kSkinPitch * 4;
 
 template <int BLOCK_N, int PASSES>
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         // transpose through the CTA-wide staging tile: the output row pitch (3 V floats) is not a multiple of 16 bytes, so
         // neither TMA nor vector stores apply; lanes along the columns give fully coalesced 4-byte stores
         {
-          float* srow = stg + (q * 32 + lane) * kSkinPitch + 48 * half;
+          float4* srow = reinterpret_cast<float4*>(stg + (q * 32 + lane) * kSkinPitch + 48 * half);
 #pragma unroll
-          for (int j = 0; j < 48; ++j) srow[j] = o[j];
+          for (int j = 0; j < 12; ++j) srow[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         }
         asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32));
         if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 10);
