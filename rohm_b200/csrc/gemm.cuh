@@ -55,6 +55,8 @@ enum GemmAct : int { kActNone = 0, kActGelu = 1, kActSilu = 2, kActMish = 3 };
 struct alignas(64) GemmParams {
   CUtensorMap a_hi[kMaxSegs];
   CUtensorMap a_lo[kMaxSegs];
+  // B must be constant for the lifetime of the launch chain (a packed weight matrix): the kernel requests its first B tiles
+  // BEFORE griddepcontrol.wait, i.e. while the previous kernel of the stream may still be running
   CUtensorMap b_hi;
   CUtensorMap b_lo;
   int seg_kblocks[kMaxSegs];    // number of gemm_block_k(kind)-wide K blocks of this segment
