@@ -13,7 +13,7 @@ done
 [ -s $G/${T}_tests.log ] && { grep -A60 "^guided tail 32x143" $G/${T}_tests.log | grep "^guided\|^t=" > $P/r2_guided_tail_32x143.txt; tail -3 $G/${T}_tests.log > $P/r2_gpu_tests_tail.txt; grep -h "max |cuda\|projection guidance\|free-run\|stagewise\|teacher" $G/${T}_tests.log | head -40 >> $P/r2_gpu_tests_tail.txt; }
 [ -s $G/${T}_smoke.log ] && tail -1 $G/${T}_smoke.log >> $P/r2_gpu_tests_tail.txt
 [ -s $G/${T}_smi.txt ] && cp $G/${T}_smi.txt $P/r2_nvidia_smi.txt
-for n in posenet lbs trajnet; do [ -s $G/${N}_ncu_${n}_summary.txt ] && cp $G/${N}_ncu_${n}_summary.txt $P/r2_ncu_${n}_summary.txt; done
+for n in posenet posenet_warm lbs trajnet; do [ -s $G/${N}_ncu_${n}_summary.txt ] && cp $G/${N}_ncu_${n}_summary.txt $P/r2_ncu_${n}_summary.txt; done
 for n in gemm lbs trajnet; do [ -s $G/${N}_${n}_traffic.json ] && cp $G/${N}_${n}_traffic.json $P/r2_${n}_traffic.json; done
 for n in racecheck memcheck; do [ -s $G/${N}_sanitizer_${n}_smoke.log ] && tail -15 $G/${N}_sanitizer_${n}_smoke.log > $P/r2_sanitizer_${n}_smoke.txt; done
 ls -la $P | tail -40

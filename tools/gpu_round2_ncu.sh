@@ -8,6 +8,10 @@ TAG=${1:-r2}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tile|attention_tc|ddpm_step" -s 52 -c 6 -o gpurun_out/${TAG}_prof_posenet python tools/profile_target.py 4 > gpurun_out/${TAG}_ncu_posenet.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tile|fk_full" -s 2 -c 2 -o gpurun_out/${TAG}_prof_lbs python tools/profile_lbs.py 3 > gpurun_out/${TAG}_ncu_lbs.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"gemm_tile|gn_mish" -s 130 -c 6 -o gpurun_out/${TAG}_prof_trajnet python tools/profile_target_trajnet.py 3 > gpurun_out/${TAG}_ncu_trajnet.log 2>&1
+# the same PoseNet layer with caches left warm between ncu's replay passes (closer to the running loop, where operands are L2 hits)
+timeout 900 ncu --set full --clock-control none --cache-control none -k regex:"gemm_tile|attention_tc" -s 52 -c 5 -o gpurun_out/${TAG}_prof_posenet_warm python tools/profile_target.py 4 > gpurun_out/${TAG}_ncu_posenet_warm.log 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_prof_posenet_warm.ncu-rep > gpurun_out/${TAG}_ncu_posenet_warm_summary.txt 2>&1
+rm -f gpurun_out/${TAG}_prof_posenet_warm.ncu-rep
 for n in posenet lbs trajnet; do
   python tools/ncu_summary.py gpurun_out/${TAG}_prof_$n.ncu-rep > gpurun_out/${TAG}_ncu_${n}_summary.txt 2>&1
 done
