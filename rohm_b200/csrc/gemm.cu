@@ -696,7 +696,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
-        // partial row statistics over this thread's 64 columns for the consumers of LN(u)
+        uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+        const bool group_full = (m0 + q * 32 + 32 <= e.M);
+        auto store_chunk = [&](int h2) {
+          const int nb = n0 + half * 32 + 64 * h2;
+          if (group_full) {
+            stage_pair_chunk(v[h2], tb, lane, &p.st_hi, &p.st_lo, nb, m0 + q * 32);
+          } else if (row_ok) {  // ragged last row group: per-thread stores
+            __half* oh = static_cast<__half*>(e.out_hi) + static_cast<int64_t>(m) * e.lds + nb;
+            __half* ol = static_cast<__half*>(e.out_lo) + static_cast<int64_t>(m) * e.lds + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ptx::split_f16(v[h2][j], oh[j], ol[j]);
+          }
+        };
+        store_chunk(0);
+        // partial row statistics over this thread's 64 columns for the consumers of LN(u) -- computed while the TMA engine
+        // reads the first chunk out of the staging tile (the second chunk has to wait for that anyway)
         float s1 = 0.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) s1 += v[0][j] + v[1][j];
@@ -709,20 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         }
         if (row_ok) e.stats_out[static_cast<int64_t>(m) * 8 + tile_n * 2 + half] = make_float2(mean_i, m2_i);
         if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 9);
-        uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
-        const bool group_full = (m0 + q * 32 + 32 <= e.M);
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int nb = n0 + half * 32 + 64 * h2;
-          if (group_full) {
-            stage_pair_chunk(v[h2], tb, lane, &p.st_hi, &p.st_lo, nb, m0 + q * 32);
-          } else if (row_ok) {  // ragged last row group: per-thread stores
-            __half* oh = static_cast<__half*>(e.out_hi) + static_cast<int64_t>(m) * e.lds + nb;
-            __half* ol = static_cast<__half*>(e.out_lo) + static_cast<int64_t>(m) * e.lds + nb;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ptx::split_f16(v[h2][j], oh[j], ol[j]);
-          }
-        }
+        store_chunk(1);
         if (tcount == 0 && warp_idx == 2 && lane == 0) stamp(p, 6);
         continue;
       }
