@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
 
   int total_iters = 0;
   for (int s = 0; s < p.num_segs; ++s) total_iters += p.seg_kblocks[s];
+  // Split-K (GemmParams::k_splits, masked / GroupNorm variant only): work item w = tile * S + split; split s runs the K
+  // iterations [s * per_split, min(total_iters, (s + 1) * per_split)).  S == 1 everywhere else: one item per tile.
+  const int S = (EPI == 2 && p.k_splits > 1) ? p.k_splits : 1;
+  const int per_split = (total_iters + S - 1) / S;
+  const int num_work = num_tiles * S;
 
   if (warp_idx == 0 && lane == 0) {
     for (int s = 0; s < p.num_segs; ++s) {
@@ -297,14 +302,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   // The B operand is a weight matrix that no kernel of the chain writes: the producer thread puts the B tiles of the first
   // pipeline stages in flight BEFORE it waits for the previous grid, so the pipeline fill (~1 us) overlaps that grid's tail.
   int prefetched = 0;
-  if (warp_idx == 0 && lane == 0 && !p.multicast_a && static_cast<int>(blockIdx.x) < num_tiles) {
-    const int n0 = (static_cast<int>(blockIdx.x) % tiles_n) * BLOCK_N;
-    prefetched = total_iters < Cfg::kStages ? total_iters : Cfg::kStages;
+  if (warp_idx == 0 && lane == 0 && !p.multicast_a && static_cast<int>(blockIdx.x) < num_work) {
+    const int tile0 = static_cast<int>(blockIdx.x) / S;
+    const int it_b = (static_cast<int>(blockIdx.x) - tile0 * S) * per_split;
+    const int cnt = (total_iters < it_b + per_split ? total_iters : it_b + per_split) - it_b;
+    const int n0 = (tile0 % tiles_n) * BLOCK_N;
+    prefetched = cnt < Cfg::kStages ? cnt : Cfg::kStages;
     for (int i = 0; i < prefetched; ++i) {
       uint8_t* st = smem + i * Cfg::kStageBytes;
       ptx::mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
-      ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[i], i * kElemK, n0);
-      if (PASSES == 3) ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[i], i * kElemK, n0);
+      ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[i], (it_b + i) * kElemK, n0);
+      if (PASSES == 3)
+        ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[i], (it_b + i) * kElemK, n0);
     }
   }
   ptx::pdl_wait_prior_grid();
@@ -314,20 +323,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     if (lane == 0) {
       int it = 0, stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / S;
         const int m0 = (tile / tiles_n) * kGemmBlockM;
         const int n0 = (tile % tiles_n) * BLOCK_N;
-        int kcol = 0;
-        for (int s = 0; s < p.num_segs; ++s) {
-          const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
-          const int nkb = p.seg_kblocks[s];
-          for (int kb = 0; kb < nkb; ++kb, ++it, kcol += kElemK) {
+        const int it_b = (w - tile * S) * per_split;
+        const int it_e = total_iters < it_b + per_split ? total_iters : it_b + per_split;
+        // (segment, K block) of the item's first iteration; the packed weight column advances by one K block per iteration
+        int s = 0, kb = it_b;
+        while (s + 1 < p.num_segs && kb >= p.seg_kblocks[s]) kb -= p.seg_kblocks[s], ++s;
+        int kcol = it_b * kElemK;
+        for (int i = it_b; i < it_e; ++i, ++it, kcol += kElemK) {
+          {
+            const int row = m0 * p.seg_row_mul[s] + p.seg_row_shift[s];
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             if (it < prefetched) {  // B of this stage is already in flight (see above): only A is missing
               if (it == 0) stamp(p, 2);
               ptx::tma_load_2d(st, &p.a_hi[s], &full_bar[stage], kb * kElemK, row);
               if (PASSES == 3) ptx::tma_load_2d(st + Cfg::kABytes, &p.a_lo[s], &full_bar[stage], kb * kElemK, row);
               if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+              if (++kb == p.seg_kblocks[s]) kb = 0, ++s;
               continue;
             }
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -352,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
               }
             }
             if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+            if (++kb == p.seg_kblocks[s]) kb = 0, ++s;
           }
         }
       }
@@ -367,13 +383,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
       };
       int it = 0, tcount = 0, stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tcount) {
         const int acc_stage = tcount % Cfg::kAccStages;
         const uint32_t acc_phase = (tcount / Cfg::kAccStages) & 1;
         ptx::mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after_sync();
         const uint32_t acc = tmem_base + static_cast<uint32_t>(acc_stage * Cfg::kAccCols);
-        for (int ki = 0; ki < total_iters; ++ki, ++it) {
+        const int it_b = (w % S) * per_split;
+        const int n_it = (total_iters < it_b + per_split ? total_iters : it_b + per_split) - it_b;
+        for (int ki = 0; ki < n_it; ++ki, ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           if (it == 0) stamp(p, 3);
           ptx::tc_fence_after_sync();
@@ -578,7 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 11);
       }
     }
-    for (int tile_idx = blockIdx.x; EPI != 4 && tile_idx < num_tiles; tile_idx += gridDim.x, ++tcount) {
+    for (int wi = blockIdx.x; EPI != 4 && wi < num_work; wi += gridDim.x, ++tcount) {
+      const int tile_idx = wi / S;
+      // split-K: the partial tile of split s goes to output rows m + s * split_row_stride
+      const int split_rows = (wi - tile_idx * S) * (EPI == 2 ? p.split_row_stride : 0);
       const int m0 = (tile_idx / tiles_n) * kGemmBlockM;
       const int n0 = (tile_idx % tiles_n) * BLOCK_N;
       const int acc_stage = tcount % Cfg::kAccStages;
@@ -591,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         clip = m / e.clip_rows;
         row_real = (m - clip * e.clip_rows) < e.clip_valid;
       }
-      const int64_t orow = static_cast<int64_t>(m) * e.out_row_mul + e.out_row_add;
+      const int64_t orow = static_cast<int64_t>(m) * e.out_row_mul + e.out_row_add + split_rows;
       const float bias_row = (e.bias != nullptr && e.bias_per_row && row_ok) ? __ldg(e.bias + m) : 0.0f;
 
       // stage this tile's per-column vectors while the MMA warp is still accumulating.  Single-buffered: the first barrier
@@ -819,10 +840,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
           __syncwarp();
           if (lane == 0 && !(p.debug_flags & 2)) {
             if (e.out != nullptr) {
-              ptx::tma_store_2d(&p.st_out, tb, nb, m0 + q * 32);
+              ptx::tma_store_2d(&p.st_out, tb, nb, m0 + q * 32 + split_rows);
             } else {
-              ptx::tma_store_2d(&p.st_hi, tb, nb, m0 + q * 32);
-              ptx::tma_store_2d(&p.st_lo, tb + 2048, nb, m0 + q * 32);
+              ptx::tma_store_2d(&p.st_hi, tb, nb, m0 + q * 32 + split_rows);
+              ptx::tma_store_2d(&p.st_lo, tb + 2048, nb, m0 + q * 32 + split_rows);
             }
             ptx::bulk_commit();
           }
@@ -921,7 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
                 if (!LEAN && e.clip_rows > 0) real = (mr % e.clip_rows) < e.clip_valid;
                 if (real) w.x += res[rr].x, w.y += res[rr].y, w.z += res[rr].z, w.w += res[rr].w;
               }
-              const int64_t orr = static_cast<int64_t>(mr) * e.out_row_mul + e.out_row_add;
+              const int64_t orr = static_cast<int64_t>(mr) * e.out_row_mul + e.out_row_add + split_rows;
               if (e.out != nullptr) *reinterpret_cast<float4*>(e.out + orr * e.ldo + nb + tc) = w;
               if (e.out_hi != nullptr) {
                 if (KIND == kKindF16) {
@@ -1104,7 +1125,17 @@ cudaError_t launch_cfg(const GemmParams& p, int m_rows, int n_cols, cudaStream_t
   GemmParams q = p;
   q.grid_m_rows = m_rows;
   q.grid_n_cols = n_cols;
-  const int tiles = ((n_cols + BLOCK_N - 1) / BLOCK_N) * ((m_rows + kGemmBlockM - 1) / kGemmBlockM);
+  int tiles = ((n_cols + BLOCK_N - 1) / BLOCK_N) * ((m_rows + kGemmBlockM - 1) / kGemmBlockM);
+  if (q.k_splits > 1) {  // split-K: masked / GroupNorm variant, fp32 partials only, every K range non-empty
+    int iters = 0;
+    for (int s = 0; s < q.num_segs; ++s) iters += q.seg_kblocks[s];
+    const int per = (iters + q.k_splits - 1) / q.k_splits;
+    if (plain || q.out == nullptr || q.out_hi != nullptr || q.bias != nullptr || q.residual != nullptr || q.gn_stats != nullptr ||
+        q.act != kActNone || q.out_row_mul != 1 || q.out_row_add != 0 || q.multicast_a || (q.k_splits - 1) * per >= iters ||
+        q.split_row_stride < m_rows)
+      return cudaErrorInvalidValue;
+    tiles *= q.k_splits;
+  }
   cudaLaunchConfig_t cfg{};
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.stats_out != nullptr) grid -= grid % 4;  // a CTA keeps its column tile: tile % 4 == blockIdx % 4 on every round

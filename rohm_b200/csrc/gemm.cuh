@@ -138,6 +138,13 @@ struct alignas(64) GemmParams {
   // developer experiments (tools/gemm_selftest only; results are wrong when set): bit 0 = the epilogue only drains TMEM (no
   // staging, no stores), bit 1 = staging writes but no TMA stores.  Slots 16.. of debug_ts: "all MMAs of tile i issued".
   int debug_flags;
+  // Split-K (TrajNet convolutions on the deep pyramid levels; masked / GroupNorm epilogue variant only): the K iterations of
+  // every output tile are cut into `k_splits` contiguous ranges, one work item each, so that a level with 6 to 22 row tiles
+  // still fills the 148 SMs with 128-wide tiles.  Split s stores its fp32 partial tile (no bias, no statistics) at output row
+  // m + s * split_row_stride of `out`; the consumer (gn_mish_split_kernel) adds the partials in a fixed order, so the result is
+  // deterministic.  0 / 1 = off.  Every range must be non-empty: (k_splits - 1) * ceil(iters / k_splits) < iters.
+  int k_splits;
+  int split_row_stride;
   // filled in by launch_gemm: extent of the tile grid
   int grid_m_rows;
   int grid_n_cols;

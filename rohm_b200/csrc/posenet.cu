@@ -31,6 +31,10 @@ namespace {
 __global__ void pack_tokens_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int C,
                                    int T, int S, int ld, int f16) {
   __shared__ float tile[32][33];
+  // programmatic dependent launch: the embedding GEMM behind this kernel may set itself up (barriers, TMEM, weight tiles)
+  // while it runs; as a dependent (a no-op for a plain launch) nothing is read before the previous kernel has completed
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -59,6 +63,8 @@ __global__ void pack_tokens_kernel(const float* __restrict__ x, float* __restric
 __global__ void unpack_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ cond_traj,
                                      float* __restrict__ out, int C, int Cout, int traj, int T, int S, int ldt) {
   __shared__ float tile[32][33];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();  // the output-head GEMM has completed
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // c0 indexes the Cout predicted channels
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -97,6 +103,8 @@ __global__ void time_token_gather_kernel(const int64_t* __restrict__ timesteps, 
                                          int table_rows, float* __restrict__ X, float* __restrict__ Xh,
                                          float* __restrict__ Xl, int S, int D, int f16, unsigned int* __restrict__ zero_buf,
                                          int zero_n) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();  // the embedding GEMM (which also writes row (b, 0)) has completed
   const int b = blockIdx.x;
   // once per forward: clear the arrival counters of the fused LayerNorm epilogues (GemmParams::ln_count)
   if (b == 0)
@@ -789,6 +797,7 @@ struct AttnTcParams {
   __half* ctx_lo;
   int S, D, H;
   float scale;
+  int split_qk_load;             // Q / K arrive on two barriers, one per 64-wide head-dim half (ROHM_B200_ATTN_SPLIT_LOAD=0: one)
   unsigned long long* debug_ts;  // developer instrumentation: CTA 0 records %globaltimer at 12 milestones
 };
 constexpr int kAtKeys = 160;                  // padded key count = UMMA N of the S product
@@ -808,7 +817,7 @@ __device__ __forceinline__ void at_stamp(const AttnTcParams& p, int slot) {
 
 __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t at_smem_raw[];
-  __shared__ uint64_t qk_full, v_full, s_full[2], p_ready[2], o_full[2];
+  __shared__ uint64_t qk_full[2], v_full, s_full[2], p_ready[2], o_full[2];  // qk_full: one barrier per 64-wide head-dim half
   __shared__ uint32_t tmem_base_smem;
   __shared__ float at_red[2][128][4];  // [tile][row][{max, max, sum, sum} of the two column halves]
   const uint32_t raw_addr = ptx::smem_u32(at_smem_raw);
@@ -822,7 +831,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.qkv_hi), ptx::prefetch_tmap(&p.qkv_lo), ptx::prefetch_tmap(&p.st_hi), ptx::prefetch_tmap(&p.st_lo);
-    ptx::mbar_init(&qk_full, 1), ptx::mbar_init(&v_full, 1);
+    ptx::mbar_init(&qk_full[0], 1), ptx::mbar_init(&qk_full[1], 1), ptx::mbar_init(&v_full, 1);
     for (int t = 0; t < 2; ++t) ptx::mbar_init(&s_full[t], 1), ptx::mbar_init(&p_ready[t], 8), ptx::mbar_init(&o_full[t], 1);
     ptx::fence_barrier_init();
   }
@@ -842,12 +851,15 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
 
   if (warp_idx == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(&qk_full, 8 * kAtQKBuf);
-      for (int pl = 0; pl < 2; ++pl) {
-        const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
-        for (int kc = 0; kc < 2; ++kc) {
-          ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, h_ * 128 + kc * 64, row0);
-          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, &qk_full, p.D + h_ * 128 + kc * 64, row0);
+      // head dims 0..63 of Q and K (both planes) first, on their own barrier: the S MMAs over that half start while the
+      // second half is still on its way (the load is bound by the SM's L2 read port: 148 KB at ~64 B/clk = 1.3 us)
+      for (int kc = 0; kc < 2; ++kc) {
+        uint64_t* bar = &qk_full[p.split_qk_load ? kc : 0];
+        if (p.split_qk_load || kc == 0) ptx::mbar_expect_tx(bar, (p.split_qk_load ? 4 : 8) * kAtQKBuf);
+        for (int pl = 0; pl < 2; ++pl) {
+          const CUtensorMap* m = pl == 0 ? &p.qkv_hi : &p.qkv_lo;
+          ptx::tma_load_2d(Qb + (pl * 2 + kc) * kAtQKBuf, m, bar, h_ * 128 + kc * 64, row0);
+          ptx::tma_load_2d(Kb + (pl * 2 + kc) * kAtQKBuf, m, bar, p.D + h_ * 128 + kc * 64, row0);
         }
       }
       // V lands on top of K: wait until every S MMA has read it
@@ -863,7 +875,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc(/*F16*/ 0, 128, kAtKeys);
       constexpr uint32_t idesc_o = ptx::make_idesc(/*F16*/ 0, 128, 128, /*b_mn_major=*/true);
-      ptx::mbar_wait(&qk_full, 0);
+      ptx::mbar_wait(&qk_full[0], 0);
       at_stamp(p, 2);
       ptx::tc_fence_after_sync();
       for (int t = 0; t < ntiles; ++t) {
@@ -871,6 +883,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 16 head-dim columns per instruction
           const int kc = ks >> 2;
+          if (t == 0 && ks == 4 && p.split_qk_load) {  // second head-dim half (its own barrier when the load is split)
+            ptx::mbar_wait(&qk_full[1], 0);
+            ptx::tc_fence_after_sync();
+          }
           const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
           const uint64_t a_hi = ptx::make_desc_kmajor<128>(ptx::smem_u32(Qb + (0 * 2 + kc) * kAtQKBuf + t * kAtTile)) + ko;
           const uint64_t a_lo = ptx::make_desc_kmajor<128>(ptx::smem_u32(Qb + (1 * 2 + kc) * kAtQKBuf + t * kAtTile)) + ko;
@@ -1707,6 +1723,8 @@ extern "C" int rohm_posenet_create(rohm_ctx* ctx, const rohm_posenet_weights* w,
       pn->attn_tc.ctx_hi = reinterpret_cast<__half*>(pn->CTXh), pn->attn_tc.ctx_lo = reinterpret_cast<__half*>(pn->CTXl);
       pn->attn_tc.D = D, pn->attn_tc.H = pn->H;
       pn->attn_tc.scale = 1.0f / sqrtf(static_cast<float>(dh));
+      const char* sq = getenv("ROHM_B200_ATTN_SPLIT_LOAD");
+      pn->attn_tc.split_qk_load = (sq == nullptr || sq[0] != '0') ? 1 : 0;
     }
     if (ea != cudaSuccess) {
       delete pn;
@@ -1785,15 +1803,16 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
 
   dim3 grid((T + 31) / 32, (pn->C + 31) / 32, B);
   prof_begin(pn, kCatOther, st);
-  pack_tokens_kernel<<<grid, dim3(32, 8), 0, st>>>(x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p,
-                                                   pn->kind == kKindF16 ? 1 : 0);
+  const bool pdl = pn->use_pdl && !pn->profiling;
+  ROHM_CUDA(ctx, launch_chain(pack_tokens_kernel, grid, dim3(32, 8), 0, st, pdl, x_t, pn->Ain_h, pn->Ain_l, pn->C, T, S, pn->Kin_p,
+                              pn->kind == kKindF16 ? 1 : 0));
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
   if ((rc = run_gemm(pn, pn->g_in, pn->w_in, rows, st)) != ROHM_OK) return rc;
   prof_begin(pn, kCatOther, st);
-  time_token_gather_kernel<<<B, 128, 0, st>>>(timesteps, pn->time_table, pn->pe_len, pn->X, pn->Xh, pn->Xl, S, D,
-                                              pn->kind == kKindF16 ? 1 : 0, nullptr, 0);
+  ROHM_CUDA(ctx, launch_chain(time_token_gather_kernel, dim3(B), dim3(128), 0, st, pdl, timesteps, pn->time_table, pn->pe_len,
+                              pn->X, pn->Xh, pn->Xl, S, D, pn->kind == kKindF16 ? 1 : 0, nullptr, 0));
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
@@ -1815,8 +1834,8 @@ static int forward_launches(rohm_posenet* pn, const float* x_t, const int64_t* t
   if ((rc = run_gemm(pn, pn->g_out, pn->w_out, rows, st)) != ROHM_OK) return rc;
   dim3 grid_o((T + 31) / 32, (pn->Cout + 31) / 32, B);
   prof_begin(pn, kCatOther, st);
-  unpack_tokens_kernel<<<grid_o, dim3(32, 8), 0, st>>>(pn->OUT, pn->cond_traj, out, pn->C, pn->Cout, pn->traj, T, S,
-                                                      pn->Cout);
+  ROHM_CUDA(ctx, launch_chain(unpack_tokens_kernel, grid_o, dim3(32, 8), 0, st, pdl, pn->OUT, pn->cond_traj, out, pn->C, pn->Cout,
+                              pn->traj, T, S, pn->Cout));
   prof_end(pn, st);
   ROHM_CUDA(ctx, cudaGetLastError());
   pn->launches++;
@@ -1877,7 +1896,7 @@ static int build_forward_graph(rohm_posenet* pn, const float* x_t, const int64_t
   if (rc == ROHM_OK && step != nullptr) {
     const int64_t clip_elems = static_cast<int64_t>(pn->C) * T;
     if (launch_ddpm_step_philox(out, x_t, step->x_next, clip_elems * B, clip_elems, step->coef_row, step->seed, step->offset,
-                                step->G, step->iters, cs) != cudaSuccess)
+                                step->G, step->iters, cs, pn->use_pdl) != cudaSuccess)
       rc = fail(ctx, ROHM_ERR_CUDA, "ddpm step launch failed during capture");
     pn->launches++;
   }
@@ -1931,7 +1950,7 @@ static int forward_or_step(rohm_posenet* pn, const float* x_t, const int64_t* ti
     if (rc == ROHM_OK && step != nullptr) {
       const int64_t clip_elems = static_cast<int64_t>(pn->C) * T;
       ROHM_CUDA(ctx, launch_ddpm_step_philox(out, x_t, step->x_next, clip_elems * B, clip_elems, step->coef_row, step->seed,
-                                             step->offset, step->G, step->iters, st));
+                                             step->offset, step->G, step->iters, st, pn->use_pdl && !pn->profiling));
       pn->launches++;
     }
     return rc;

@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(kThreads) ddpm_step_philox_kernel(const float*
                                                                     const float* __restrict__ coef, int64_t coef_stride,
                                                                     unsigned long long seed, unsigned long long offset,
                                                                     int64_t G, int iters) {
+  // as the programmatic dependent of the denoiser's last kernel (posenet.cu): the Philox state is set up while that kernel
+  // drains; x0 / x_t are read after it has completed.  A no-op for a plain launch.
   const int64_t vidx = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (vidx >= G) return;
   curandStatePhilox4_32_10_t state;
-  curand_init(seed, static_cast<unsigned long long>(vidx), offset, &state);
+  if (vidx < G) curand_init(seed, static_cast<unsigned long long>(vidx), offset, &state);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (vidx >= G) return;
   for (int k = 0; k < iters; ++k) {
     const float4 nz = curand_normal4(&state);
     const float z[4] = {nz.x, nz.y, nz.z, nz.w};
@@ -208,10 +211,16 @@ int ddpm_step_philox_policy(rohm_ctx* ctx, int64_t numel, int64_t* G, int* iters
 }
 cudaError_t launch_ddpm_step_philox(const float* x0, const float* x_t, float* out, int64_t numel, int64_t clip_elems,
                                     const float* coef, unsigned long long seed, unsigned long long offset, int64_t G, int iters,
-                                    cudaStream_t st) {
-  ddpm_step_philox_kernel<<<static_cast<unsigned>(G / kThreads), kThreads, 0, st>>>(
-      x0, x_t, nullptr, nullptr, 0, out, numel, clip_elems, coef, static_cast<int64_t>(0), seed, offset, G, iters);
-  return cudaGetLastError();
+                                    cudaStream_t st, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(G / kThreads)), cfg.blockDim = dim3(kThreads), cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, ddpm_step_philox_kernel, x0, x_t, static_cast<const float*>(nullptr),
+                            static_cast<const float*>(nullptr), 0, out, numel, clip_elems, coef, static_cast<int64_t>(0), seed,
+                            offset, G, iters);
 }
 }  // namespace rohm
 

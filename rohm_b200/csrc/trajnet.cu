@@ -174,6 +174,106 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
   }
 }
 
+// The same for a split-K convolution: one CTA per (clip, group).  y = bias + the `splits` fp32 partials (added in split order:
+// deterministic) of the group's T x (C / groups) real elements is formed once into shared memory, its mean / variance are
+// reduced inside the CTA (the producing GEMM writes no statistics), then out = Mish(GroupNorm(y)) [+ tp] [+ r1] [+ r2]; pad
+// rows are written as zeros.  part: [splits][split_stride] floats, each a [B * Tp, C] matrix.
+__global__ void __launch_bounds__(256) gn_mish_split_kernel(const float* __restrict__ part, int splits, int64_t split_stride,
+                                                            const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ tp,
+                                                            int tp_stride, const float* __restrict__ r1,
+                                                            const float* __restrict__ r2, float* __restrict__ out,
+                                                            float* __restrict__ out_hi, float* __restrict__ out_lo, int C, int Tp,
+                                                            int T, int groups, int f16) {
+  extern __shared__ float4 gn_vals[];  // T * (C / groups) / 4
+  __shared__ double red[2][8];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+  const int b = blockIdx.x / groups, g = blockIdx.x - b * groups;
+  const int gs = C / groups, gs4 = gs / 4;
+  const int n4 = T * gs4;
+  const int c4 = C / 4;
+  const int64_t row0 = static_cast<int64_t>(b) * Tp;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int t = i / gs4;
+    const int c = g * gs + (i - t * gs4) * 4;
+    const int64_t idx = (row0 + t) * c4 + c / 4;
+    float4 v = *reinterpret_cast<const float4*>(bias + c);
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + idx);
+      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+    }
+    gn_vals[i] = v;
+    s1 += static_cast<double>(v.x) + static_cast<double>(v.y) + static_cast<double>(v.z) + static_cast<double>(v.w);
+    s2 += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+          static_cast<double>(v.w) * v.w;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
+  __syncthreads();
+  s1 = 0.0, s2 = 0.0;
+  for (int wv = 0; wv < static_cast<int>(blockDim.x >> 5); ++wv) s1 += red[0][wv], s2 += red[1][wv];
+  const double n = static_cast<double>(gs) * static_cast<double>(T);
+  const double mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float mu = static_cast<float>(mean);
+  const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  auto put = [&](int64_t idx, const float4& v) {
+    if (out != nullptr) reinterpret_cast<float4*>(out)[idx] = v;
+    if (out_hi != nullptr && f16) {
+      uint2 h, l;
+      ptx::split_f16x4(v, h, l);
+      reinterpret_cast<uint2*>(out_hi)[idx] = h;
+      reinterpret_cast<uint2*>(out_lo)[idx] = l;
+    } else if (out_hi != nullptr) {
+      float4 h, l;
+      h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
+      l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+      reinterpret_cast<float4*>(out_hi)[idx] = h;
+      reinterpret_cast<float4*>(out_lo)[idx] = l;
+    }
+  };
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int t = i / gs4;
+    const int c = g * gs + (i - t * gs4) * 4;
+    const int64_t idx = (row0 + t) * c4 + c / 4;
+    const float4 x = gn_vals[i];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float4 v;
+    v.x = mish_f((x.x - mu) * rstd * ga.x + be.x);
+    v.y = mish_f((x.y - mu) * rstd * ga.y + be.y);
+    v.z = mish_f((x.z - mu) * rstd * ga.z + be.z);
+    v.w = mish_f((x.w - mu) * rstd * ga.w + be.w);
+    if (tp != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(tp + static_cast<int64_t>(b) * tp_stride + c);
+      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+    }
+    if (r1 != nullptr) {
+      const float4 a = reinterpret_cast<const float4*>(r1)[idx];
+      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+    }
+    if (r2 != nullptr) {
+      const float4 a = reinterpret_cast<const float4*>(r2)[idx];
+      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+    }
+    put(idx, v);
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < (Tp - T) * gs4; i += blockDim.x) {  // pad rows: the next convolution's zero padding
+    const int t = T + i / gs4;
+    const int c = g * gs + (i % gs4) * 4;
+    put((row0 + t) * c4 + c / 4, zero);
+  }
+}
+
 // padded-clip rows [B * Tp, ld] -> compact [B, T, C]
 __global__ void unpack_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int Tp, int C, int ld,
                                    int64_t total) {
@@ -228,6 +328,11 @@ struct Conv {
   float* bias = nullptr;
   int level_out = 0;   // GEMM rows are the rows of this level (for transposed convs: the INPUT level)
   double* stats = nullptr;
+  // split-K (deep pyramid levels): `splits` fp32 partial results of [split_rows, Cout] each in the branch's partial scratch;
+  // bias, statistics and GroupNorm move into gn_mish_split_kernel
+  int splits = 1;
+  float* partial = nullptr;
+  int64_t split_rows = 0;
 };
 
 }  // namespace
@@ -257,6 +362,10 @@ struct rohm_trajnet {
   // RTB-internal scratch, one set per concurrently running branch (0: U-Net, 1: TrajControl)
   float *scratchY[2] = {nullptr, nullptr}, *scratchRes[2] = {nullptr, nullptr};
   Act scratchA[2];
+  // Split-K partials of the GroupNorm'd convolutions (ROHM_B200_TRAJ_SPLITK=0 turns split-K off): kMaxSplits x the largest
+  // 128-row-padded [rows, C] level matrix, per branch
+  float* scratchSplit[2] = {nullptr, nullptr};
+  bool use_splitk = true;
   // The forward is captured as a graph with parallel branches: the TrajControl branch next to the U-Net encoder, every
   // block's 1x1 residual convolution next to its conv1 -> GroupNorm -> conv2 chain.  None of these GEMMs fills the 148 SMs
   // (11 to 96 tiles), so running them side by side shortens the critical path at no cost.  ROHM_B200_TRAJ_PARALLEL=0: serial.
@@ -363,6 +472,40 @@ int pick_bn(int N, int64_t rows) {
   return best;
 }
 
+// Split-K choice for a GroupNorm'd convolution (conv1 / conv2 of a ResidualTemporalBlock) with `stages` K blocks.  On the deep
+// levels a tile's K loop (40 to 80 stages of 64 columns) is the whole launch: cutting it into S ranges lets 128-wide tiles
+// (the cheapest per flop: the A stripe is read once per 128 columns) still cover the 148 SMs.  Model, in us: one wave of work
+// items costs (stages / S) * t_stage(bn) + fixed launch / prologue / epilogue; the consumer reads S partials.
+// Returns S (1 = keep the single-pass path and pick_bn's width); *bn_out is only written when S > 1.
+constexpr int kMaxSplits = 8;
+int pick_split(int N, int64_t rows, int stages, int* bn_out) {
+  if (stages < 16 || N % 32 != 0) return 1;
+  const int64_t m_tiles = (rows + kGemmBlockM - 1) / kGemmBlockM;
+  auto t_stage = [](int bn) { return bn == 128 ? 0.55 : bn == 64 ? 0.42 : 0.36; };
+  const double t_fixed = 4.0, t_partial = 0.4;
+  auto cost = [&](int bn, int S) {
+    const int64_t items = m_tiles * ((N + bn - 1) / bn) * S;
+    const int per = (stages + S - 1) / S;
+    return static_cast<double>((items + 147) / 148) * (per * t_stage(bn) + t_fixed) + (S > 1 ? S * t_partial : 0.0);
+  };
+  const int bn1 = pick_bn(N, rows);
+  const double base = cost(bn1, 1);
+  int best_bn = bn1, best_S = 1;
+  double best = base;
+  for (int bn : {128, 64}) {
+    if (bn > N || N % bn != 0) continue;
+    for (int S = 2; S <= kMaxSplits; ++S) {
+      const int per = (stages + S - 1) / S;
+      if (per < 4 || (S - 1) * per >= stages) continue;  // at least 4 stages per item, no empty range
+      const double c = cost(bn, S);
+      if (c < best) best = c, best_bn = bn, best_S = S;
+    }
+  }
+  if (best_S == 1 || best > 0.85 * base) return 1;  // not worth a second code path
+  *bn_out = best_bn;
+  return best_S;
+}
+
 // Builds one convolution as a segmented GEMM.
 //   kind 0: Conv1d(ks, stride, pad = ks/2 for stride 1, 1 for the stride-2 k3 downsample)
 //   kind 1 / 2: even / odd output phase of ConvTranspose1d(k4, s2, p1) (GEMM rows = input level rows)
@@ -395,6 +538,11 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   PackedWeight& pw = cv.w;
   pw.N = Cout, pw.K = Ktot, pw.Kp = Ktot;
   pw.block_n = pick_bn(Cout, rows_of(tn, (kind == 0) ? out->level : srcs[0]->level));
+  if (with_stats && tn->use_splitk && kind == 0 && stride == 1 && out->f32 != nullptr && out->hi == nullptr && out->ld == Cout) {
+    int bn = pw.block_n;
+    cv.splits = pick_split(Cout, rows_of(tn, out->level), Ktot / kblk, &bn);
+    if (cv.splits > 1) pw.block_n = bn;
+  }
   pw.Np = static_cast<int>(round_up(Cout, pw.block_n));
   pw.kind = tn->kind;
   pw.hi = static_cast<float*>(tn->pool.bytes(static_cast<int64_t>(pw.Np) * Ktot * gemm_elem_bytes(tn->kind)));
@@ -446,7 +594,16 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   g.out_row_add = (kind == 2) ? 1 : 0;
   if (out->f32) g.out = out->f32, g.ldo = out->ld;
   if (out->hi) g.out_hi = out->hi, g.out_lo = out->lo, g.lds = out->ld;
-  if (with_stats) {
+  if (cv.splits > 1) {
+    // partial results instead of the block's fp32 scratch; bias / statistics / GroupNorm happen in gn_mish_split_kernel
+    const int br = name.rfind("controlnet.", 0) == 0 ? 1 : 0;
+    cv.split_rows = static_cast<int64_t>(round_up(rows_of(tn, row_level), kGemmBlockM));
+    cv.partial = tn->scratchSplit[br];
+    g.out = cv.partial, g.ldo = Cout, g.out_hi = nullptr, g.out_lo = nullptr;
+    g.bias = nullptr;
+    g.k_splits = cv.splits;
+    g.split_row_stride = static_cast<int>(cv.split_rows);
+  } else if (with_stats) {
     const int64_t need = static_cast<int64_t>(tn->max_batch) * kGroups * 2;
     if (tn->stats_used + need > tn->stats_cap) return fail(tn->ctx, ROHM_ERR_INVALID, "stats arena too small");
     cv.stats = tn->stats_arena + tn->stats_used;
@@ -458,7 +615,7 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   (void)out_compact_T;
   // fp32-only or fp16-pair-only outputs with the identity row map leave through TMA bulk stores (the transposed-conv phases
   // and the few convolutions that write both forms keep the per-thread epilogue)
-  if (gemm_enable_tma_store(&g, rows_of(tn, row_level), tn->kind) != 0)
+  if (gemm_enable_tma_store(&g, cv.splits > 1 ? cv.splits * cv.split_rows : rows_of(tn, row_level), tn->kind) != 0)
     return fail(tn->ctx, ROHM_ERR_CUDA, "store tensor map failed for conv '%s'", name.c_str());
   tn->convs[name] = cv;
   return ROHM_OK;
@@ -525,6 +682,17 @@ int run_gn(rohm_trajnet* tn, const std::string& conv_name, const std::string& no
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = tn->use_pdl ? 1 : 0;
+  if (cv.splits > 1) {  // split-K convolution: partials + bias -> statistics -> GroupNorm / Mish, one CTA per (clip, group)
+    cfg.gridDim = dim3(static_cast<unsigned>(B * kGroups));
+    cfg.dynamicSmemBytes = static_cast<size_t>(tn->Tl[level]) * (C / kGroups) * sizeof(float);
+    ROHM_CUDA(tn->ctx, cudaLaunchKernelEx(&cfg, gn_mish_split_kernel, static_cast<const float*>(cv.partial), cv.splits,
+                                          static_cast<int64_t>(cv.split_rows) * C, static_cast<const float*>(cv.bias),
+                                          static_cast<const float*>(nb.first), static_cast<const float*>(nb.second), tp,
+                                          tn->tp_total, r1, r2, out->f32, out->hi, out->lo, C, tn->Tp[level], tn->Tl[level],
+                                          kGroups, tn->kind == kKindF16 ? 1 : 0));
+    tn->launches++;
+    return ROHM_OK;
+  }
   ROHM_CUDA(tn->ctx, cudaLaunchKernelEx(&cfg, gn_mish_kernel, static_cast<const float*>(y), static_cast<const double*>(cv.stats),
                                         static_cast<const float*>(nb.first), static_cast<const float*>(nb.second), tp, tn->tp_total,
                                         r1, r2, out->f32, out->hi, out->lo, C, tn->Tp[level], tn->Tl[level], kGroups, total4,
@@ -631,6 +799,20 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
     tn->scratchA[br].lo = tn->pool.floats(max_elems);
   }
   if (const char* env = getenv("ROHM_B200_TRAJ_PARALLEL")) tn->parallel = env[0] != '0';
+  if (const char* env = getenv("ROHM_B200_TRAJ_SPLITK")) tn->use_splitk = env[0] != '0';
+  if (tn->use_splitk) {
+    int64_t max_padded = 0;
+    const int widths[kLevels] = {m / 8, m / 4, m / 2, m, 2 * m};
+    for (int l = 0; l < kLevels; ++l)
+      max_padded = std::max<int64_t>(max_padded, static_cast<int64_t>(round_up(rows_of(tn, l), kGemmBlockM)) * widths[l]);
+    for (int br = 0; br < 2; ++br) {
+      tn->scratchSplit[br] = tn->pool.floats(kMaxSplits * max_padded);
+      if (!tn->scratchSplit[br]) {
+        delete tn;
+        return fail(ctx, ROHM_ERR_CUDA, "split-K scratch alloc failed");
+      }
+    }
+  }
   tn->stats_cap = static_cast<int64_t>(64) * max_batch * kGroups * 2;
   tn->stats_arena = static_cast<double*>(tn->pool.bytes(tn->stats_cap * static_cast<int64_t>(sizeof(double))));
   if (!tn->scratchY[1] || !tn->scratchRes[1] || !tn->scratchA[1].hi || !tn->scratchA[1].lo || !tn->scratchY[0] ||
