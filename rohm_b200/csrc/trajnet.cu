@@ -174,6 +174,48 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
   }
 }
 
+// One float4 of an activation in its stored forms: fp32 and / or the hi/lo operand pair of the next convolution.
+__device__ __forceinline__ void store_act4(float* out, float* out_hi, float* out_lo, int64_t idx, const float4& v, int f16) {
+  if (out != nullptr) reinterpret_cast<float4*>(out)[idx] = v;
+  if (out_hi != nullptr && f16) {
+    uint2 h, l;
+    ptx::split_f16x4(v, h, l);
+    reinterpret_cast<uint2*>(out_hi)[idx] = h;
+    reinterpret_cast<uint2*>(out_lo)[idx] = l;
+  } else if (out_hi != nullptr) {
+    float4 h, l;
+    h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
+    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    reinterpret_cast<float4*>(out_hi)[idx] = h;
+    reinterpret_cast<float4*>(out_lo)[idx] = l;
+  }
+}
+
+// Split-K convolution without a GroupNorm behind it (the stride-2 downsampling convolutions): out = bias + the partials (in
+// split order) on real rows, 0 on pad rows.  4 channels per thread over the [B * Tp, C] output.
+__global__ void __launch_bounds__(256) sum_split_kernel(const float* __restrict__ part, int splits, int64_t split_stride,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        float* __restrict__ out_hi, float* __restrict__ out_lo, int C, int Tp,
+                                                        int T, int64_t total4, int f16) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = C / 4;
+  const int64_t row = i / c4;
+  const int c = static_cast<int>(i - row * c4) * 4;
+  const int t = static_cast<int>(row % Tp);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < T) {
+    v = *reinterpret_cast<const float4*>(bias + c);
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + i);
+      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+    }
+  }
+  store_act4(out, out_hi, out_lo, i, v, f16);
+}
+
 // The same for a split-K convolution: one CTA per (clip, group).  y = bias + the `splits` fp32 partials (added in split order:
 // deterministic) of the group's T x (C / groups) real elements is formed once into shared memory, its mean / variance are
 // reduced inside the CTA (the producing GEMM writes no statistics), then out = Mish(GroupNorm(y)) [+ tp] [+ r1] [+ r2]; pad
@@ -225,21 +267,6 @@ __global__ void __launch_bounds__(256) gn_mish_split_kernel(const float* __restr
   var = var < 0.0 ? 0.0 : var;
   const float mu = static_cast<float>(mean);
   const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
-  auto put = [&](int64_t idx, const float4& v) {
-    if (out != nullptr) reinterpret_cast<float4*>(out)[idx] = v;
-    if (out_hi != nullptr && f16) {
-      uint2 h, l;
-      ptx::split_f16x4(v, h, l);
-      reinterpret_cast<uint2*>(out_hi)[idx] = h;
-      reinterpret_cast<uint2*>(out_lo)[idx] = l;
-    } else if (out_hi != nullptr) {
-      float4 h, l;
-      h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
-      l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
-      reinterpret_cast<float4*>(out_hi)[idx] = h;
-      reinterpret_cast<float4*>(out_lo)[idx] = l;
-    }
-  };
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     const int t = i / gs4;
     const int c = g * gs + (i - t * gs4) * 4;
@@ -264,13 +291,13 @@ __global__ void __launch_bounds__(256) gn_mish_split_kernel(const float* __restr
       const float4 a = reinterpret_cast<const float4*>(r2)[idx];
       v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
     }
-    put(idx, v);
+    store_act4(out, out_hi, out_lo, idx, v, f16);
   }
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = threadIdx.x; i < (Tp - T) * gs4; i += blockDim.x) {  // pad rows: the next convolution's zero padding
     const int t = T + i / gs4;
     const int c = g * gs + (i % gs4) * 4;
-    put((row0 + t) * c4 + c / 4, zero);
+    store_act4(out, out_hi, out_lo, (row0 + t) * c4 + c / 4, zero, f16);
   }
 }
 
@@ -333,6 +360,8 @@ struct Conv {
   int splits = 1;
   float* partial = nullptr;
   int64_t split_rows = 0;
+  bool sum_after = false;  // no GroupNorm behind it: sum_split_kernel writes `sum_out` right after the GEMM
+  Act sum_out;
 };
 
 }  // namespace
@@ -478,7 +507,7 @@ int pick_bn(int N, int64_t rows) {
 // items costs (stages / S) * t_stage(bn) + fixed launch / prologue / epilogue; the consumer reads S partials.
 // Returns S (1 = keep the single-pass path and pick_bn's width); *bn_out is only written when S > 1.
 constexpr int kMaxSplits = 8;
-int pick_split(int N, int64_t rows, int stages, int* bn_out) {
+int pick_split(int N, int64_t rows, int stages, int* bn_out, double extra_us = 0.0) {
   if (stages < 16 || N % 32 != 0) return 1;
   const int64_t m_tiles = (rows + kGemmBlockM - 1) / kGemmBlockM;
   auto t_stage = [](int bn) { return bn == 128 ? 0.55 : bn == 64 ? 0.42 : 0.36; };
@@ -501,7 +530,7 @@ int pick_split(int N, int64_t rows, int stages, int* bn_out) {
       if (c < best) best = c, best_bn = bn, best_S = S;
     }
   }
-  if (best_S == 1 || best > 0.85 * base) return 1;  // not worth a second code path
+  if (best_S == 1 || best + extra_us > 0.85 * base) return 1;  // not worth a second code path (extra_us: an added launch)
   *bn_out = best_bn;
   return best_S;
 }
@@ -538,10 +567,14 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   PackedWeight& pw = cv.w;
   pw.N = Cout, pw.K = Ktot, pw.Kp = Ktot;
   pw.block_n = pick_bn(Cout, rows_of(tn, (kind == 0) ? out->level : srcs[0]->level));
-  if (with_stats && tn->use_splitk && kind == 0 && stride == 1 && out->f32 != nullptr && out->hi == nullptr && out->ld == Cout) {
+  const bool can_split = tn->use_splitk && kind == 0 && out->ld == Cout && Cout % 4 == 0;
+  if (can_split && ((with_stats && stride == 1 && out->f32 != nullptr && out->hi == nullptr) || (!with_stats && ks > 1))) {
     int bn = pw.block_n;
-    cv.splits = pick_split(Cout, rows_of(tn, out->level), Ktot / kblk, &bn);
-    if (cv.splits > 1) pw.block_n = bn;
+    cv.splits = pick_split(Cout, rows_of(tn, out->level), Ktot / kblk, &bn, with_stats ? 0.0 : 4.0);
+    if (cv.splits > 1) {
+      pw.block_n = bn;
+      if (!with_stats) cv.sum_after = true, cv.sum_out = *out;
+    }
   }
   pw.Np = static_cast<int>(round_up(Cout, pw.block_n));
   pw.kind = tn->kind;
@@ -596,7 +629,7 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
   if (out->hi) g.out_hi = out->hi, g.out_lo = out->lo, g.lds = out->ld;
   if (cv.splits > 1) {
     // partial results instead of the block's fp32 scratch; bias / statistics / GroupNorm happen in gn_mish_split_kernel
-    const int br = name.rfind("controlnet.", 0) == 0 ? 1 : 0;
+    const int br = (name.rfind("controlnet.", 0) == 0 || name[0] == 'k') ? 1 : 0;  // TrajControl convolutions: "controlnet.*", "k*"
     cv.split_rows = static_cast<int64_t>(round_up(rows_of(tn, row_level), kGemmBlockM));
     cv.partial = tn->scratchSplit[br];
     g.out = cv.partial, g.ldo = Cout, g.out_hi = nullptr, g.out_lo = nullptr;
@@ -666,8 +699,52 @@ int run_conv(rohm_trajnet* tn, const std::string& name, int B, cudaStream_t st) 
   Conv& cv = it->second;
   const int rows = B * tn->Tp[cv.level_out];
   cv.g.M = rows;
-  ROHM_CUDA(tn->ctx, launch_gemm(cv.g, rows, cv.w.N, cv.w.block_n, tn->passes, st, tn->use_pdl, tn->kind));
+  // developer instrumentation: ROHM_B200_TRAJ_TS=<conv name>[,<conv name>...] prints CTA 0's %globaltimer stamps of that convolution's third
+  // launch outside stream capture (use with ROHM_B200_GRAPH=0)
+  unsigned long long* d_ts = nullptr;
+  if (const char* want = getenv("ROHM_B200_TRAJ_TS")) {
+    static std::map<std::string, int> ts_calls;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool listed = ("," + std::string(want) + ",").find("," + name + ",") != std::string::npos;  // comma-separated names
+    if (listed && cap == cudaStreamCaptureStatusNone && ++ts_calls[name] == 3 &&
+        cudaMalloc(&d_ts, 32 * sizeof(unsigned long long)) == cudaSuccess) {
+      cudaMemset(d_ts, 0, 32 * sizeof(unsigned long long));
+      cudaStreamSynchronize(st);
+    }
+  }
+  GemmParams launch_params = cv.g;
+  launch_params.debug_ts = d_ts;
+  ROHM_CUDA(tn->ctx, launch_gemm(launch_params, rows, cv.w.N, cv.w.block_n, tn->passes, st, tn->use_pdl, tn->kind));
   tn->launches++;
+  if (d_ts != nullptr) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d_ts);
+    int iters = 0;
+    for (int sgi = 0; sgi < cv.g.num_segs; ++sgi) iters += cv.g.seg_kblocks[sgi];
+    fprintf(stderr, "conv %s (rows %d, N %d, block_n %d, %d K blocks, %d splits) CTA0 timeline (ns): setup %llu | first A tma %llu | "
+            "first stage landed %llu | item0 mma issued %llu | item0 acc ready %llu | item0 epilogue done %llu | all mma issued %llu | "
+            "last item drained %llu | stores done %llu | end %llu\n", name.c_str(), rows, cv.w.N, cv.w.block_n, iters, cv.splits,
+            h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0],
+            h[7] - h[0]);
+  }
+  if (cv.sum_after) {
+    const int C = cv.w.N;
+    const int64_t total4 = static_cast<int64_t>(rows) * C / 4;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>((total4 + 255) / 256)), cfg.blockDim = dim3(256), cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = tn->use_pdl ? 1 : 0;
+    ROHM_CUDA(tn->ctx, cudaLaunchKernelEx(&cfg, sum_split_kernel, static_cast<const float*>(cv.partial), cv.splits,
+                                          static_cast<int64_t>(cv.split_rows) * C, static_cast<const float*>(cv.bias),
+                                          cv.sum_out.f32, cv.sum_out.hi, cv.sum_out.lo, C, tn->Tp[cv.level_out],
+                                          tn->Tl[cv.level_out], total4, tn->kind == kKindF16 ? 1 : 0));
+    tn->launches++;
+  }
   return ROHM_OK;
 }
 
