@@ -250,12 +250,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   const int num_work = num_tiles * S;
 
   if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.b_hi);  // needed first: the weight tiles are requested right below
+    if (PASSES == 3) ptx::prefetch_tmap(&p.b_lo);
     for (int s = 0; s < p.num_segs; ++s) {
       ptx::prefetch_tmap(&p.a_hi[s]);
       if (PASSES == 3) ptx::prefetch_tmap(&p.a_lo[s]);
     }
-    ptx::prefetch_tmap(&p.b_hi);
-    if (PASSES == 3) ptx::prefetch_tmap(&p.b_lo);
     for (int i = 0; i < Cfg::kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], p.multicast_a ? 2 : 1);  // multicast: the slot is refilled by both CTAs of the pair
@@ -267,6 +267,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
     if (EPI == 3)
       for (int i = 0; i < kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_barrier_init();
+  }
+  // The B operand is a weight matrix that no kernel of the chain writes: the producer thread puts the B tiles of the first
+  // pipeline stages in flight right after it has initialised the barriers -- BEFORE the CTA-wide setup barrier (TMEM
+  // allocation, epilogue parameters) and before it waits for the previous grid -- so the pipeline fill (~1 us, tensor-map
+  // fetch included) overlaps both the setup and that grid's tail.
+  int prefetched = 0;
+  if (warp_idx == 0 && lane == 0 && !p.multicast_a && static_cast<int>(blockIdx.x) < num_work) {
+    const int tile0 = static_cast<int>(blockIdx.x) / S;
+    const int it_b = (static_cast<int>(blockIdx.x) - tile0 * S) * per_split;
+    const int cnt = (total_iters < it_b + per_split ? total_iters : it_b + per_split) - it_b;
+    const int n0 = (tile0 % tiles_n) * BLOCK_N;
+    prefetched = cnt < Cfg::kStages ? cnt : Cfg::kStages;
+    for (int i = 0; i < prefetched; ++i) {
+      uint8_t* st = smem + i * Cfg::kStageBytes;
+      ptx::mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+      ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[i], (it_b + i) * kElemK, n0);
+      if (PASSES == 3)
+        ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[i], (it_b + i) * kElemK, n0);
+    }
   }
   if (warp_idx == 1) {
     ptx::tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
@@ -299,23 +318,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
   // prologue then overlaps this kernel's tail; it blocks in its own griddepcontrol.wait until this grid has completed
   // and flushed), then order everything below after the previous kernel.
   ptx::pdl_launch_dependents();
-  // The B operand is a weight matrix that no kernel of the chain writes: the producer thread puts the B tiles of the first
-  // pipeline stages in flight BEFORE it waits for the previous grid, so the pipeline fill (~1 us) overlaps that grid's tail.
-  int prefetched = 0;
-  if (warp_idx == 0 && lane == 0 && !p.multicast_a && static_cast<int>(blockIdx.x) < num_work) {
-    const int tile0 = static_cast<int>(blockIdx.x) / S;
-    const int it_b = (static_cast<int>(blockIdx.x) - tile0 * S) * per_split;
-    const int cnt = (total_iters < it_b + per_split ? total_iters : it_b + per_split) - it_b;
-    const int n0 = (tile0 % tiles_n) * BLOCK_N;
-    prefetched = cnt < Cfg::kStages ? cnt : Cfg::kStages;
-    for (int i = 0; i < prefetched; ++i) {
-      uint8_t* st = smem + i * Cfg::kStageBytes;
-      ptx::mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
-      ptx::tma_load_2d(st + Cfg::kSplit * Cfg::kABytes, &p.b_hi, &full_bar[i], (it_b + i) * kElemK, n0);
-      if (PASSES == 3)
-        ptx::tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &p.b_lo, &full_bar[i], (it_b + i) * kElemK, n0);
-    }
-  }
   ptx::pdl_wait_prior_grid();
 
   if (warp_idx == 0) {

@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
   }
 }
 
+constexpr int kMaxSplitsDev = 8;  // most K ranges a convolution is cut into (= kMaxSplits of the host-side choice)
+
 // One float4 of an activation in its stored forms: fp32 and / or the hi/lo operand pair of the next convolution.
 __device__ __forceinline__ void store_act4(float* out, float* out_hi, float* out_lo, int64_t idx, const float4& v, int f16) {
   if (out != nullptr) reinterpret_cast<float4*>(out)[idx] = v;
@@ -207,11 +209,14 @@ __global__ void __launch_bounds__(256) sum_split_kernel(const float* __restrict_
   const int t = static_cast<int>(row % Tp);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t < T) {
+    float4 a[kMaxSplitsDev];
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplitsDev; ++sp)
+      if (sp < splits) a[sp] = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + i);
     v = *reinterpret_cast<const float4*>(bias + c);
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + i);
-      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
-    }
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplitsDev; ++sp)
+      if (sp < splits) v.x += a[sp].x, v.y += a[sp].y, v.z += a[sp].z, v.w += a[sp].w;
   }
   store_act4(out, out_hi, out_lo, i, v, f16);
 }
@@ -241,11 +246,16 @@ __global__ void __launch_bounds__(256) gn_mish_split_kernel(const float* __restr
     const int t = i / gs4;
     const int c = g * gs + (i - t * gs4) * 4;
     const int64_t idx = (row0 + t) * c4 + c / 4;
+    // all partials of this float4 are requested before the first is used (one L2 round trip instead of `splits`); they are
+    // still added in split order
+    float4 a[kMaxSplitsDev];
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplitsDev; ++sp)
+      if (sp < splits) a[sp] = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + idx);
     float4 v = *reinterpret_cast<const float4*>(bias + c);
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(part + sp * split_stride) + idx);
-      v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
-    }
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplitsDev; ++sp)
+      if (sp < splits) v.x += a[sp].x, v.y += a[sp].y, v.z += a[sp].z, v.w += a[sp].w;
     gn_vals[i] = v;
     s1 += static_cast<double>(v.x) + static_cast<double>(v.y) + static_cast<double>(v.z) + static_cast<double>(v.w);
     s2 += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
@@ -360,6 +370,7 @@ struct Conv {
   int splits = 1;
   float* partial = nullptr;
   int64_t split_rows = 0;
+  bool gn_in_kernel = false;  // un-split GroupNorm'd convolution whose statistics are taken by gn_mish_split_kernel (partial = y)
   bool sum_after = false;  // no GroupNorm behind it: sum_split_kernel writes `sum_out` right after the GEMM
   Act sum_out;
 };
@@ -395,6 +406,10 @@ struct rohm_trajnet {
   // 128-row-padded [rows, C] level matrix, per branch
   float* scratchSplit[2] = {nullptr, nullptr};
   bool use_splitk = true;
+  // GroupNorm statistics inside the GroupNorm kernel (one CTA per (clip, group), the split-K consumer with one "partial") for
+  // every GroupNorm'd convolution, instead of per-chunk double atomics in the GEMM epilogue: the epilogue of a small
+  // convolution drops from 3.4-5.0 us to 1.7-2.2 us (CTA timelines, ROHM_B200_TRAJ_TS).  ROHM_B200_TRAJ_GN_EPILOGUE=1: old path.
+  bool gn_in_kernel = true;
   // The forward is captured as a graph with parallel branches: the TrajControl branch next to the U-Net encoder, every
   // block's 1x1 residual convolution next to its conv1 -> GroupNorm -> conv2 chain.  None of these GEMMs fills the 148 SMs
   // (11 to 96 tiles), so running them side by side shortens the critical path at no cost.  ROHM_B200_TRAJ_PARALLEL=0: serial.
@@ -506,12 +521,12 @@ int pick_bn(int N, int64_t rows) {
 // (the cheapest per flop: the A stripe is read once per 128 columns) still cover the 148 SMs.  Model, in us: one wave of work
 // items costs (stages / S) * t_stage(bn) + fixed launch / prologue / epilogue; the consumer reads S partials.
 // Returns S (1 = keep the single-pass path and pick_bn's width); *bn_out is only written when S > 1.
-constexpr int kMaxSplits = 8;
+constexpr int kMaxSplits = kMaxSplitsDev;
 int pick_split(int N, int64_t rows, int stages, int* bn_out, double extra_us = 0.0) {
   if (stages < 16 || N % 32 != 0) return 1;
   const int64_t m_tiles = (rows + kGemmBlockM - 1) / kGemmBlockM;
-  auto t_stage = [](int bn) { return bn == 128 ? 0.55 : bn == 64 ? 0.42 : 0.36; };
-  const double t_fixed = 4.0, t_partial = 0.4;
+  auto t_stage = [](int bn) { return bn == 128 ? 0.60 : bn == 64 ? 0.42 : 0.41; };  // measured (ROHM_B200_TRAJ_TS): A-bound below 128
+  const double t_fixed = 4.5, t_partial = 0.4;
   auto cost = [&](int bn, int S) {
     const int64_t items = m_tiles * ((N + bn - 1) / bn) * S;
     const int per = (stages + S - 1) / S;
@@ -636,6 +651,10 @@ int make_conv(rohm_trajnet* tn, const std::string& name, const std::string& wkey
     g.bias = nullptr;
     g.k_splits = cv.splits;
     g.split_row_stride = static_cast<int>(cv.split_rows);
+  } else if (with_stats && tn->gn_in_kernel && out->f32 != nullptr && out->hi == nullptr && out->ld == Cout && Cout % (4 * kGroups) == 0) {
+    cv.gn_in_kernel = true;  // y = conv without bias; bias + statistics + GroupNorm in gn_mish_split_kernel (one "partial")
+    cv.partial = out->f32;
+    g.bias = nullptr;
   } else if (with_stats) {
     const int64_t need = static_cast<int64_t>(tn->max_batch) * kGroups * 2;
     if (tn->stats_used + need > tn->stats_cap) return fail(tn->ctx, ROHM_ERR_INVALID, "stats arena too small");
@@ -759,7 +778,7 @@ int run_gn(rohm_trajnet* tn, const std::string& conv_name, const std::string& no
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = tn->use_pdl ? 1 : 0;
-  if (cv.splits > 1) {  // split-K convolution: partials + bias -> statistics -> GroupNorm / Mish, one CTA per (clip, group)
+  if (cv.splits > 1 || cv.gn_in_kernel) {  // partial(s) + bias -> statistics -> GroupNorm / Mish, one CTA per (clip, group)
     cfg.gridDim = dim3(static_cast<unsigned>(B * kGroups));
     cfg.dynamicSmemBytes = static_cast<size_t>(tn->Tl[level]) * (C / kGroups) * sizeof(float);
     ROHM_CUDA(tn->ctx, cudaLaunchKernelEx(&cfg, gn_mish_split_kernel, static_cast<const float*>(cv.partial), cv.splits,
@@ -877,6 +896,7 @@ extern "C" int rohm_trajnet_create(rohm_ctx* ctx, int n_params, const char* cons
   }
   if (const char* env = getenv("ROHM_B200_TRAJ_PARALLEL")) tn->parallel = env[0] != '0';
   if (const char* env = getenv("ROHM_B200_TRAJ_SPLITK")) tn->use_splitk = env[0] != '0';
+  if (const char* env = getenv("ROHM_B200_TRAJ_GN_EPILOGUE")) tn->gn_in_kernel = env[0] == '0';
   if (tn->use_splitk) {
     int64_t max_padded = 0;
     const int widths[kLevels] = {m / 8, m / 4, m / 2, m, 2 * m};
