@@ -215,6 +215,13 @@ ROHM_API void rohm_body_destroy(rohm_body* bd);
  * more than 16 bones).  Introspection only. */
 ROHM_API int rohm_body_uses_fused_lbs(const rohm_body* bd);
 
+/* Row pitch, in floats, of the `vertices` buffers handed to rohm_body_forward / rohm_body_from_repr[_layout] from now on:
+ * frame n's vertices start at vertices + n * pitch.  0 (the default) = dense [N, V, 3] as smplx returns them
+ * (reference: body_model output `.vertices`, test_amass_full.py:392-428).  A pitch that is a multiple of 4 floats (>= 3 V;
+ * 16-byte-aligned buffer) lets the fused launch write the vertices with TMA bulk stores instead of 4-byte stores (3 V =
+ * 31425 floats is not 16-byte divisible); only valid when rohm_body_uses_fused_lbs() is 1. */
+ROHM_API int rohm_body_set_vertex_pitch(rohm_body* bd, int64_t pitch_floats);
+
 /* SMPLX.forward with jaw / eyes / hands / expression = 0 (exactly how RoHM calls it): global_orient [N,3], body_pose
  * [N,63] axis-angle, betas [N,10], transl [N,3] -> joints [N, num_joints, 3] (first num_joints <= 55 posed joints +
  * transl; NULL to skip) and vertices [N, V, 3] (NULL to skip). */

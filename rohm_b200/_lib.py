@@ -65,6 +65,7 @@ SIGNATURES = {
     "rohm_body_create": (_i, [_p, _p, _p, _i, _p, _p, _p, C.POINTER(C.c_int), _i, _i64, _i, _i, C.POINTER(_p)]),
     "rohm_body_destroy": (None, [_p]),
     "rohm_body_uses_fused_lbs": (_i, [_p]),
+    "rohm_body_set_vertex_pitch": (_i, [_p, _i64]),
     "rohm_body_forward": (_i, [_p, _p, _p, _p, _p, _i64, _p, _i, _p, _p]),
     "rohm_body_from_repr": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p]),
     "rohm_body_from_repr_layout": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _i, _p, _p]),

@@ -51,6 +51,19 @@ class BodyKernels:
                                            self.max_frames, int(with_vertices), precision, C.byref(handle))
         _lib.check(rc, self.ctx)
         self.handle = handle
+        # The fused blend + skinning launch writes the vertices with TMA bulk stores when every frame's row starts on a 16-byte
+        # boundary: 3 V = 31425 floats does not, so the buffer gets 3 pad floats per frame and the caller a strided [N, V, 3]
+        # view of it (same values, `.contiguous()` gives smplx's dense layout).  ROHM_B200_LBS_TMA_STORE=0: dense rows, 4-byte stores.
+        self.vertex_pitch = 0
+        if with_vertices and self.lib.rohm_body_uses_fused_lbs(handle) and os.environ.get("ROHM_B200_LBS_TMA_STORE", "1") != "0":
+            pitch = -(-self.V * 3 // 4) * 4
+            _lib.check(self.lib.rohm_body_set_vertex_pitch(handle, pitch), self.ctx)
+            self.vertex_pitch = pitch
+
+    def _vertex_buffer(self, n):
+        if not self.vertex_pitch:
+            return torch.empty(n, self.V, 3, device=self.device)
+        return torch.empty(n, self.vertex_pitch, device=self.device)[:, :self.V * 3].view(n, self.V, 3)
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -69,7 +82,7 @@ class BodyKernels:
         f = lambda t, w: t.reshape(N, w).to(device=self.device, dtype=torch.float32).contiguous()
         go, bp, be, tr = f(global_orient, 3), f(body_pose, 63), f(betas, 10), f(transl, 3)
         joints = torch.empty(N, num_joints, 3, device=self.device)
-        verts = torch.empty(N, self.V, 3, device=self.device) if want_vertices else None
+        verts = self._vertex_buffer(N) if want_vertices else None
         rc = self.lib.rohm_body_forward(self.handle, C.c_void_p(go.data_ptr()), C.c_void_p(bp.data_ptr()),
                                         C.c_void_p(be.data_ptr()), C.c_void_p(tr.data_ptr()), N,
                                         C.c_void_p(joints.data_ptr()), num_joints,
@@ -85,7 +98,7 @@ class BodyKernels:
         else:
             B, _, _, T = x.shape
         joints = torch.empty(B * T, num_joints, 3, device=self.device)
-        verts = torch.empty(B * T, self.V, 3, device=self.device) if want_vertices else None
+        verts = self._vertex_buffer(B * T) if want_vertices else None
         rc = self.lib.rohm_body_from_repr_layout(self.handle, C.c_void_p(x.data_ptr()), int(bool(channels_last)),
                                                  C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), B, T,
                                                  C.c_void_p(joints.data_ptr()), num_joints,

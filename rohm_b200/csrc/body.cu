@@ -859,6 +859,21 @@ extern "C" void rohm_body_destroy(rohm_body* bd) { delete bd; }
 
 extern "C" int rohm_body_uses_fused_lbs(const rohm_body* bd) { return bd != nullptr && bd->fused_lbs ? 1 : 0; }
 
+extern "C" int rohm_body_set_vertex_pitch(rohm_body* bd, int64_t pitch_floats) {
+  if (bd == nullptr) return ROHM_ERR_INVALID;
+  if (pitch_floats == 0) {
+    bd->vertex_pitch = 0;
+    return ROHM_OK;
+  }
+  if (!bd->fused_lbs)
+    return fail(bd->ctx, ROHM_ERR_STATE, "rohm_body_set_vertex_pitch: only the fused blend + skinning launch writes pitched rows");
+  if (pitch_floats < static_cast<int64_t>(bd->V) * 3 || pitch_floats % 4 != 0 || pitch_floats > 0x7fffffff)
+    return fail(bd->ctx, ROHM_ERR_INVALID, "rohm_body_set_vertex_pitch: pitch %lld must be a multiple of 4 floats and >= 3 V = %d",
+                static_cast<long long>(pitch_floats), bd->V * 3);
+  bd->vertex_pitch = pitch_floats;
+  return ROHM_OK;
+}
+
 // SMPLX.forward as RoHM calls it (jaw / eyes / hands / expression zero).  global_orient [N,3], body_pose [N,63]
 // (axis-angle), betas [N,10], transl [N,3] -> joints [N, num_joints<=55, 3] and (optionally) vertices [N, V, 3].
 extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, const float* body_pose, const float* betas,
@@ -885,6 +900,16 @@ extern "C" int rohm_body_forward(rohm_body* bd, const float* global_orient, cons
     GemmParams g = bd->g_skin;
     g.M = static_cast<int>(N);
     g.out = vertices;
+    if (bd->vertex_pitch != 0) {
+      // pitched output (rohm_body_set_vertex_pitch): rows start on 16-byte boundaries, so the tile leaves through TMA stores
+      if ((reinterpret_cast<uintptr_t>(vertices) & 15u) != 0)
+        return fail(ctx, ROHM_ERR_INVALID, "rohm_body_forward: a pitched vertex buffer must be 16-byte aligned");
+      g.ldo = static_cast<int>(bd->vertex_pitch);
+      if (make_store_tmap(&g.st_out, vertices, N, static_cast<int64_t>(bd->V) * 3, bd->vertex_pitch, false, kGemmBlockM) != 0)
+        return fail(ctx, ROHM_ERR_CUDA, "rohm_body_forward: vertex store tensor map failed");
+      g.st_hi = g.st_out, g.st_lo = g.st_out;
+      g.tma_store = 1;
+    }
     static int ts_calls = 0;
     unsigned long long* d_ts = nullptr;
     if (getenv("ROHM_B200_LBS_TS") != nullptr && ++ts_calls == 3) {  // developer instrumentation: CTA 0's %globaltimer stamps

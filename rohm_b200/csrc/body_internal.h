@@ -30,6 +30,7 @@ struct rohm_body {
   // two-kernel path (blend GEMM -> v_posed -> skin_kernel), which is also the fallback.
   rohm::GemmParams g_skin{};
   bool fused_lbs = false;
+  int64_t vertex_pitch = 0;  // floats between the vertex rows of two frames in the caller's buffer; 0 = dense (3 V)
   int64_t a_frame_stride = 0;  // fused path: A is [55][12][a_frame_stride] (frames contiguous); two-kernel path: [frames][55][12]
   int* skin_nb = nullptr;
   int* skin_bone = nullptr;

@@ -566,10 +566,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tile_kernel(const __grid_con
         }
         if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 9);
         if (has_next) publish_tables(buf ^ 1, nw0, nw1, nbone, nnb);
+        // TMA-store variant: the previous tile's bulk stores (issued by this thread) have finished reading the staging tile
+        if (e.tma_store && warp_idx == 2 && lane == 0) ptx::bulk_wait_read_all();
         // one barrier: the next tile's tables are visible, and every warp has finished storing the previous tile's rows out of
         // the staging tile that is overwritten below
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32));
         if (has_next) request_transforms(buf ^ 1, (next / tiles_n) * kGemmBlockM);
+        if (e.tma_store) {
+          // Output rows with a 16-byte-multiple pitch (rohm_body_set_vertex_pitch): the tile leaves through TMA.  Staging = three
+          // 128-row x 128-byte SWIZZLE_128B boxes (32 columns each; 16-byte chunk c of row r at slot c ^ (r & 7): the row-per-thread
+          // 16-byte writes are conflict-free); one thread issues the three bulk tensor stores, which clip the ragged last row /
+          // column tile themselves.  The 96 epilogue-issued 4-byte loads / stores per thread of the path below disappear.
+          uint8_t* const sb = reinterpret_cast<uint8_t*>(stg);
+          const int r = q * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const int cc = 12 * half + j;  // 16-byte chunk of the 96-column row
+            *reinterpret_cast<float4*>(sb + (cc >> 3) * (kGemmBlockM * 128) + r * 128 + (((cc & 7) ^ (r & 7)) << 4)) =
+                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          ptx::fence_proxy_async();
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32));
+          if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 10);
+          if (warp_idx == 2 && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (n0 + 32 * j < e.N) ptx::tma_store_2d(&p.st_out, sb + j * (kGemmBlockM * 128), n0 + 32 * j, m0);
+            ptx::bulk_commit();
+          }
+          if (tcount == 1 && warp_idx == 2 && lane == 0) stamp(p, 11);
+          continue;
+        }
         // transpose through the CTA-wide staging tile: the output row pitch (3 V floats) is not a multiple of 16 bytes, so
         // neither TMA nor vector stores apply; lanes along the columns give fully coalesced 4-byte stores
         {
@@ -1185,13 +1212,14 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return static_cast<int>(r);
 }
 
-static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half) {
+static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half,
+                            int box_rows = 32) {
   auto fn = get_encode_fn();
   if (fn == nullptr) return -1;
   const int eb = half ? 2 : 4;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * eb};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estride[2] = {1u, 1u};
   return static_cast<int>(fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                              const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1199,8 +1227,8 @@ static int encode_store_map(CUtensorMap* map, const void* base, int64_t rows, in
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
 }
 
-int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half) {
-  return encode_store_map(map, base, rows, cols, ld, half);
+int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half, int box_rows) {
+  return encode_store_map(map, base, rows, cols, ld, half, box_rows);
 }
 
 int gemm_enable_multicast(GemmParams* p, const void* a_hi, const void* a_lo, int64_t rows, int64_t cols, int64_t ld, int n_cols,

@@ -167,9 +167,9 @@ int gemm_enable_tma_store(GemmParams* p, int64_t rows_total, int kind);
 int gemm_enable_multicast(GemmParams* p, const void* a_hi, const void* a_lo, int64_t rows, int64_t cols, int64_t ld, int n_cols,
                           int block_n, int kind);
 
-// Tensor map for 32 x 32-element TMA store boxes over a row-major [rows, cols] matrix with pitch ld: fp32 with
+// Tensor map for box_rows x 32-element TMA store boxes over a row-major [rows, cols] matrix with pitch ld: fp32 with
 // SWIZZLE_128B (128-byte box rows) or fp16 with SWIZZLE_64B (64-byte box rows).  Returns 0 or a CUresult.
-int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half);
+int make_store_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool half, int box_rows = 32);
 
 // Launches the tile kernel.  block_n in {32, 64, 96, 128}; passes in {1, 3} (kKindF16: 3 only).
 // grid = ceil(M_tiles) x ceil(N_tiles) where M_tiles covers `m_rows` GEMM rows.

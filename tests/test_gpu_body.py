@@ -57,6 +57,30 @@ def test_zero_pose_and_edge_rotations(body, cuda_device):
     assert float((out.vertices.cpu().double() - v).abs().max()) < 5e-5
 
 
+def test_pitched_tma_vertex_store_equals_the_dense_store(body, cuda_device, monkeypatch):
+    """The fused LBS launch writes pitched rows (16-byte-aligned frames, TMA bulk stores; the default) and dense rows (4-byte
+    stores, ROHM_B200_LBS_TMA_STORE=0) from the same accumulators: bit-identical vertices, ragged last row / column tiles
+    included (N = 1, 129, 300 frames; 3 V = 327 x 96 + 33 columns)."""
+    from rohm_b200.body_model import BodyKernels
+    bm, _ = body
+    monkeypatch.setenv("ROHM_B200_LBS_TMA_STORE", "1")
+    k_tma = BodyKernels(bm, cuda_device, 300, True)
+    monkeypatch.setenv("ROHM_B200_LBS_TMA_STORE", "0")
+    k_dense = BodyKernels(bm, cuda_device, 300, True)
+    assert k_dense.vertex_pitch == 0
+    if not k_tma.vertex_pitch:
+        pytest.skip("fused LBS launch not in use on this handle")
+    assert k_tma.vertex_pitch % 4 == 0 and k_tma.vertex_pitch >= 3 * k_tma.V
+    for N in (1, 129, 300):
+        go, bp, be, tr = (t.to(cuda_device) for t in _params(N, 40 + N))
+        j1, v1 = k_tma.forward(go, bp, be, tr, True)
+        j2, v2 = k_dense.forward(go, bp, be, tr, True)
+        assert v1.shape == v2.shape == (N, k_tma.V, 3) and v2.is_contiguous()
+        assert v1.data_ptr() % 16 == 0 and (N == 1 or v1.stride() == (k_tma.vertex_pitch, 3, 1))  # torch normalises size-1 strides
+        assert torch.equal(v1, v2) and torch.equal(j1, j2)
+        assert torch.equal(v1.contiguous().view(N, -1), v2.view(N, -1))
+
+
 def _motion(B, T, seed, dseed=3):
     ds = synthetic.make_dataset('pose', seed=dseed, realistic_std=True)
     return ds, synthetic.plausible_motion(B, T, seed, ds)
