@@ -204,3 +204,36 @@ def test_launch_switches_do_not_change_the_result(nets, cuda_device):
     finally:
         eng.lib.rohm_trajnet_set_option(eng.handle, 0, 1)
         eng.lib.rohm_trajnet_set_option(eng.handle, 1, 1)
+
+
+@pytest.mark.parametrize("env", [{"ROHM_B200_TRAJ_SPLITK": "0"}, {"ROHM_B200_TRAJ_GN_EPILOGUE": "1"},
+                                 {"ROHM_B200_TRAJ_SPLITK": "0", "ROHM_B200_TRAJ_GN_EPILOGUE": "1"}])
+def test_split_k_and_in_kernel_statistics_agree_with_the_single_pass_paths(nets, cuda_device, monkeypatch, env):
+    """The default engine cuts the deep-level convolutions into K ranges (fp32 partials added in split order by the GroupNorm
+    kernel) and takes every GroupNorm's statistics inside that kernel; the engines built with ROHM_B200_TRAJ_SPLITK=0 and / or
+    ROHM_B200_TRAJ_GN_EPILOGUE=1 (one K loop per tile, statistics as double atomics in the GEMM epilogue: the round-2a path)
+    compute the same function with a different summation order: both must agree with the oracle and with each other far
+    inside the parity tolerance, at a batch where the split path uses 3-6 ranges (64 clips) and at one where it uses 8 (2 clips)."""
+    _, sd = nets[True]
+    for B, seed in ((2, 51), (64, 52)):
+        T = 144
+        gen = torch.Generator().manual_seed(seed)
+        b = synthetic.trajnet_batch(B, T, seed, control=True)
+        x = torch.randn(B, T, 13, generator=gen)
+        ts = torch.randint(0, 1000, (B,), generator=gen)
+        batch = {k: v.to(cuda_device) for k, v in b.items()}
+        batch['x_t'] = x.to(cuda_device)
+        default_m, _ = _build(True, cuda_device)
+        out_default = default_m(batch, ts.to(cuda_device)).cpu()
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        other_m, _ = _build(True, cuda_device)
+        out_other = other_m(batch, ts.to(cuda_device)).cpu()
+        for k in env:
+            monkeypatch.delenv(k)
+        scale = float(out_default.abs().max())
+        assert float((out_default - out_other).abs().max()) < 2e-5 * max(1.0, scale)
+        if B == 2:
+            with torch.no_grad():
+                ref = trajnet_oracle.trajnet_forward(sd, x, b['cond'], ts, control_cond=b['control_cond'])
+            assert float((out_default - ref).abs().max()) < TOL and float((out_other - ref).abs().max()) < TOL
