@@ -192,6 +192,13 @@ ROHM_API int rohm_trajnet_set_cond(rohm_trajnet* tn, const float* cond, const fl
 /* TrajNet.forward (trajnet.py:177-275).  x_t: [B, frames, traj_feat_dim]; time: int64 [B]; out: same shape as x_t. */
 ROHM_API int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
                                   void* stream);
+/* One whole ancestral step of the TrajNet sampler (gaussian_diffusion_trajnet.py:388-434, p_sample without cond_fn):
+ * x0_out = TrajNet.forward(x_t, time), x_next = coef1 x0 + coef2 x_t + sigma z with z drawn inside the update kernel exactly as
+ * torch.randn_like(x_t) would draw it from (seed, offset) -- forward and update are ONE graph launch.  Arguments as
+ * rohm_posenet_sample_step (coef_row: device float[8] of the step). */
+ROHM_API int rohm_trajnet_sample_step(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* x0_out, float* x_next,
+                                      const float* coef_row, uint64_t seed, uint64_t offset, uint64_t* offset_increment, int B,
+                                      void* stream);
 ROHM_API int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value); /* 0: CUDA-graph replay, 1: programmatic dependent launch (both default 1) */
 ROHM_API int rohm_trajnet_launches_per_forward(const rohm_trajnet* tn);
 

@@ -426,10 +426,11 @@ struct rohm_trajnet {
   // CUDA graph of one forward per batch size
   struct FwdGraph {
     int B = 0;
+    bool with_step = false;  // forward + Philox-fused ancestral update (rohm_trajnet_sample_step)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t n_pack = nullptr, n_time = nullptr, n_unpack = nullptr;
-    cudaKernelNodeParams p_pack{}, p_time{}, p_unpack{};
+    cudaGraphNode_t n_pack = nullptr, n_time = nullptr, n_unpack = nullptr, n_step = nullptr;
+    cudaKernelNodeParams p_pack{}, p_time{}, p_unpack{}, p_step{};
   };
   std::vector<FwdGraph> graphs;
   bool use_graph = true;
@@ -1212,9 +1213,16 @@ static int trajnet_forward_launches(rohm_trajnet* tn, const float* x_t, const in
   return ROHM_OK;
 }
 
-// TrajNet.forward (trajnet.py:177-275).  x_t: [B, T, traj_dim]; time: int64 [B]; out: [B, T, traj_dim].
-extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
-                                    void* stream) {
+struct TrajStepArgs {  // the ancestral update appended to the forward (rohm_trajnet_sample_step)
+  float* x_next;
+  const float* coef_row;
+  unsigned long long seed, offset;
+  int64_t G;
+  int iters;
+};
+
+static int trajnet_forward_or_step(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B, void* stream,
+                                   const TrajStepArgs* step) {
   if (tn == nullptr) return ROHM_ERR_INVALID;
   rohm_ctx* ctx = tn->ctx;
   rohm::DeviceGuard device_guard__(ctx);
@@ -1224,16 +1232,32 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   ROHM_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
-  if (!tn->use_graph || cap != cudaStreamCaptureStatusNone) return trajnet_forward_launches(tn, x_t, time, out, B, st);
+  const int64_t clip_elems = static_cast<int64_t>(tn->T) * tn->traj_dim;
+  auto launch_step = [&](cudaStream_t s_) {
+    return launch_ddpm_step_philox(out, x_t, step->x_next, clip_elems * B, clip_elems, step->coef_row, step->seed, step->offset,
+                                   step->G, step->iters, s_, tn->use_pdl);
+  };
+  if (!tn->use_graph || cap != cudaStreamCaptureStatusNone) {
+    int rc = trajnet_forward_launches(tn, x_t, time, out, B, st);
+    if (rc == ROHM_OK && step != nullptr) {
+      ROHM_CUDA(ctx, launch_step(st));
+      tn->launches++;
+    }
+    return rc;
+  }
 
   rohm_trajnet::FwdGraph* fg = nullptr;
   for (auto& g : tn->graphs)
-    if (g.B == B) fg = &g;
+    if (g.B == B && g.with_step == (step != nullptr)) fg = &g;
   if (fg == nullptr) {
     if (tn->capture_stream == nullptr) ROHM_CUDA(ctx, cudaStreamCreateWithFlags(&tn->capture_stream, cudaStreamNonBlocking));
     cudaStream_t cs = tn->capture_stream;
     ROHM_CUDA(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     int rc = trajnet_forward_launches(tn, x_t, time, out, B, cs);
+    if (rc == ROHM_OK && step != nullptr) {
+      if (launch_step(cs) != cudaSuccess) rc = fail(ctx, ROHM_ERR_CUDA, "ddpm step launch failed during capture");
+      tn->launches++;
+    }
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
     if (rc != ROHM_OK) {
@@ -1242,7 +1266,7 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
     }
     ROHM_CUDA(ctx, e);
     rohm_trajnet::FwdGraph ng;
-    ng.B = B, ng.graph = graph;
+    ng.B = B, ng.graph = graph, ng.with_step = step != nullptr;
     size_t n = 0;
     ROHM_CUDA(ctx, cudaGraphGetNodes(graph, nullptr, &n));
     std::vector<cudaGraphNode_t> nodes(n);
@@ -1256,8 +1280,9 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
       if (kp.func == reinterpret_cast<void*>(pack_rows_kernel)) ng.n_pack = node, ng.p_pack = kp;
       else if (kp.func == reinterpret_cast<void*>(trajnet_time_kernel)) ng.n_time = node, ng.p_time = kp;
       else if (kp.func == reinterpret_cast<void*>(unpack_rows_kernel)) ng.n_unpack = node, ng.p_unpack = kp;
+      else if (kp.func == const_cast<void*>(ddpm_step_philox_kernel_address())) ng.n_step = node, ng.p_step = kp;
     }
-    if (!ng.n_pack || !ng.n_time || !ng.n_unpack) {
+    if (!ng.n_pack || !ng.n_time || !ng.n_unpack || (step != nullptr && !ng.n_step)) {
       cudaGraphDestroy(graph);
       return fail(ctx, ROHM_ERR_CUDA, "trajnet graph: boundary nodes not found");
     }
@@ -1294,8 +1319,41 @@ extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const in
     kp.kernelParams = args.data();
     ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_unpack, &kp));
   }
+  if (step != nullptr) {  // x0, x_t, out, coef row, Philox seed / offset of this step (ddpm_step_philox_kernel's argument list)
+    cudaKernelNodeParams kp = fg->p_step;
+    std::vector<void*> args(kp.kernelParams, kp.kernelParams + 14);
+    const void* a_x0 = out;
+    void* a_next = step->x_next;
+    const void* a_coef = step->coef_row;
+    unsigned long long a_seed = step->seed, a_off = step->offset;
+    args[0] = &a_x0, args[1] = &a_x, args[5] = &a_next, args[8] = &a_coef, args[10] = &a_seed, args[11] = &a_off;
+    kp.kernelParams = args.data();
+    ROHM_CUDA(ctx, cudaGraphExecKernelNodeSetParams(fg->exec, fg->n_step, &kp));
+  }
   ROHM_CUDA(ctx, cudaGraphLaunch(fg->exec, st));
   return ROHM_OK;
+}
+
+// TrajNet.forward (trajnet.py:177-275).  x_t: [B, T, traj_dim]; time: int64 [B]; out: [B, T, traj_dim].
+extern "C" int rohm_trajnet_forward(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* out, int B,
+                                    void* stream) {
+  return trajnet_forward_or_step(tn, x_t, time, out, B, stream, nullptr);
+}
+
+// One whole ancestral step (gaussian_diffusion_trajnet.py p_sample without cond_fn): forward + in-kernel-noise update as one
+// graph launch; see rohm_posenet_sample_step.
+extern "C" int rohm_trajnet_sample_step(rohm_trajnet* tn, const float* x_t, const int64_t* time, float* x0_out, float* x_next,
+                                        const float* coef_row, uint64_t seed, uint64_t offset, uint64_t* offset_increment,
+                                        int B, void* stream) {
+  if (tn == nullptr) return ROHM_ERR_INVALID;
+  if (x_next == nullptr || coef_row == nullptr)
+    return fail(tn->ctx, ROHM_ERR_INVALID, "rohm_trajnet_sample_step: null pointer");
+  TrajStepArgs sa{x_next, coef_row, seed, offset, 0, 0};
+  unsigned long long inc = 0;
+  int rc = ddpm_step_philox_policy(tn->ctx, static_cast<int64_t>(tn->T) * tn->traj_dim * B, &sa.G, &sa.iters, &inc);
+  if (rc != ROHM_OK) return rc;
+  if (offset_increment != nullptr) *offset_increment = inc;
+  return trajnet_forward_or_step(tn, x_t, time, x0_out, B, stream, &sa);
 }
 
 extern "C" int rohm_trajnet_set_option(rohm_trajnet* tn, int option, int value) {

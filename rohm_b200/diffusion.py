@@ -259,12 +259,32 @@ class _GaussianDiffusion:
         x0, nxt = e.sample_step(x, ts.to(th.int64).contiguous(), self._coef_row(t, step_index))
         return {"sample": nxt, "pred_xstart": x0, "x_t": x}
 
+    def _fused_trajnet_step(self, model, batch, x, t, step_index, model_kwargs):
+        """TrajNet, step without cond_fn, noise from torch's generator, no model kwargs: forward + update as ONE graph launch
+        (rohm_trajnet_sample_step); the same arithmetic and the same noise as the separate launches below."""
+        if self._POSENET or step_index is None or model_kwargs or not self._noise_in_kernel(x):
+            return None
+        model = self._wrap_model(model)  # respaced schedules: step index -> original timestep
+        inner = model.model if isinstance(model, _WrappedModel) else model
+        if not hasattr(inner, "traj_feat_dim") or not hasattr(inner, "_engine") or x.dim() != 3 or self.rescale_timesteps or \
+                t.is_floating_point():
+            return None
+        from .trajnet_engine import prepare
+        batch['x_t'] = x
+        ts = model.map_timesteps(t) if isinstance(model, _WrappedModel) else t
+        e, xc, tsc = prepare(inner, batch, ts)
+        batch['x_t'] = xc
+        x0, nxt = e.sample_step(xc, tsc, self._coef_row(t, step_index))
+        return {"sample": nxt, "pred_xstart": x0, "x_t": xc}
+
     def p_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                  const_noise=False, _step_index=None):
         """x_{t-1} = coef1[t] x0 + coef2[t] x_t + (t != 0) exp(0.5 logvar[t]) noise, x0 = model(batch | x_t, t).
         Returns {'sample', 'pred_xstart', 'x_t'}."""
         if cond_fn is None and not const_noise:
             fused = self._fused_posenet_step(model, batch, x, t, _step_index, model_kwargs)
+            if fused is None:
+                fused = self._fused_trajnet_step(model, batch, x, t, _step_index, model_kwargs)
             if fused is not None:
                 return fused
         x, x0 = self._denoise(model, batch, x, t, model_kwargs)
@@ -299,6 +319,8 @@ class _GaussianDiffusion:
                       (step is None or any(step <= last for _, _, last in _GUIDANCE[grad_type])))
         if not guided_now:
             fused = self._fused_posenet_step(model, batch, x, t, _step_index, model_kwargs)
+            if fused is None and cond_fn is None and not const_noise:
+                fused = self._fused_trajnet_step(model, batch, x, t, _step_index, model_kwargs)
             if fused is not None:
                 return fused
         x, x0 = self._denoise(model, batch, x, t, model_kwargs)

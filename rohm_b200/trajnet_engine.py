@@ -75,6 +75,21 @@ class TrajNetEngine:
         _lib.check(rc, self.ctx)
         return out
 
+    def sample_step(self, x_t, time, coef_row):
+        """One whole ancestral step as one graph launch (rohm_trajnet_sample_step): -> (pred_xstart, x_{t-1}); the noise is
+        what torch.randn_like(x_t) would have drawn (torch's CUDA generator is advanced accordingly)."""
+        from .ops import cuda_generator_state
+        x0, nxt = torch.empty_like(x_t), torch.empty_like(x_t)
+        gen, seed, offset = cuda_generator_state(x_t.device)
+        inc = C.c_uint64(0)
+        rc = self.lib.rohm_trajnet_sample_step(self.handle, C.c_void_p(x_t.data_ptr()), C.c_void_p(time.data_ptr()),
+                                               C.c_void_p(x0.data_ptr()), C.c_void_p(nxt.data_ptr()),
+                                               C.c_void_p(coef_row.data_ptr()), seed, offset, C.byref(inc), x_t.shape[0],
+                                               self._stream())
+        _lib.check(rc, self.ctx)
+        gen.set_offset(offset + int(inc.value))
+        return x0, nxt
+
     @property
     def launches_per_forward(self):
         return int(self.lib.rohm_trajnet_launches_per_forward(self.handle))
@@ -104,6 +119,13 @@ def get_engine(module, B, T, device):
 
 
 def run_forward(module, batch, time):
+    e, x_t, ts = prepare(module, batch, time)
+    return e.forward(x_t, ts)
+
+
+def prepare(module, batch, time):
+    """Argument checks, engine lookup and the step-invariant condition pyramid of one denoiser call: -> (engine, x_t as a
+    contiguous fp32 tensor, time as contiguous int64)."""
     x_t, cond = batch['x_t'], batch['cond']
     if x_t.device.type != "cuda":
         raise RohmB200Error("TrajNet: batch tensors must live on a CUDA device (no CPU path)")
@@ -129,4 +151,4 @@ def run_forward(module, batch, time):
         e.cond_ref, e.cond_version, e.cond_B = cond, cond._version, B
         e.control_ref, e.control_version = control, (control._version if control is not None else -1)
     ts = time.to(device=x_t.device, dtype=torch.int64).contiguous()
-    return e.forward(_f32c(x_t), ts)
+    return e, _f32c(x_t), ts

@@ -237,3 +237,26 @@ def test_split_k_and_in_kernel_statistics_agree_with_the_single_pass_paths(nets,
             with torch.no_grad():
                 ref = trajnet_oracle.trajnet_forward(sd, x, b['cond'], ts, control_cond=b['control_cond'])
             assert float((out_default - ref).abs().max()) < TOL and float((out_other - ref).abs().max()) < TOL
+
+
+def test_fused_sample_step_equals_the_unfused_chain(nets, cuda_device, monkeypatch):
+    """One graph launch per step (TrajNet forward + in-kernel-noise update, rohm_trajnet_sample_step) == forward,
+    torch.randn_like, update as separate launches: bit for bit, vanilla and TrajControl, for an un-respaced and a respaced
+    schedule, through p_sample_loop and through eval_losses' cond_fn_with_grad route; torch's generator ends in the same state."""
+    gen = torch.cuda.default_generators[cuda_device.index]
+    a = argparse.Namespace(noise_schedule='cosine', sigma_small=True)
+    for control in (False, True):
+        m, _ = nets[control]
+        B, T = 3, 144
+        batch = {k: v.to(cuda_device) for k, v in synthetic.trajnet_batch(B, T, 9, control=control).items()}
+        for steps, resp in ((1000, 'ddim6'), (6, '')):
+            d = diffusion.create_gaussian_diffusion(a, diffusion, diffusion.SpacedDiffusionTrajNet, steps, resp, cuda_device)
+            for with_grad in (False, True):
+                outs, offs = [], []
+                for fused in (True, False):
+                    monkeypatch.setattr(diffusion, "_FUSED_STEP", fused)
+                    torch.manual_seed(77)
+                    outs.append(d.p_sample_loop(m, dict(batch), [B, T, 13], clip_denoised=False, cond_fn_with_grad=with_grad))
+                    offs.append(gen.get_offset())
+                assert torch.equal(outs[0], outs[1]) and offs[0] == offs[1], (control, steps, resp, with_grad)
+                assert bool(torch.isfinite(outs[0]).all())
