@@ -120,3 +120,52 @@ def test_branch_free_erf_gelu_constants_match_float64():
     ref = 0.5 * x64 * (1.0 + erf(x64 / math.sqrt(2.0)))
     assert np.abs(gelu - ref).max() < 3e-7  # tools/fit_gelu_erf.py reports 2.5e-7 (fp32 erff formulation: 4.5e-7)
     assert gelu[x > 8.0].tolist() == x64[x > 8.0].tolist() and np.all(np.abs(gelu[x < -8.0]) < 3e-8)  # saturation
+
+
+def test_split_k_partials_added_in_order_stay_fp32_grade():
+    """TrajNet's deep-level convolutions (trajnet.cu: pick_split, gemm.cu: GemmParams::k_splits): the K extent is cut into S
+    contiguous ranges, every range is accumulated on its own (two accumulators, as above), stored as an fp32 partial and the
+    consumer adds bias + partials in split order.  S more fp32 roundings per output: the result stays in the error class of the
+    single-pass product, and the order is fixed, so it is deterministic."""
+    rng = np.random.default_rng(5)
+    for K, S in ((5120, 6), (2560, 3), (1280, 5)):
+        a = rng.standard_normal((40, K)).astype(f32)
+        w = (rng.standard_normal((64, K)) / math.sqrt(K)).astype(f32)
+        bias = rng.standard_normal(64).astype(f32)
+        ref = a.astype(f64) @ w.astype(f64).T + bias.astype(f64)
+        s = weight_scale(w)
+        per = -(-(K // 64) // S) * 64  # ranges of whole 64-column K blocks, ceil(blocks / S) each, the last one shorter
+        assert (S - 1) * per < K         # launch_cfg's requirement: no empty range
+        acc = bias.astype(f32)[None, :].repeat(40, axis=0)
+        for sp in range(S):
+            k0, k1 = sp * per, min(K, (sp + 1) * per)
+            # one weight scale per matrix (not per range), as the kernel packs it
+            ah, al = split_f16(a[:, k0:k1])
+            wh, wl = split_f16((w[:, k0:k1] * f32(s)).astype(f32))
+            main = (ah.astype(f64) @ wh.astype(f64).T).astype(f32)
+            cross = (al.astype(f64) @ wh.astype(f64).T + ah.astype(f64) @ wl.astype(f64).T).astype(f32)
+            part = ((main + cross) * f32(1.0 / s)).astype(f32)
+            acc = (acc + part).astype(f32)
+        single = (gemm_f16x2(a, w) + bias).astype(f32)
+        bound = np.abs(a.astype(f64)) @ np.abs(w.astype(f64)).T + np.abs(bias.astype(f64))
+        assert (np.abs(acc.astype(f64) - ref) / (2.0 ** -20 * bound)).max() < 1.0
+        assert np.abs(acc.astype(f64) - ref).max() <= 4.0 * max(np.abs(single.astype(f64) - ref).max(), 1e-7)
+
+
+def test_group_statistics_taken_in_the_groupnorm_kernel():
+    """gn_mish_split_kernel: per (clip, group) sum and sum of squares of the fp32 values accumulated in double, mean and
+    E[x^2] - mean^2 formed in double, mu / rstd cast to fp32 -- against GroupNorm in float64 (torch.nn.GroupNorm(8, C), eps 1e-5)
+    for the group shapes of the five pyramid levels, including a large common offset (cancellation in E[x^2] - mean^2)."""
+    rng = np.random.default_rng(6)
+    for T, gs, offset in ((144, 8, 0.0), (72, 16, 3.0), (36, 32, -50.0), (18, 64, 400.0), (9, 64, 0.0), (144, 4, 1e3)):
+        y = (rng.standard_normal((T, gs)) * 2.0 + offset).astype(f32)
+        s1 = y.astype(f64).sum()
+        s2 = (y.astype(f64) * y.astype(f64)).sum()
+        n = float(T * gs)
+        mean = s1 / n
+        var = max(s2 / n - mean * mean, 0.0)
+        mu, rstd = f32(mean), f32(1.0 / math.sqrt(var + 1e-5))
+        got = ((y - mu) * rstd).astype(f64)
+        y64 = y.astype(f64)
+        ref = (y64 - y64.mean()) / np.sqrt(y64.var() + 1e-5)
+        assert np.abs(got - ref).max() < 2e-6 * max(1.0, abs(offset) / 2.0)
