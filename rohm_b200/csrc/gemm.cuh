@@ -13,7 +13,11 @@
 // * PASSES == 3: D += A_lo*W_hi + A_hi*W_lo + A_hi*W_hi  (drops only the lo*lo term, ~2^-22 relative).
 //   PASSES == 1: D += A_hi*W_hi (plain TF32, ~2^-11 relative) -- the documented fast mode.
 //
-// Kernel shape: persistent, grid = min(#tiles, #SMs), 128 x BLOCK_N output tiles, 320 threads per CTA:
+// * Split-K (GemmParams::k_splits, masked / GroupNorm variant): a work item is a (tile, K range) pair; partial tiles are plain
+//   fp32 stores at a per-split row offset and the consumer kernel adds them in split order (TrajNet's deep pyramid levels, where
+//   6-22 row tiles with 40-80 K blocks each would otherwise leave most SMs idle or force 32-wide tiles).
+//
+// Kernel shape: persistent, grid = min(#work items, #SMs), 128 x BLOCK_N output tiles, 320 threads per CTA:
 //   warp 0   : TMA producer (one elected lane)        smem ring of 64 KB stages: full[]/empty[] mbarriers
 //   warp 1   : TMEM allocator + tcgen05.mma issuer    two accumulator stages in TMEM (tmem_full[]/tmem_empty[])
 //   warps 2-9: epilogue (tcgen05.ld -> scale / bias / activation / row mask / GroupNorm sums -> swizzled smem tile ->

@@ -8,9 +8,12 @@
 //   * Downsample (k3, stride 2) = the same with a row-stride-2 TMA descriptor,
 //   * ConvTranspose (k4, s2)    = two GEMMs (even / odd output frames), 2 taps each, row-interleaved stores,
 // so every convolution is one launch of the tcgen05 segmented-A GEMM (gemm.cu) and no im2col / concat / transpose
-// buffer exists.  GroupNorm statistics are accumulated by the GEMM epilogue; one fused elementwise kernel applies
-// GroupNorm + Mish (+ time projection, + residual, + TrajControl residual) and emits the TF32 hi/lo operands of the
-// next convolution.  The step-invariant condition pyramid and control_zero_conv_0 run once per condition (set_cond).
+// buffer exists.  The convolutions of the deep pyramid levels are cut along K into 3-6 ranges (pick_split: 128-wide tiles x K
+// ranges cover the 148 SMs where 6-22 row tiles alone cannot); one kernel per GroupNorm'd convolution (gn_mish_split_kernel, a
+// CTA per (clip, group)) adds bias + the fp32 partial(s) in split order, takes the group's statistics, applies GroupNorm + Mish
+// (+ time projection, + residual, + TrajControl residual) and emits the hi/lo operand pair of the next convolution.  The
+// step-invariant condition pyramid and control_zero_conv_0 run once per condition (set_cond).  rohm_trajnet_sample_step appends
+// the in-kernel-noise sampler update to the forward graph.
 #include <cmath>
 #include <map>
 #include <new>
