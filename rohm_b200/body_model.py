@@ -251,7 +251,8 @@ class BodyModel(nn.Module):
     def forward(self, transl=None, global_orient=None, body_pose=None, betas=None, return_verts=True, **zeros):
         """Call-compatible with ``smplx_model(**smplx_params_dict)`` as RoHM uses it
         (motion_representation.py:379-389): jaw / eye / hand poses and expression are accepted and must be zero.
-        Returns an object with ``.joints`` [N, 55, 3] and ``.vertices`` [N, V, 3]."""
+        Returns an object with ``.joints`` [N, 55, 3] and ``.vertices`` [N, V, 3] (a strided view of a 16-byte-pitched buffer
+        when the fused launch stores through TMA: same values and shape, ``.contiguous()`` gives smplx's dense layout)."""
         dev = self.v_template.device
         if dev.type != "cuda":
             raise RohmB200Error("BodyModel: the model must live on a CUDA device (no CPU path)")
